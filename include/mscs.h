@@ -1,0 +1,172 @@
+/*
+ * mscs.h -- C ABI of libmscs.so: the B200 (sm_100a) implementation of the multi-scale and
+ * cross-scale dense supervised contrastive loss.
+ *
+ * The reference has no FFI: the loss is plain Python/ATen, dispatched by class name from
+ * losses/LossWrapper.py:33,68-71.  This header is the boundary a binding would use; the
+ * Python host side (mscs_b200/losses.py, _ops.py) mirrors the reference classes on top of it
+ * through ctypes.  Every entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing blocks
+ *     except mscs_plan_fetch (one small D2H + stream synchronise);
+ *   - every function returns 0 on success, <0 for an invalid argument, >0 for a cudaError_t;
+ *     mscs_last_error() returns a thread-local message for the last failure;
+ *   - memory is owned by the caller (the host side allocates workspaces with the sizes
+ *     mscs_*_bytes report); the library keeps no global mutable state.
+ */
+#ifndef MSCS_H_
+#define MSCS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSCS_MAX_SCALES 8
+#define MSCS_MAX_TERMS 16   /* single-scale terms + cross-scale terms */
+#define MSCS_MAX_PASSES 32  /* backward passes: 1 per ms term, up to 2 per cs term */
+
+/* library info ------------------------------------------------------------------------- */
+const char* mscs_version(void);
+const char* mscs_last_error(void);
+/* 1 if a CUDA device with compute capability 10.x is present */
+int mscs_device_ok(void);
+
+/* ---------------------------------------------------------------------------------------
+ * K1 -- sampling.  Replaces get_dist_and_classes (DenseContrastiveLossV2.py:194-206),
+ * sample_anchors_fast (:86-125) and _select_views_per_class (:64-84) for ALL scales of one
+ * call in one go.  Bit-exact with the reference given the MT19937 state of the torch CPU
+ * default generator at the time of the call.
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n, H, W;               /* label map (n,H,W) int64                                */
+  int32_t num_scales;
+  int32_t fh[MSCS_MAX_SCALES];   /* feature map height / width per scale                   */
+  int32_t fw[MSCS_MAX_SCALES];
+  int32_t num_classes;           /* A = num_all_classes (V2.py:16); last column is dropped  */
+  int32_t min_views;             /* min_views_per_class (V2.py:21)                         */
+  int32_t max_views;             /* max_views_per_class (V2.py:27); 1 = no cap (V2.py:65)  */
+  int32_t max_total;             /* max_features_total (V2.py:28)                          */
+} mscs_sample_cfg;
+
+/* per-scale result header, written by the plan kernel, fetched by mscs_plan_fetch */
+typedef struct {
+  int32_t T;          /* kept (image,class) pairs                       (V2.py:111) */
+  int32_t V;          /* views per pair                                  (V2.py:64-84) */
+  int32_t N;          /* T*V anchors                                                 */
+  int32_t min_count;  /* min pixel count over kept pairs                 (V2.py:110) */
+  int32_t log_flag;   /* log_this_step as the reference sets it          (V2.py:75,83) */
+  int32_t dl_h, dl_w; /* down-sampled label size (H//s, W//s), s = W//fw (V2.py:46,205) */
+  int32_t error;      /* 0 ok, 1 = no pair kept, 2 = a kept pair has a single pixel  */
+  int64_t draw_base;  /* offset of this scale's first draw in the MT19937 stream     */
+  int64_t draws;      /* sum over kept pairs of (count-1)                            */
+} mscs_scale_plan;
+
+/* bytes of device workspace K1 needs for this configuration (labels, histograms, plan) */
+size_t mscs_sample_workspace_bytes(const mscs_sample_cfg* cfg);
+/* upper bound of MT19937 draws one call can consume (sizes the stream buffer, uint32 each) */
+size_t mscs_sample_max_draws(const mscs_sample_cfg* cfg);
+
+/* Phase 1 (async): down-sample, histogram, plan.  `plan_dev` receives num_scales
+ * mscs_scale_plan records. */
+int mscs_sample_plan(const mscs_sample_cfg* cfg, const int64_t* labels, void* workspace,
+                     mscs_scale_plan* plan_dev, void* stream);
+/* D2H of the plan records + stream synchronise (the one host sync of the forward pass;
+ * the reference has ~1000). */
+int mscs_plan_fetch(const mscs_scale_plan* plan_dev, mscs_scale_plan* plan_host, int num_scales,
+                    void* stream);
+/* Phase 2 (async): MT19937 stream + per-pair Fisher-Yates prefix + rank->pixel selection.
+ *   mt_state_host : 624 words + position (0..624) of the torch CPU generator (host memory);
+ *   draws_dev     : scratch, >= total draws uint32;
+ * outputs per scale s (arrays of N_s entries, N_s from the fetched plan):
+ *   idx_ref[s]  : flat pixel index y*w+x in REFERENCE order k*V+v            (V2.py:122)
+ *   pair_ref[s] : (T,2) int32 (image, class) in reference order              (V2.py:106-107)
+ *   pix[s]      : image*dl_h*dl_w + y*w+x, rows sorted by class (kernel order)
+ *   cls[s]      : class id of each sorted row
+ *   seg[s]      : A+1 int32, seg[c] = first sorted row of class c, seg[A] = N
+ */
+int mscs_sample_select(const mscs_sample_cfg* cfg, const mscs_scale_plan* plan_host,
+                       const uint32_t* mt_state_host, int mt_pos, void* workspace,
+                       uint32_t* draws_dev, int32_t* const* idx_ref, int32_t* const* pair_ref,
+                       int32_t* const* pix, int32_t* const* cls, int32_t* const* seg, void* stream);
+/* host helper: advance an MT19937 state by k draws exactly as at::mt19937 does */
+int mscs_mt19937_advance_host(uint32_t* mt_state_host, int* mt_pos, uint64_t k);
+
+/* ---------------------------------------------------------------------------------------
+ * K2 -- gather + L2 normalise.  Replaces the strided gather features[b,:,idx] (V2.py:123)
+ * and F.normalize(p=2, dim=1) (V2.py:138, _ms.py:95,104).
+ *   feat : fp32 NCHW (n,C,fh,fw) contiguous;  pix/N from K1
+ *   anc_bf16 : (N_pad, C_pad) bf16 row-major, C_pad = C rounded up to 64, N_pad = N rounded
+ *              up to 256; padding is written as zeros   (operand of the similarity kernels)
+ *   anc_f32  : (N, C) fp32 unit rows (used by the normalisation backward)
+ *   inv_norm : (N) 1/max(||x||, 1e-12)
+ * ------------------------------------------------------------------------------------- */
+int mscs_gather_normalize(const float* feat, int n, int C, int plane, const int32_t* pix, int N,
+                          void* anc_bf16, float* anc_f32, float* inv_norm, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K3 / K4 -- fused similarity + loss forward and backward for every term of one call.
+ * Replaces contrastive_loss/get_masks2/get_loss (V2.py:127-192), the cross-scale
+ * contrastive_loss/InfoNce_loss (_ms.py:84-161), the weighted combination (_ms.py:51-80)
+ * and the autograd backward of all of it.  The N x N logits are never materialised.
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  /* anchors (rows) and keys (columns); for a single-scale term they are the same set */
+  const void* a_bf16; const void* k_bf16;   /* (N_pad, C_pad) bf16                     */
+  const int32_t* a_cls; const int32_t* k_seg; /* row classes; key class segments (A+1)  */
+  const int32_t* k_cls; const int32_t* a_seg; /* used by the key-side backward pass      */
+  int32_t N1, N2;
+  int32_t self_mask;      /* 1: single-scale term (V2.py:164-170), 0: cross-scale (_ms.py:128) */
+  int32_t need_dk;        /* 0 when the key side is detached (_ms.py:66-67) or self_mask */
+  float temperature;
+  float weight;           /* weights[s] / w_high_low / w_high_mid  (_ms.py:54,72,79)     */
+  int32_t a_set, k_set;   /* which anchor set (scale) rows/cols belong to: grads accumulate per set */
+  /* per-anchor statistics, N1 floats each, zero-initialised by the caller */
+  float* neg_sum;   /* sum_k neg exp(l_ik)                          (V2.py:183-184) */
+  float* pos_sum;   /* sum_j pos [l_ij - log(e^l_ij + neg_i)]       (V2.py:186-187) */
+  float* s_sum;     /* sum_j pos 1/(e^l_ij + neg_i)     (backward) */
+  float* coef_s;    /* out: S_i/(div_i N1)  */
+  float* coef_pn;   /* out: neg_i/(div_i N1) */
+} mscs_term;
+
+typedef struct {
+  int32_t num_terms;
+  int32_t C_pad;
+  int32_t num_classes;
+  mscs_term terms[MSCS_MAX_TERMS];
+  float* term_loss;   /* out: num_terms floats, unweighted per-term losses (ms_losses/cs_losses) */
+  float* total_loss;  /* out: 1 float = sum_t weight_t * term_loss_t                  */
+  void* work;         /* scratch, mscs_sim_workspace_bytes() */
+} mscs_sim_job;
+
+size_t mscs_sim_workspace_bytes(const mscs_sim_job* job);
+/* forward: negative sweep, positive sweep, finalise (loss + backward coefficients) */
+int mscs_sim_forward(const mscs_sim_job* job, void* stream);
+/* backward: dF[set] (N_set, C) fp32 += d total_loss / d unit rows * (*grad_out), for every
+ * set; the caller zero-initialises dF.  grad_out is a device scalar (upstream gradient). */
+int mscs_sim_backward(const mscs_sim_job* job, const float* grad_out, float* const* dF_sets,
+                      const int32_t* dF_ld, void* stream);
+/* plain CUDA-core fp32 versions of the two calls above: validation kernels for the tests,
+ * never used by the product path */
+int mscs_debug_sim_forward_simt(const mscs_sim_job* job, const float* const* f32_sets, void* stream);
+int mscs_debug_sim_backward_simt(const mscs_sim_job* job, const float* const* f32_sets,
+                                 const float* grad_out, float* const* dF_sets, const int32_t* dF_ld,
+                                 void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Scatter -- normalisation backward + dense gradient.  Replaces the autograd backward of
+ * F.normalize and of the CopySlices/index gather (V2.py:123,138): writes the full dense
+ * (n,C,fh,fw) gradient: zeros everywhere except the sampled pixels.
+ * ------------------------------------------------------------------------------------- */
+int mscs_scatter_grad(const float* dF, int ldF, const float* anc_f32, const float* inv_norm,
+                      const int32_t* pix, int N, int n, int C, int plane, float* dfeat,
+                      int zero_fill, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSCS_H_ */
