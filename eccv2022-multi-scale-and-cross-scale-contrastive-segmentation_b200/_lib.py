@@ -1,0 +1,91 @@
+"""ctypes binding of libmscs.so (include/mscs.h).  No fallback: if the library is missing or a
+call fails, a RuntimeError is raised -- there is no CPU or PyTorch path behind this module."""
+import ctypes as C
+import os
+
+MAX_SCALES, MAX_TERMS = 8, 16
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmscs.so")
+
+
+class SampleCfg(C.Structure):
+    _fields_ = [("n", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("num_scales", C.c_int32),
+                ("fh", C.c_int32 * MAX_SCALES), ("fw", C.c_int32 * MAX_SCALES),
+                ("num_classes", C.c_int32), ("min_views", C.c_int32), ("max_views", C.c_int32),
+                ("max_total", C.c_int32)]
+
+
+class ScalePlan(C.Structure):
+    _fields_ = [("T", C.c_int32), ("V", C.c_int32), ("N", C.c_int32), ("min_count", C.c_int32),
+                ("log_flag", C.c_int32), ("dl_h", C.c_int32), ("dl_w", C.c_int32), ("error", C.c_int32),
+                ("draw_base", C.c_int64), ("draws", C.c_int64)]
+
+
+class Term(C.Structure):
+    _fields_ = [("a_bf16", C.c_void_p), ("k_bf16", C.c_void_p),
+                ("a_cls", C.c_void_p), ("k_seg", C.c_void_p), ("k_cls", C.c_void_p), ("a_seg", C.c_void_p),
+                ("N1", C.c_int32), ("N2", C.c_int32), ("self_mask", C.c_int32), ("need_dk", C.c_int32),
+                ("temperature", C.c_float), ("weight", C.c_float), ("a_set", C.c_int32), ("k_set", C.c_int32),
+                ("neg_sum", C.c_void_p), ("pos_sum", C.c_void_p), ("s_sum", C.c_void_p),
+                ("coef_s", C.c_void_p), ("coef_pn", C.c_void_p)]
+
+
+class SimJob(C.Structure):
+    _fields_ = [("num_terms", C.c_int32), ("C_pad", C.c_int32), ("num_classes", C.c_int32),
+                ("terms", Term * MAX_TERMS), ("term_loss", C.c_void_p), ("total_loss", C.c_void_p),
+                ("work", C.c_void_p)]
+
+
+_PTRS = C.POINTER(C.c_void_p)
+_SIGNATURES = {
+    "mscs_version": (C.c_char_p, []),
+    "mscs_last_error": (C.c_char_p, []),
+    "mscs_device_ok": (C.c_int, []),
+    "mscs_sample_workspace_bytes": (C.c_size_t, [C.POINTER(SampleCfg)]),
+    "mscs_sample_max_draws": (C.c_size_t, [C.POINTER(SampleCfg)]),
+    "mscs_sample_plan": (C.c_int, [C.POINTER(SampleCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mscs_plan_fetch": (C.c_int, [C.c_void_p, C.POINTER(ScalePlan), C.c_int, C.c_void_p]),
+    "mscs_sample_select": (C.c_int, [C.POINTER(SampleCfg), C.POINTER(ScalePlan), C.c_void_p, C.c_int, C.c_void_p,
+                                     C.c_void_p, _PTRS, _PTRS, _PTRS, _PTRS, _PTRS, C.c_void_p]),
+    "mscs_mt19937_advance_host": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_uint64]),
+    "mscs_gather_normalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mscs_sim_workspace_bytes": (C.c_size_t, [C.POINTER(SimJob)]),
+    "mscs_sim_forward": (C.c_int, [C.POINTER(SimJob), C.c_void_p]),
+    "mscs_sim_backward": (C.c_int, [C.POINTER(SimJob), C.c_void_p, _PTRS, C.POINTER(C.c_int32), C.c_void_p]),
+    "mscs_debug_sim_forward_simt": (C.c_int, [C.POINTER(SimJob), _PTRS, C.c_void_p]),
+    "mscs_debug_sim_backward_simt": (C.c_int, [C.POINTER(SimJob), _PTRS, C.c_void_p, _PTRS, C.POINTER(C.c_int32),
+                                               C.c_void_p]),
+    "mscs_scatter_grad": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                    C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+}
+EXPORTS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load():
+    """Load libmscs.so (once).  Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+                               f"g.build()'` (or `make -C {os.path.join(_HERE, 'csrc')}`). There is no fallback path.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().mscs_last_error().decode()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr_array(ptrs):
+    arr = (C.c_void_p * len(ptrs))(*ptrs)
+    return arr

@@ -1,0 +1,312 @@
+"""Host orchestration of the CUDA path and the single ``torch.autograd.Function`` on top of it.
+
+PyTorch is plumbing here (device memory from the caching allocator, the current stream, autograd
+bookkeeping); every computation between "labels + feature maps in" and "scalar loss / dense
+feature gradients out" is a libmscs.so kernel.  Nothing in this module computes on the CPU and
+there is no fallback: a missing library or a non-sm_100 device raises.
+"""
+import ctypes as C
+import struct
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_MT_N = 624
+
+
+@dataclass
+class LossSpec:
+    """Flat, resolved loss configuration (see losses.py for the reference key rules)."""
+    num_classes: int
+    temperature: float
+    cs_temperature: float
+    min_views: int = 5
+    max_views: int = 2500
+    max_total: int = 10000
+    weights: List[float] = field(default_factory=lambda: [1.0])
+    cross_scale: bool = False
+    detach_deepest: bool = False
+    w_high_low: float = 1.0
+    w_high_mid: float = 1.0
+
+
+@dataclass
+class ScaleSample:
+    """Sampling result of one scale (device tensors unless noted)."""
+    T: int
+    V: int
+    N: int
+    log_flag: bool
+    dl_h: int
+    dl_w: int
+    idx_ref: torch.Tensor    # (T, V) int32 flat pixel index in REFERENCE order (V2.py:122)
+    pair_ref: torch.Tensor   # (T, 2) int32 (image, class) in reference order (V2.py:106-107)
+    pix: torch.Tensor        # (N,) int32 image*plane + pixel, rows sorted by class
+    cls: torch.Tensor        # (N,) int32 class of each sorted row
+    seg: torch.Tensor        # (A+1,) int32 class segments of the sorted rows
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_device(t):
+    if not t.is_cuda:
+        raise RuntimeError("mscs_b200 runs on a B200 GPU only: got a CPU tensor (there is no CPU fallback)")
+
+
+# ---- torch CPU generator <-> MT19937 state ----------------------------------------------------
+def torch_mt_state():
+    """(state uint32[624], pos) of the torch CPU default generator (at::mt19937 layout:
+    [seed u64][left i32][seeded i32][next u64][624 x u64] ...)."""
+    raw = torch.get_rng_state().numpy()
+    _seed, left, _seeded, nxt = struct.unpack_from("<QiiQ", raw.tobytes()[:24], 0)
+    mt = np.ascontiguousarray(raw[24:24 + 8 * _MT_N].view(np.uint64).astype(np.uint32))
+    pos = _MT_N if left == 1 else int(nxt)
+    return mt, pos
+
+
+def torch_mt_advance(mt, pos, draws):
+    """Advance the torch CPU default generator by ``draws`` 32-bit outputs -- what the reference's
+    per-pair ``torch.randperm`` calls would have consumed (V2.py:121)."""
+    if draws <= 0:
+        return
+    lib = _lib.load()
+    cpos = C.c_int(pos)
+    _lib.check(lib.mscs_mt19937_advance_host(mt.ctypes.data_as(C.c_void_p), C.byref(cpos), C.c_uint64(draws)),
+               "mscs_mt19937_advance_host")
+    raw = torch.get_rng_state().numpy().copy()
+    hdr = struct.pack("<ii", 625 - cpos.value, 1)
+    raw[8:16] = np.frombuffer(hdr, dtype=np.uint8)
+    raw[16:24] = np.frombuffer(struct.pack("<Q", cpos.value), dtype=np.uint8)
+    raw[24:24 + 8 * _MT_N] = mt.astype(np.uint64).view(np.uint8)
+    torch.set_rng_state(torch.from_numpy(raw))
+
+
+# ---- K1 -----------------------------------------------------------------------------------
+def sample_anchors(labels, feat_hw, spec, mt_state=None):
+    """All scales of one call.  ``feat_hw``: [(h, w)] per scale.  ``mt_state``: None = consume the
+    torch CPU default generator exactly as the reference does, or an explicit (uint32[624], pos)."""
+    lib = _lib.load()
+    _require_device(labels)
+    if labels.dtype != torch.int64:
+        labels = labels.long()
+    labels = labels.contiguous()
+    n, H, W = labels.shape
+    S = len(feat_hw)
+    cfg = _lib.SampleCfg()
+    cfg.n, cfg.H, cfg.W, cfg.num_scales = n, H, W, S
+    for s, (h, w) in enumerate(feat_hw):
+        cfg.fh[s], cfg.fw[s] = h, w
+    cfg.num_classes, cfg.min_views = spec.num_classes, spec.min_views
+    cfg.max_views, cfg.max_total = spec.max_views, spec.max_total
+    dev = labels.device
+    ws_bytes = lib.mscs_sample_workspace_bytes(C.byref(cfg))
+    if ws_bytes == 0:
+        raise RuntimeError("mscs_sample_workspace_bytes: " + lib.mscs_last_error().decode())
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    plan_dev = torch.empty(S * C.sizeof(_lib.ScalePlan), dtype=torch.uint8, device=dev)
+    st = _stream()
+    _lib.check(lib.mscs_sample_plan(C.byref(cfg), labels.data_ptr(), ws.data_ptr(), plan_dev.data_ptr(), st),
+               "mscs_sample_plan")
+    plan = (_lib.ScalePlan * S)()
+    _lib.check(lib.mscs_plan_fetch(plan_dev.data_ptr(), plan, S, st), "mscs_plan_fetch")
+    for s in range(S):
+        if plan[s].error == 1:   # reference: torch.min() of an empty tensor raises (V2.py:110)
+            raise RuntimeError(f"scale {s}: no (image, class) pair has >= min_views_per_class="
+                               f"{spec.min_views} pixels (the reference raises here too, V2.py:110)")
+        if plan[s].error == 2:   # reference: 0-d squeeze then .shape[0] raises (V2.py:119-121)
+            raise IndexError(f"scale {s}: a kept class has a single pixel (the reference raises here too)")
+    total = sum(int(plan[s].draws) for s in range(S))
+    own_rng = mt_state is None
+    mt, pos = torch_mt_state() if own_rng else (np.ascontiguousarray(mt_state[0], dtype=np.uint32), int(mt_state[1]))
+    draws = torch.empty(total + 64 + 1024, dtype=torch.int32, device=dev)
+    A = spec.num_classes
+    # one int32 slab for every per-scale index array
+    sizes = []
+    for s in range(S):
+        N, T = plan[s].N, plan[s].T
+        sizes += [N, 2 * T, N, N, A + 1]
+    slab = torch.empty(sum((x + 15) // 16 * 16 for x in sizes), dtype=torch.int32, device=dev)
+    views, off = [], 0
+    for x in sizes:
+        views.append(slab[off:off + x])
+        off += (x + 15) // 16 * 16
+    out = []
+    arrs = [[], [], [], [], []]
+    for s in range(S):
+        v = views[5 * s:5 * s + 5]
+        for k in range(5):
+            arrs[k].append(v[k].data_ptr())
+        out.append(ScaleSample(T=plan[s].T, V=plan[s].V, N=plan[s].N, log_flag=bool(plan[s].log_flag),
+                               dl_h=plan[s].dl_h, dl_w=plan[s].dl_w,
+                               idx_ref=v[0].view(plan[s].T, plan[s].V), pair_ref=v[1].view(plan[s].T, 2),
+                               pix=v[2], cls=v[3], seg=v[4]))
+    _lib.check(lib.mscs_sample_select(C.byref(cfg), plan, mt.ctypes.data_as(C.c_void_p), pos, ws.data_ptr(),
+                                      draws.data_ptr(), *[_lib.ptr_array(a) for a in arrs], st),
+               "mscs_sample_select")
+    if own_rng:
+        torch_mt_advance(mt, pos, total)
+    return out
+
+
+# ---- K2 -----------------------------------------------------------------------------------
+@dataclass
+class AnchorSet:
+    N: int
+    C: int
+    C_pad: int
+    bf16: torch.Tensor       # (N_pad, C_pad) bf16 unit rows (zero padded)
+    f32: torch.Tensor        # (N, C) fp32 unit rows
+    inv_norm: torch.Tensor   # (N,)
+
+
+def gather_normalize(feat, sample):
+    lib = _lib.load()
+    n, Cc, h, w = feat.shape
+    N = sample.N
+    C_pad, N_pad = (Cc + 63) // 64 * 64, (N + 255) // 256 * 256
+    dev = feat.device
+    bf = torch.empty((N_pad, C_pad), dtype=torch.bfloat16, device=dev)
+    f32 = torch.empty((N, Cc), dtype=torch.float32, device=dev)
+    inv = torch.empty((N,), dtype=torch.float32, device=dev)
+    _lib.check(lib.mscs_gather_normalize(feat.data_ptr(), n, Cc, h * w, sample.pix.data_ptr(), N, bf.data_ptr(),
+                                         f32.data_ptr(), inv.data_ptr(), _stream()), "mscs_gather_normalize")
+    return AnchorSet(N=N, C=Cc, C_pad=C_pad, bf16=bf, f32=f32, inv_norm=inv)
+
+
+# ---- K3 / K4 ------------------------------------------------------------------------------
+@dataclass
+class SimState:
+    job: _lib.SimJob
+    keep: list                      # tensors the job points into
+    term_loss: torch.Tensor
+    total: torch.Tensor
+    num_ms: int
+    cs_logged: List[int]            # indices (into term_loss) of the cs terms that go to cs_losses
+
+
+def build_job(spec, samples, sets, single_scale):
+    """Terms of one call: one single-scale term per scale (V2.py:55 via _ms.py:53-59) and, when
+    cross_scale_contrast, scale 0 against the deepest and second-deepest scales (_ms.py:62-80)."""
+    S = len(sets)
+    terms = [(s, s, True, spec.weights[s], spec.temperature, False) for s in range(S)]
+    cs_logged = []
+    if spec.cross_scale and not single_scale:
+        assert S > 1, "cross_scale_contrast needs at least two scales (_ms.py:63-64)"
+        need_dk = not spec.detach_deepest
+        terms.append((0, S - 1, False, spec.w_high_low, spec.cs_temperature, need_dk))
+        if not spec.detach_deepest:          # _ms.py:66-70: not logged when the deepest scale is detached
+            cs_logged.append(len(terms) - 1)
+        if S > 2:
+            terms.append((0, S - 2, False, spec.w_high_mid, spec.cs_temperature, need_dk))
+            cs_logged.append(len(terms) - 1)
+    if len(terms) > _lib.MAX_TERMS:
+        raise ValueError(f"{len(terms)} loss terms exceed the supported {_lib.MAX_TERMS}")
+    dev = sets[0].bf16.device
+    n_rows = [sets[a].N for a, *_ in terms]
+    stats = torch.zeros(3 * sum(n_rows), dtype=torch.float32, device=dev)
+    coefs = torch.empty(2 * sum(n_rows), dtype=torch.float32, device=dev)
+    out = torch.empty(len(terms) + 1, dtype=torch.float32, device=dev)
+    job = _lib.SimJob()
+    job.num_terms, job.C_pad, job.num_classes = len(terms), sets[0].C_pad, spec.num_classes
+    so = co = 0
+    for i, (a, k, self_mask, weight, tau, need_dk) in enumerate(terms):
+        t = job.terms[i]
+        t.a_bf16, t.k_bf16 = sets[a].bf16.data_ptr(), sets[k].bf16.data_ptr()
+        t.a_cls, t.k_seg = samples[a].cls.data_ptr(), samples[k].seg.data_ptr()
+        t.k_cls, t.a_seg = samples[k].cls.data_ptr(), samples[a].seg.data_ptr()
+        t.N1, t.N2, t.self_mask, t.need_dk = sets[a].N, sets[k].N, int(self_mask), int(need_dk)
+        t.temperature, t.weight, t.a_set, t.k_set = tau, weight, a, k
+        n1 = sets[a].N
+        t.neg_sum = stats[so:so + n1].data_ptr()
+        t.pos_sum = stats[so + n1:so + 2 * n1].data_ptr()
+        t.s_sum = stats[so + 2 * n1:so + 3 * n1].data_ptr()
+        t.coef_s = coefs[co:co + n1].data_ptr()
+        t.coef_pn = coefs[co + n1:co + 2 * n1].data_ptr()
+        so += 3 * n1
+        co += 2 * n1
+    job.term_loss, job.total_loss = out.data_ptr(), out[len(terms):].data_ptr()
+    work = torch.empty(_lib.load().mscs_sim_workspace_bytes(C.byref(job)), dtype=torch.uint8, device=dev)
+    job.work = work.data_ptr()
+    return SimState(job=job, keep=[stats, coefs, out, work], term_loss=out[:len(terms)], total=out[len(terms)],
+                    num_ms=S, cs_logged=cs_logged)
+
+
+def sim_forward(state):
+    _lib.check(_lib.load().mscs_sim_forward(C.byref(state.job), _stream()), "mscs_sim_forward")
+
+
+def sim_backward(state, sets, grad_out):
+    lib = _lib.load()
+    dev = sets[0].bf16.device
+    dFs = [torch.zeros((a.N, a.C_pad), dtype=torch.float32, device=dev) for a in sets]
+    ptrs = [0] * _lib.MAX_SCALES
+    lds = (C.c_int32 * _lib.MAX_SCALES)()
+    for s, d in enumerate(dFs):
+        ptrs[s], lds[s] = d.data_ptr(), d.shape[1]
+    g = grad_out.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+    _lib.check(lib.mscs_sim_backward(C.byref(state.job), g.data_ptr(), _lib.ptr_array(ptrs), lds, _stream()),
+               "mscs_sim_backward")
+    return dFs
+
+
+def scatter_grad(dF, aset, sample, feat_shape, dtype):
+    lib = _lib.load()
+    n, Cc, h, w = feat_shape
+    out = torch.empty(feat_shape, dtype=torch.float32, device=dF.device)
+    _lib.check(lib.mscs_scatter_grad(dF.data_ptr(), dF.shape[1], aset.f32.data_ptr(), aset.inv_norm.data_ptr(),
+                                     sample.pix.data_ptr(), aset.N, n, Cc, h * w, out.data_ptr(), 1, _stream()),
+               "mscs_scatter_grad")
+    return out if dtype == torch.float32 else out.to(dtype)
+
+
+# ---- the autograd.Function ----------------------------------------------------------------
+class MsCsContrastiveFn(torch.autograd.Function):
+    """(labels, spec, single_scale, holder, *features) -> (total_loss 0-d, term_losses (n_terms,)).
+
+    ``holder`` (a dict) receives the sampling results and term bookkeeping for the caller
+    (log_this_step, ms/cs split, reference-order indices)."""
+
+    @staticmethod
+    def forward(ctx, labels, spec, single_scale, holder, *feats):
+        if not _lib.load().mscs_device_ok():
+            raise RuntimeError("mscs_b200 needs a compute-capability 10.x (B200) device; no fallback exists")
+        feats32 = []
+        for f in feats:
+            _require_device(f)
+            f32 = f.detach()
+            if f32.dtype != torch.float32:
+                f32 = f32.float()
+            feats32.append(f32.contiguous())
+        if labels.device != feats32[0].device:
+            labels = labels.to(feats32[0].device)
+        with torch.cuda.device(feats32[0].device):
+            samples = sample_anchors(labels, [tuple(f.shape[-2:]) for f in feats32], spec)
+            sets = [gather_normalize(f, s) for f, s in zip(feats32, samples)]
+            state = build_job(spec, samples, sets, single_scale)
+            sim_forward(state)
+        holder["samples"], holder["state"] = samples, state
+        ctx.samples, ctx.sets, ctx.state = samples, sets, state
+        ctx.shapes = [tuple(f.shape) for f in feats]
+        ctx.dtypes = [f.dtype for f in feats]
+        total = state.total.reshape(())
+        terms = state.term_loss
+        ctx.mark_non_differentiable(terms)
+        return total, terms
+
+    @staticmethod
+    def backward(ctx, grad_total, _grad_terms):
+        with torch.cuda.device(ctx.sets[0].bf16.device):
+            dFs = sim_backward(ctx.state, ctx.sets, grad_total)
+            grads = []
+            for s in range(len(ctx.sets)):
+                if ctx.needs_input_grad[4 + s]:
+                    grads.append(scatter_grad(dFs[s], ctx.sets[s], ctx.samples[s], ctx.shapes[s], ctx.dtypes[s]))
+                else:
+                    grads.append(None)
+        return (None, None, None, None, *grads)

@@ -1,0 +1,107 @@
+// gather.cu -- K2 (gather sampled embeddings + L2 normalise) and the scatter half of K4
+// (normalisation backward + dense gradient).
+//   gather  : features[b,:,idx] (V2.py:123) + F.normalize(p=2, dim=1, eps=1e-12) (V2.py:138)
+//   scatter : autograd backward of both: dx = (dF - f (f.dF)) / max(||x||, eps), written into
+//             a dense zero (n,C,h,w) gradient at the sampled pixels.
+// HBM-bound byte movers: NCHW means one anchor is C scalars `plane` floats apart (one 32 B
+// sector per useful 4 B), so one warp owns one anchor and keeps 8 independent loads in flight.
+#include "common.cuh"
+
+namespace mscs {
+
+constexpr int kMaxC = 256;
+
+__global__ void __launch_bounds__(256)
+k_gather_normalize(const float* __restrict__ feat, int C, int C_pad, int plane, const int* __restrict__ pix,
+                   int N, int N_pad, __nv_bfloat16* __restrict__ anc_bf16, float* __restrict__ anc_f32,
+                   float* __restrict__ inv_norm) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= N_pad) return;
+  __nv_bfloat16* orow = anc_bf16 + (size_t)row * C_pad;
+  if (row >= N) {                       // zero padding rows (TMA tiles read them)
+    for (int c = lane; c < C_pad; c += 32) orow[c] = __float2bfloat16(0.f);
+    return;
+  }
+  const int gp = pix[row];
+  const int b = gp / plane, p = gp - b * plane;
+  const float* src = feat + ((size_t)b * C) * plane + p;
+  float v[kMaxC / 32];
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxC / 32; ++j) {
+    int c = lane + 32 * j;
+    v[j] = (c < C) ? __ldg(src + (size_t)c * plane) : 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < kMaxC / 32; ++j) ss = fmaf(v[j], v[j], ss);
+  ss = warp_sum(ss);
+  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  if (lane == 0) inv_norm[row] = inv;
+#pragma unroll
+  for (int j = 0; j < kMaxC / 32; ++j) {
+    int c = lane + 32 * j;
+    float f = v[j] * inv;
+    if (c < C) anc_f32[(size_t)row * C + c] = f;
+    if (c < C_pad) orow[c] = __float2bfloat16(c < C ? f : 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_scatter_grad(const float* __restrict__ dF, int ldF, const float* __restrict__ anc_f32,
+               const float* __restrict__ inv_norm, const int* __restrict__ pix, int N, int C, int plane,
+               float* __restrict__ dfeat) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const float* g = dF + (size_t)row * ldF;
+  const float* f = anc_f32 + (size_t)row * C;
+  float gv[kMaxC / 32], fv[kMaxC / 32];
+  float dot = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxC / 32; ++j) {
+    int c = lane + 32 * j;
+    gv[j] = (c < C) ? g[c] : 0.f;
+    fv[j] = (c < C) ? f[c] : 0.f;
+    dot = fmaf(gv[j], fv[j], dot);
+  }
+  dot = warp_sum(dot);
+  const float inv = inv_norm[row];
+  const bool clamped = inv >= 1e12f;        // ||x|| <= eps: F.normalize divides by the constant eps
+  const int gp = pix[row];
+  const int b = gp / plane, p = gp - b * plane;
+  float* dst = dfeat + ((size_t)b * C) * plane + p;
+#pragma unroll
+  for (int j = 0; j < kMaxC / 32; ++j) {
+    int c = lane + 32 * j;
+    if (c < C) dst[(size_t)c * plane] = (clamped ? gv[j] : (gv[j] - fv[j] * dot)) * inv;
+  }
+}
+
+}  // namespace mscs
+
+using namespace mscs;
+
+extern "C" int mscs_gather_normalize(const float* feat, int n, int C, int plane, const int32_t* pix, int N,
+                                     void* anc_bf16, float* anc_f32, float* inv_norm, void* stream_) {
+  MSCS_CHECK_ARG(feat && pix && anc_bf16 && anc_f32 && inv_norm, "null pointer argument");
+  MSCS_CHECK_ARG(C >= 1 && C <= kMaxC, "C=%d unsupported (1..%d)", C, kMaxC);
+  MSCS_CHECK_ARG(n >= 1 && plane >= 1 && N >= 1, "bad sizes");
+  const int C_pad = (C + 63) / 64 * 64, N_pad = (N + 255) / 256 * 256;
+  k_gather_normalize<<<ceil_div(N_pad, 8), 256, 0, (cudaStream_t)stream_>>>(
+      feat, C, C_pad, plane, pix, N, N_pad, (__nv_bfloat16*)anc_bf16, anc_f32, inv_norm);
+  MSCS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mscs_scatter_grad(const float* dF, int ldF, const float* anc_f32, const float* inv_norm,
+                                 const int32_t* pix, int N, int n, int C, int plane, float* dfeat,
+                                 int zero_fill, void* stream_) {
+  MSCS_CHECK_ARG(dF && anc_f32 && inv_norm && pix && dfeat, "null pointer argument");
+  MSCS_CHECK_ARG(C >= 1 && C <= kMaxC && ldF >= C, "C=%d / ldF=%d unsupported", C, ldF);
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (zero_fill) MSCS_CUDA(cudaMemsetAsync(dfeat, 0, sizeof(float) * (size_t)n * C * plane, st));
+  k_scatter_grad<<<ceil_div(N, 8), 256, 0, st>>>(dF, ldF, anc_f32, inv_norm, pix, N, C, plane, dfeat);
+  MSCS_LAUNCH_CHECK();
+  return 0;
+}

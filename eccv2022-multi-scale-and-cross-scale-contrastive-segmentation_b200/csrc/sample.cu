@@ -1,0 +1,517 @@
+// sample.cu -- K1: label down-sampling, per-(image,class) histograms, class-balanced anchor
+// selection.  Integer work, bit-exact with the reference:
+//   losses/DenseContrastiveLossV2.py:194-206  nearest down-sampling (float32 round trip)
+//   losses/DenseContrastiveLossV2.py:86-125   histogram, pair list, per-pair randperm
+//   losses/DenseContrastiveLossV2.py:64-84    views-per-class rule
+// torch.randperm on the CPU default generator (V2.py:121) = MT19937 + forward Fisher-Yates
+// (ATen, third party; restated in oracle/mt19937.py and pinned there against torch itself).
+#include "common.cuh"
+
+namespace mscs {
+
+constexpr int kTile = 1024;      // pixels per histogram tile
+constexpr int kMaxV = 16384;     // views per pair the selection kernel supports
+
+struct ScaleGeo {
+  int dl_h, dl_w, hw, tiles;
+  int tile_base;                 // first global tile id of this scale
+  int ident_y, ident_x;
+  float sy, sx;                  // float(in)/out, as ATen computes it
+  size_t off_dlab, off_tilecnt, off_counts, off_kmap, off_pair, off_seg;
+  int pair_cap;
+};
+
+struct SampleLayout {
+  int S, n, H, W, A;
+  ScaleGeo g[MSCS_MAX_SCALES];
+  int total_tiles;
+  size_t counts_begin, counts_bytes;   // contiguous region holding every scale's counts
+  size_t bytes;
+};
+
+// pair arrays inside the workspace (per scale, pair_cap entries each)
+struct PairArrays {
+  int* b; int* c; int* cnt; int* dst; long long* off;
+};
+__host__ __device__ static inline PairArrays pair_arrays(char* ws, const ScaleGeo& g) {
+  PairArrays p;
+  char* base = ws + g.off_pair;
+  p.off = reinterpret_cast<long long*>(base);
+  p.b = reinterpret_cast<int*>(base + sizeof(long long) * g.pair_cap);
+  p.c = p.b + g.pair_cap;
+  p.cnt = p.c + g.pair_cap;
+  p.dst = p.cnt + g.pair_cap;
+  return p;
+}
+
+static int make_layout(const mscs_sample_cfg* cfg, SampleLayout* L) {
+  MSCS_CHECK_ARG(cfg != nullptr, "cfg is null");
+  MSCS_CHECK_ARG(cfg->num_scales >= 1 && cfg->num_scales <= MSCS_MAX_SCALES, "num_scales %d out of range",
+                 cfg->num_scales);
+  MSCS_CHECK_ARG(cfg->n >= 1 && cfg->H >= 1 && cfg->W >= 1, "bad label shape");
+  MSCS_CHECK_ARG(cfg->num_classes >= 2 && cfg->num_classes <= 32767, "num_classes %d out of range",
+                 cfg->num_classes);
+  L->S = cfg->num_scales; L->n = cfg->n; L->H = cfg->H; L->W = cfg->W; L->A = cfg->num_classes;
+  size_t off = 0;
+  int tile_base = 0;
+  // counts first, contiguous, so one memset clears them all
+  L->counts_begin = 0;
+  for (int s = 0; s < L->S; ++s) {
+    L->g[s].off_counts = off;
+    off += align_up(sizeof(int) * (size_t)L->n * L->A, 256);
+  }
+  L->counts_bytes = off;
+  for (int s = 0; s < L->S; ++s) {
+    ScaleGeo& g = L->g[s];
+    MSCS_CHECK_ARG(cfg->fw[s] >= 1 && cfg->fh[s] >= 1, "bad feature size at scale %d", s);
+    int scale = cfg->W / cfg->fw[s];                       // V2.py:46 (width only)
+    MSCS_CHECK_ARG(scale >= 1, "feature map wider than the label map at scale %d", s);
+    g.dl_h = cfg->H / scale; g.dl_w = cfg->W / scale;      // V2.py:205
+    MSCS_CHECK_ARG(g.dl_h >= 1 && g.dl_w >= 1, "empty down-sampled label at scale %d", s);
+    g.hw = g.dl_h * g.dl_w;
+    // the flat index y*dl_w+x addresses the flattened feature plane (V2.py:97,123): it must fit
+    MSCS_CHECK_ARG((long long)g.hw <= (long long)cfg->fh[s] * cfg->fw[s],
+                   "scale %d: down-sampled label %dx%d exceeds the feature plane %dx%d (the reference would "
+                   "index out of range)", s, g.dl_h, g.dl_w, cfg->fh[s], cfg->fw[s]);
+    g.tiles = ceil_div(g.hw, kTile);
+    g.tile_base = tile_base;
+    tile_base += g.tiles * L->n;
+    g.ident_y = (g.dl_h == cfg->H); g.ident_x = (g.dl_w == cfg->W);
+    g.sy = (float)cfg->H / (float)g.dl_h;
+    g.sx = (float)cfg->W / (float)g.dl_w;
+    g.pair_cap = L->n * (L->A - 1);
+    g.off_dlab = off;    off += align_up(sizeof(short) * (size_t)L->n * g.hw, 256);
+    g.off_tilecnt = off; off += align_up(sizeof(int) * (size_t)L->n * g.tiles * L->A, 256);
+    g.off_kmap = off;    off += align_up(sizeof(int) * (size_t)g.pair_cap, 256);
+    g.off_pair = off;    off += align_up((sizeof(long long) + 4 * sizeof(int)) * (size_t)g.pair_cap, 256);
+    g.off_seg = off;     off += align_up(sizeof(int) * (size_t)(L->A + 1), 256);
+  }
+  L->total_tiles = tile_base;
+  L->bytes = off;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// k_label_hist: one CTA per (scale, image, 1024-pixel tile).  Reads the int64 label at the
+// nearest-neighbour source position, writes the int16 down-sampled label, a per-tile class
+// histogram (for rank->pixel selection) and accumulates the per-image histogram.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int nearest_src(int dst, float scale, int in_size, int ident) {
+  if (ident) return dst;
+  int src = (int)floorf(__fmul_rn((float)dst, scale));
+  return min(src, in_size - 1);
+}
+
+__global__ void __launch_bounds__(256)
+k_label_hist(const __grid_constant__ SampleLayout L, const long long* __restrict__ labels, char* ws) {
+  extern __shared__ int hist[];
+  int t = blockIdx.x;
+  int s = 0;
+#pragma unroll 1
+  for (int i = 1; i < L.S; ++i) if (t >= L.g[i].tile_base) s = i;
+  const ScaleGeo& g = L.g[s];
+  int local = t - g.tile_base;
+  int b = local / g.tiles, tile = local % g.tiles;
+  for (int c = threadIdx.x; c < L.A; c += blockDim.x) hist[c] = 0;
+  __syncthreads();
+  short* dlab = reinterpret_cast<short*>(ws + g.off_dlab) + (size_t)b * g.hw;
+  const long long* lab = labels + (size_t)b * L.H * L.W;
+#pragma unroll
+  for (int i = 0; i < kTile / 256; ++i) {
+    int p = tile * kTile + i * 256 + threadIdx.x;
+    if (p < g.hw) {
+      int y = p / g.dl_w, x = p - y * g.dl_w;
+      int sy = nearest_src(y, g.sy, L.H, g.ident_y);
+      int sx = nearest_src(x, g.sx, L.W, g.ident_x);
+      long long v = lab[(size_t)sy * L.W + sx];
+      // the reference converts label -> float32 -> int64 (V2.py:205-206)
+      float f = (float)v;
+      long long c = (long long)f;
+      bool ok = (c >= 0 && c < L.A);
+      if (ok) atomicAdd(&hist[(int)c], 1);
+      dlab[p] = ok ? (short)c : (short)-1;
+    }
+  }
+  __syncthreads();
+  int* tilecnt = reinterpret_cast<int*>(ws + g.off_tilecnt) + ((size_t)b * g.tiles + tile) * L.A;
+  int* counts = reinterpret_cast<int*>(ws + g.off_counts) + (size_t)b * L.A;
+  for (int c = threadIdx.x; c < L.A; c += blockDim.x) {
+    int h = hist[c];
+    tilecnt[c] = h;
+    if (h) atomicAdd(&counts[c], h);
+  }
+}
+
+// exclusive prefix over the tiles of each (scale, image, class): tilecnt becomes "number of
+// class-c pixels of image b before this tile"
+__global__ void k_tile_scan(const __grid_constant__ SampleLayout L, char* ws) {
+  int s = blockIdx.y;
+  const ScaleGeo& g = L.g[s];
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= L.n * L.A) return;
+  int b = e / L.A, c = e - b * L.A;
+  int* tc = reinterpret_cast<int*>(ws + g.off_tilecnt) + (size_t)b * g.tiles * L.A + c;
+  int run = 0;
+  for (int t = 0; t < g.tiles; ++t) {
+    int v = tc[(size_t)t * L.A];
+    tc[(size_t)t * L.A] = run;
+    run += v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_plan: one CTA per scale.  Pair list in torch.where row-major order (V2.py:106), minimum
+// count (V2.py:110), views-per-class rule (V2.py:64-84), MT19937 stream offsets (one
+// randperm(count) = count-1 draws per pair, V2.py:121), and the class-sorted row layout.
+// ---------------------------------------------------------------------------------------
+struct PlanCfg { int min_views, max_views, max_total; };
+
+__global__ void __launch_bounds__(1024)
+k_plan(const __grid_constant__ SampleLayout L, PlanCfg pc, char* ws, mscs_scale_plan* plan) {
+  const int s = blockIdx.x;
+  const ScaleGeo& g = L.g[s];
+  const int A = L.A, n = L.n;
+  const int* counts = reinterpret_cast<const int*>(ws + g.off_counts);
+  int* kmap = reinterpret_cast<int*>(ws + g.off_kmap);
+  int* seg = reinterpret_cast<int*>(ws + g.off_seg);
+  PairArrays pa = pair_arrays(ws, g);
+  extern __shared__ int npc[];                       // pairs per class, A+1 entries
+  __shared__ int warp_pairs[32];
+  __shared__ long long warp_draws[32];
+  __shared__ int carry_pairs, min_count, single_px;
+  __shared__ long long carry_draws;
+  __shared__ int sh_V;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int c = tid; c <= A; c += blockDim.x) npc[c] = 0;
+  if (tid == 0) { carry_pairs = 0; carry_draws = 0; min_count = 0x7fffffff; single_px = 0; }
+  __syncthreads();
+  const int entries = n * (A - 1);
+  for (int base = 0; base < entries; base += blockDim.x) {
+    int e = base + tid;
+    int cnt = 0, flag = 0, b = 0, c = 0;
+    if (e < entries) {
+      b = e / (A - 1); c = e - b * (A - 1);
+      cnt = counts[b * A + c];
+      flag = cnt >= pc.min_views && cnt > 0;
+    }
+    // block exclusive scan of (flag, flag ? cnt-1 : 0)
+    int pf = flag;
+    long long df = flag ? (long long)(cnt - 1) : 0;
+    int ps = pf; long long ds = df;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int p2 = __shfl_up_sync(0xffffffffu, ps, o);
+      long long d2 = __shfl_up_sync(0xffffffffu, ds, o);
+      if (lane >= o) { ps += p2; ds += d2; }
+    }
+    if (lane == 31) { warp_pairs[wid] = ps; warp_draws[wid] = ds; }
+    __syncthreads();
+    if (wid == 0) {
+      int wp = warp_pairs[lane]; long long wd = warp_draws[lane];
+      int wps = wp; long long wds = wd;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int p2 = __shfl_up_sync(0xffffffffu, wps, o);
+        long long d2 = __shfl_up_sync(0xffffffffu, wds, o);
+        if (lane >= o) { wps += p2; wds += d2; }
+      }
+      warp_pairs[lane] = wps - wp; warp_draws[lane] = wds - wd;   // exclusive
+    }
+    __syncthreads();
+    int k = carry_pairs + warp_pairs[wid] + ps - pf;
+    long long off = carry_draws + warp_draws[wid] + ds - df;
+    if (e < entries) kmap[e] = flag ? k : -1;
+    if (flag) {
+      pa.b[k] = b; pa.c[k] = c; pa.cnt[k] = cnt; pa.off[k] = off;
+      atomicMin(&min_count, cnt);
+      atomicAdd(&npc[c], 1);
+      if (cnt == 1) single_px = 1;
+    }
+    __syncthreads();
+    if (tid == blockDim.x - 1) { carry_pairs = k + pf; carry_draws = off + df; }
+    __syncthreads();
+  }
+  const int T = carry_pairs;
+  if (tid == 0) {
+    int V = 0, logf = 0;
+    if (T > 0) {
+      if (pc.max_views == 1) {
+        V = min_count;
+      } else {
+        V = min(min_count, pc.max_views);
+        logf = (V == pc.max_views);
+      }
+      if ((long long)V * T > (long long)pc.max_total) { V = pc.max_total / T; logf = 1; }
+    }
+    sh_V = V;
+    // exclusive scan of pairs-per-class -> class base (in pairs); npc[c] becomes the base
+    int run = 0;
+    for (int c = 0; c <= A; ++c) { int v = npc[c]; npc[c] = run; run += v; }
+    mscs_scale_plan h;
+    h.T = T; h.V = V; h.N = T * V; h.min_count = T > 0 ? min_count : 0; h.log_flag = logf;
+    h.dl_h = g.dl_h; h.dl_w = g.dl_w;
+    h.error = (T == 0) ? 1 : (single_px ? 2 : 0);
+    h.draw_base = 0; h.draws = carry_draws;
+    plan[s] = h;
+  }
+  __syncthreads();
+  const int V = sh_V;
+  for (int c = tid; c <= A; c += blockDim.x) seg[c] = npc[c] * V;
+  // rank of each pair inside its class (pairs of one class appear in ascending image order)
+  for (int c = tid; c < A - 1; c += blockDim.x) {
+    int r = npc[c];
+    for (int b = 0; b < n; ++b) {
+      int k = kmap[b * (A - 1) + c];
+      if (k >= 0) { pa.dst[k] = r * V; ++r; }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_mt_stream: the raw tempered MT19937 output stream, `total` words, starting at (state,pos).
+// One CTA: a 624-word block regenerates in three dependent phases of 227/227/170 words.
+// ---------------------------------------------------------------------------------------
+struct MtState { uint32_t w[624]; };
+
+__device__ __forceinline__ uint32_t mt_twist(uint32_t u, uint32_t v) {
+  uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu);
+  return (y >> 1) ^ ((v & 1u) ? 0x9908b0dfu : 0u);
+}
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+  y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+  return y;
+}
+
+__global__ void __launch_bounds__(256)
+k_mt_stream(const uint32_t* __restrict__ state, int pos, long long total, uint32_t* __restrict__ out) {
+  __shared__ uint32_t buf[2][624];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 624; i += 256) buf[0][i] = state[i];
+  __syncthreads();
+  long long produced = 0;
+  // remaining words of the current block
+  for (int j = pos + tid; j < 624; j += 256) {
+    long long o = j - pos;
+    if (o < total) out[o] = mt_temper(buf[0][j]);
+  }
+  produced = 624 - pos;
+  int cur = 0;
+  while (produced < total) {
+    const uint32_t* c = buf[cur];
+    uint32_t* nx = buf[cur ^ 1];
+    if (tid < 227) nx[tid] = c[tid + 397] ^ mt_twist(c[tid], c[tid + 1]);
+    __syncthreads();
+    if (tid < 227) { int k = 227 + tid; nx[k] = nx[tid] ^ mt_twist(c[k], c[k + 1]); }
+    __syncthreads();
+    if (tid < 170) {
+      int k = 454 + tid;
+      if (k < 623) nx[k] = nx[k - 227] ^ mt_twist(c[k], c[k + 1]);
+      else nx[623] = nx[396] ^ mt_twist(c[623], nx[0]);
+    }
+    __syncthreads();
+    for (int j = tid; j < 624; j += 256) {
+      long long o = produced + j;
+      if (o < total) out[o] = mt_temper(nx[j]);
+    }
+    produced += 624;
+    cur ^= 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_fy_select: one CTA per kept pair.  (1) first V steps of the forward Fisher-Yates shuffle
+// that torch.randperm(count) performs (only they decide perm[:V], V2.py:121-122) resolved in
+// parallel; (2) rank -> pixel: the r-th pixel of class c in image b in raster order
+// (= nonzero()[r], V2.py:119) via the per-tile prefix table and a ballot scan of one tile.
+// ---------------------------------------------------------------------------------------
+struct SelectArgs {
+  long long draw_base[MSCS_MAX_SCALES];
+  int T[MSCS_MAX_SCALES], V[MSCS_MAX_SCALES];
+  int* idx_ref[MSCS_MAX_SCALES];
+  int* pair_ref[MSCS_MAX_SCALES];
+  int* pix[MSCS_MAX_SCALES];
+  int* cls[MSCS_MAX_SCALES];
+  int* seg[MSCS_MAX_SCALES];
+};
+
+__global__ void __launch_bounds__(256)
+k_fy_select(const __grid_constant__ SampleLayout L, const __grid_constant__ SelectArgs a, char* ws,
+            const uint32_t* __restrict__ draws) {
+  const int s = blockIdx.y, k = blockIdx.x;
+  if (k >= a.T[s]) return;
+  const ScaleGeo& g = L.g[s];
+  const int V = a.V[s], A = L.A;
+  PairArrays pa = pair_arrays(ws, g);
+  const int b = pa.b[k], c = pa.c[k], cnt = pa.cnt[k], dst = pa.dst[k];
+  const uint32_t* u = draws + a.draw_base[s] + pa.off[k];
+  extern __shared__ int sm[];
+  int* t_arr = sm;            // t_i = i + z_i : position swapped with i at step i
+  int* w_arr = sm + V;        // w_arr[p] = latest step j < p that wrote position p (t_j == p), or -1
+  int* r_arr = sm + 2 * V;    // resolved rank perm[i]
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    a.pair_ref[s][2 * k] = b; a.pair_ref[s][2 * k + 1] = c;
+    if (k == 0) for (int i = 0; i <= A; ++i) a.seg[s][i] = reinterpret_cast<const int*>(ws + g.off_seg)[i];
+  }
+  for (int i = tid; i < V; i += blockDim.x) {
+    int t = i;
+    if (i < cnt - 1) t = i + (int)(u[i] % (uint32_t)(cnt - i));
+    t_arr[i] = t;
+    w_arr[i] = -1;
+  }
+  __syncthreads();
+  for (int j = tid; j < V; j += blockDim.x) {
+    int t = t_arr[j];
+    if (t != j && t < V) atomicMax(&w_arr[t], j);
+  }
+  __syncthreads();
+  for (int i = tid; i < V; i += blockDim.x) {
+    const int t = t_arr[i];
+    int j1 = -1;
+    for (int j = i - 1; j >= 0; --j) if (t_arr[j] == t) { j1 = j; break; }
+    int r = t;
+    if (j1 >= 0) {                 // position t was last written at step j1 with the value then at j1
+      r = j1;
+      while (w_arr[r] >= 0) r = w_arr[r];
+    }
+    r_arr[i] = r;
+  }
+  __syncthreads();
+  // rank -> pixel, one warp per sample
+  const int lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  const int* prefix = reinterpret_cast<const int*>(ws + g.off_tilecnt) + (size_t)b * g.tiles * A + c;
+  const short* dlab = reinterpret_cast<const short*>(ws + g.off_dlab) + (size_t)b * g.hw;
+  for (int i = wid; i < V; i += nw) {
+    int r = r_arr[i];
+    int lo = 0, hi = g.tiles - 1;          // last tile whose exclusive prefix <= r
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (prefix[(size_t)mid * A] <= r) lo = mid; else hi = mid - 1;
+    }
+    int rem = r - prefix[(size_t)lo * A];
+    int p = -1;
+    for (int ch = 0; ch < kTile / 32; ++ch) {
+      int q = lo * kTile + ch * 32 + lane;
+      int v = (q < g.hw) ? (int)dlab[q] : -1;
+      unsigned m = __ballot_sync(0xffffffffu, v == c);
+      int pc = __popc(m);
+      if (rem < pc) { p = lo * kTile + ch * 32 + (int)__fns(m, 0, rem + 1); break; }
+      rem -= pc;
+    }
+    if (lane == 0) {
+      a.idx_ref[s][(size_t)k * V + i] = p;
+      a.pix[s][dst + i] = b * g.hw + p;
+      a.cls[s][dst + i] = c;
+    }
+  }
+}
+
+}  // namespace mscs
+
+using namespace mscs;
+
+extern "C" size_t mscs_sample_workspace_bytes(const mscs_sample_cfg* cfg) {
+  SampleLayout L;
+  if (make_layout(cfg, &L) != 0) return 0;
+  return L.bytes;
+}
+
+extern "C" size_t mscs_sample_max_draws(const mscs_sample_cfg* cfg) {
+  SampleLayout L;
+  if (make_layout(cfg, &L) != 0) return 0;
+  size_t d = 0;
+  for (int s = 0; s < L.S; ++s) d += (size_t)L.n * L.g[s].hw;
+  return d;
+}
+
+extern "C" int mscs_sample_plan(const mscs_sample_cfg* cfg, const int64_t* labels, void* workspace,
+                                mscs_scale_plan* plan_dev, void* stream_) {
+  SampleLayout L;
+  int rc = make_layout(cfg, &L);
+  if (rc) return rc;
+  MSCS_CHECK_ARG(labels && workspace && plan_dev, "null pointer argument");
+  MSCS_CHECK_ARG(cfg->min_views >= 0 && cfg->max_views >= 1 && cfg->max_total >= 1, "bad sampling limits");
+  cudaStream_t st = (cudaStream_t)stream_;
+  char* ws = (char*)workspace;
+  MSCS_CUDA(cudaMemsetAsync(ws + L.counts_begin, 0, L.counts_bytes, st));
+  k_label_hist<<<L.total_tiles, 256, sizeof(int) * L.A, st>>>(L, (const long long*)labels, ws);
+  MSCS_LAUNCH_CHECK();
+  dim3 gs(ceil_div(L.n * L.A, 128), L.S);
+  k_tile_scan<<<gs, 128, 0, st>>>(L, ws);
+  MSCS_LAUNCH_CHECK();
+  PlanCfg pc{cfg->min_views, cfg->max_views, cfg->max_total};
+  k_plan<<<L.S, 1024, sizeof(int) * (L.A + 1), st>>>(L, pc, ws, plan_dev);
+  MSCS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mscs_plan_fetch(const mscs_scale_plan* plan_dev, mscs_scale_plan* plan_host, int num_scales,
+                               void* stream_) {
+  MSCS_CHECK_ARG(plan_dev && plan_host && num_scales >= 1 && num_scales <= MSCS_MAX_SCALES, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream_;
+  MSCS_CUDA(cudaMemcpyAsync(plan_host, plan_dev, sizeof(mscs_scale_plan) * num_scales, cudaMemcpyDeviceToHost, st));
+  MSCS_CUDA(cudaStreamSynchronize(st));
+  long long base = 0;
+  for (int s = 0; s < num_scales; ++s) { plan_host[s].draw_base = base; base += plan_host[s].draws; }
+  return 0;
+}
+
+extern "C" int mscs_sample_select(const mscs_sample_cfg* cfg, const mscs_scale_plan* plan_host,
+                                  const uint32_t* mt_state_host, int mt_pos, void* workspace,
+                                  uint32_t* draws_dev, int32_t* const* idx_ref, int32_t* const* pair_ref,
+                                  int32_t* const* pix, int32_t* const* cls, int32_t* const* seg,
+                                  void* stream_) {
+  SampleLayout L;
+  int rc = make_layout(cfg, &L);
+  if (rc) return rc;
+  MSCS_CHECK_ARG(plan_host && mt_state_host && workspace && draws_dev, "null pointer argument");
+  MSCS_CHECK_ARG(mt_pos >= 0 && mt_pos <= 624, "mt_pos %d out of range", mt_pos);
+  cudaStream_t st = (cudaStream_t)stream_;
+  SelectArgs a;
+  long long total = 0;
+  int maxT = 0, maxV = 0;
+  for (int s = 0; s < L.S; ++s) {
+    MSCS_CHECK_ARG(plan_host[s].error == 0, "scale %d: sampling plan reports error %d", s, plan_host[s].error);
+    MSCS_CHECK_ARG(plan_host[s].V <= kMaxV, "scale %d: %d views per class exceeds the supported %d", s,
+                   plan_host[s].V, kMaxV);
+    a.draw_base[s] = plan_host[s].draw_base; a.T[s] = plan_host[s].T; a.V[s] = plan_host[s].V;
+    a.idx_ref[s] = idx_ref[s]; a.pair_ref[s] = pair_ref[s]; a.pix[s] = pix[s]; a.cls[s] = cls[s]; a.seg[s] = seg[s];
+    total = plan_host[s].draw_base + plan_host[s].draws;
+    if (plan_host[s].T > maxT) maxT = plan_host[s].T;
+    if (plan_host[s].V > maxV) maxV = plan_host[s].V;
+  }
+  // MT19937 state -> device (624 words at the head of the draws buffer's tail: use a small async copy)
+  uint32_t* state_dev = draws_dev + align_up((size_t)total, 64);
+  MSCS_CUDA(cudaMemcpyAsync(state_dev, mt_state_host, sizeof(uint32_t) * 624, cudaMemcpyHostToDevice, st));
+  if (total > 0) {
+    k_mt_stream<<<1, 256, 0, st>>>(state_dev, mt_pos, total, draws_dev);
+    MSCS_LAUNCH_CHECK();
+  }
+  size_t smem = sizeof(int) * 3 * (size_t)maxV;
+  if (smem > 48 * 1024)
+    MSCS_CUDA(cudaFuncSetAttribute(k_fy_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(maxT, L.S);
+  k_fy_select<<<grid, 256, smem, st>>>(L, a, (char*)workspace, draws_dev);
+  MSCS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mscs_mt19937_advance_host(uint32_t* mt, int* pos, uint64_t k) {
+  MSCS_CHECK_ARG(mt && pos && *pos >= 0 && *pos <= 624, "bad MT19937 state");
+  int p = *pos;
+  while (k > 0) {
+    if (p >= 624) {
+      // regenerate in place (the sequential form of the published algorithm)
+      for (int i = 0; i < 624; ++i) {
+        uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+        mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
+      p = 0;
+    }
+    uint64_t take = (uint64_t)(624 - p) < k ? (uint64_t)(624 - p) : k;
+    p += (int)take;
+    k -= take;
+  }
+  *pos = p;
+  return 0;
+}

@@ -1,0 +1,350 @@
+// sim_bwd.cu -- K4 (tensor half): fused backward of the similarity / loss, recomputing logit
+// tiles instead of storing them.  Replaces the autograd backward of V2.py:138-188 and
+// _ms.py:95-156 up to d loss / d (unit rows); the normalisation backward + dense scatter is
+// gather.cu.
+//
+// One pass computes  dX_rows += scale * W(rows, cols) * Y_cols  with
+//   W_ij = E_ij (cS_i + cS_j)                                   (negative pair)
+//   W_ij = -( cPN_i / (E_ij + neg_i) + cPN_j / (E_ij + neg_j) ) (positive pair, 0 on the diagonal)
+// where cS = S/(div N1), cPN = neg/(div N1) come from the forward (k_finalize).  A single-scale
+// term is ONE pass with both the row and column coefficients (W = G + G^T, so no second product);
+// a cross-scale term is a pass with row coefficients only (dA) and, unless the key side is
+// detached, a pass with rows = keys and column coefficients only (dK).
+//
+// CTA = 128 rows (X tile resident in smem) x a run of 128-column tiles.  Per tile:
+//   MMA 1  S = X Y^T              (both K-major)        -> TMEM, double buffered
+//   epilogue: W = f(exp2(S)) as bf16 into smem (128-byte swizzled, K-major A operand)
+//   MMA 2  dX += W Y              (Y tile re-used from smem as an MN-major B operand) -> TMEM
+// dX stays in TMEM for the whole run and is flushed with fp32 reductions at the end.
+#include "sim_tc.cuh"
+
+namespace mscs {
+
+constexpr int kBwdThreads = 384;
+
+struct BwdDev {
+  const int* row_cls; const int* col_seg;
+  const float* row_cs; const float* row_cpn; const float* row_neg;
+  const float* col_cs; const float* col_cpn; const float* col_neg;
+  float* dF; int ld;
+  int n_rows, n_cols, self_mask, x_map, y_map;
+  float scale_log2, out_scale;
+};
+struct BwdArgs {
+  alignas(64) CUtensorMap maps[MSCS_MAX_SCALES];
+  BwdDev p[MSCS_MAX_PASSES];
+  WorkTable work;
+  const float* grad_out;
+};
+
+__host__ __device__ constexpr size_t bwd_smem_bytes(int KB) {
+  return 1024 + (size_t)(3 * KB + 2) * kBlkBytes + 3 * 128 * sizeof(float) + 256;
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+template <int KB>
+__global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constant__ BwdArgs args) {
+  constexpr int CP = KB * 64;                       // padded channel count = N of the second MMA
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smA = smem;                                         // [KB][128][128 B]   X tile
+  uint8_t* smB = smA + (size_t)KB * kBlkBytes;                 // [2][KB][128][128 B] Y tiles
+  uint8_t* smW = smB + (size_t)2 * KB * kBlkBytes;             // [2][128][128 B]    W halves (64 columns each)
+  float* cstat = reinterpret_cast<float*>(smW + 2 * kBlkBytes);   // [3][128] column coefficients
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cstat + 3 * 128);
+  uint64_t* a_full = bars;        uint64_t* a_empty = bars + 1;
+  uint64_t* b_full = bars + 2;    uint64_t* b_empty = bars + 4;     // [2]
+  uint64_t* s_full = bars + 6;    uint64_t* s_empty = bars + 8;     // [2]
+  uint64_t* w_full = bars + 10;   uint64_t* w_empty = bars + 12;    // [2]
+  uint64_t* df_full = bars + 14;  uint64_t* df_empty = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    ptx::mbar_init(a_full, 1); ptx::mbar_init(a_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1);
+      ptx::mbar_init(&s_full[i], 1); ptx::mbar_init(&s_empty[i], 8);
+      ptx::mbar_init(&w_full[i], 4); ptx::mbar_init(&w_empty[i], 1);
+    }
+    ptx::mbar_init(df_full, 1); ptx::mbar_init(df_empty, 8);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc(tmem_slot, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_dF = tmem_base + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA producer =================
+      Walker wk(args.work);
+      Segment sg;
+      uint32_t a_phase = 0, it = 0;
+      while (wk.next(sg)) {
+        const BwdDev& p = args.p[sg.owner];
+        ptx::mbar_wait(a_empty, a_phase ^ 1);
+        ptx::mbar_expect_tx(a_full, KB * kBlkBytes);
+        for (int kb = 0; kb < KB; ++kb)
+          ptx::tma_load_2d(smA + (size_t)kb * kBlkBytes, &args.maps[p.x_map], a_full, kb * kKBlk, sg.rb * 128);
+        a_phase ^= 1;
+        for (int ct = sg.c_begin; ct < sg.c_end; ++ct, ++it) {
+          const uint32_t st = it & 1;
+          ptx::mbar_wait(&b_empty[st], ((it >> 1) & 1) ^ 1);
+          ptx::mbar_expect_tx(&b_full[st], KB * kBlkBytes);
+          for (int kb = 0; kb < KB; ++kb)
+            ptx::tma_load_2d(smB + (size_t)(st * KB + kb) * kBlkBytes, &args.maps[p.y_map], &b_full[st],
+                             kb * kKBlk, ct * kTileN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================= MMA issuer =================
+      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, kTileN, 0, 0);   // S  = X Y^T
+      constexpr uint32_t idesc_d = ptx::umma_idesc_bf16(128, CP, 0, 1);       // dX += W Y (B MN-major)
+      const uint32_t a_addr = ptx::smem_u32(smA), b_addr = ptx::smem_u32(smB), w_addr = ptx::smem_u32(smW);
+      Walker wk(args.work);
+      Segment sg;
+      uint32_t a_phase = 0, it = 0, seg = 0;
+      auto issue_s = [&](uint32_t cur) {
+        const uint32_t st = cur & 1, ph = (cur >> 1) & 1;
+        ptx::mbar_wait(&b_full[st], ph);
+        ptx::mbar_wait(&s_empty[st], ph ^ 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = ptx::umma_desc_sw128(a_addr + kb * kBlkBytes + k * 32, 16, 1024);
+            const uint64_t bd = ptx::umma_desc_sw128(b_addr + (st * KB + kb) * kBlkBytes + k * 32, 16, 1024);
+            ptx::umma_ss(tmem_base + st * 128, ad, bd, idesc_s, (kb | k) != 0);
+          }
+        ptx::umma_commit(&s_full[st]);
+      };
+      while (wk.next(sg)) {
+        ptx::mbar_wait(a_full, a_phase); a_phase ^= 1;
+        ptx::mbar_wait(df_empty, (seg & 1) ^ 1);
+        ptx::tc_fence_after();
+        const int ntiles = sg.c_end - sg.c_begin;
+        issue_s(it);
+        for (int j = 0; j < ntiles; ++j) {
+          const uint32_t cur = it + j, st = cur & 1;
+          if (j + 1 < ntiles) issue_s(cur + 1);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            ptx::mbar_wait(&w_full[h], cur & 1);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = ptx::umma_desc_sw128(w_addr + h * kBlkBytes + k * 32, 16, 1024);
+              // Y rows h*64 + k*16 .. +16 are the K slice; LBO = next 64-channel block, SBO = next 8 K rows
+              const uint64_t bd = ptx::umma_desc_sw128(b_addr + st * KB * kBlkBytes + (h * 64 + k * 16) * 128,
+                                                       kBlkBytes, 1024);
+              ptx::umma_ss(tmem_dF, ad, bd, idesc_d, (j | h | k) != 0);
+            }
+            ptx::umma_commit(&w_empty[h]);
+          }
+          ptx::umma_commit(&b_empty[st]);
+        }
+        ptx::umma_commit(df_full);
+        ptx::umma_commit(a_empty);
+        it += ntiles; ++seg;
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue: thread = (row, 64-column half) =================
+    const int h = (warp - 4) >> 2, quad = warp & 3;
+    const int wg_tid = threadIdx.x - (4 + 4 * h) * 32;      // 0..127 inside the column-half group
+    const int r_loc = quad * 32 + lane;                     // row inside the tile = TMEM lane
+    float* cs_s = cstat; float* cs_pn = cstat + 128; float* cs_neg = cstat + 256;
+    uint8_t* wrow = smW + (size_t)h * kBlkBytes + (size_t)r_loc * 128;
+    const float gout = *args.grad_out;
+    Walker wk(args.work);
+    Segment sg;
+    uint32_t it = 0, seg = 0;
+    while (wk.next(sg)) {
+      const BwdDev& p = args.p[sg.owner];
+      const int row = sg.rb * 128 + r_loc;
+      const bool valid = row < p.n_rows;
+      int p0 = 0, p1 = 0;
+      if (valid) { const int y = p.row_cls[row]; p0 = p.col_seg[y]; p1 = p.col_seg[y + 1]; }
+      const unsigned plen = (unsigned)(p1 - p0);
+      int wmin = valid ? p0 : 0x7fffffff, wmax = valid ? p1 : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        wmin = min(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
+        wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+      }
+      const float rcs = (valid && p.row_cs) ? p.row_cs[row] : 0.f;
+      const float rcpn = (valid && p.row_cpn) ? p.row_cpn[row] : 0.f;
+      const float rneg = (valid && p.row_neg) ? p.row_neg[row] : 1.f;
+      const int self_col = p.self_mask ? row : -1;
+      const float scale = p.scale_log2;
+      for (int ct = sg.c_begin; ct < sg.c_end; ++ct, ++it) {
+        const uint32_t buf = it & 1;
+        const int cb = ct * kTileN + h * 64;               // first global column of this thread's half
+        // stage the column coefficients of this half (64 columns) in smem
+        named_bar_sync(1 + h, 128);
+        if (wg_tid < 64) {
+          const int c = cb + wg_tid; const bool ok = c < p.n_cols;
+          cs_s[h * 64 + wg_tid] = (ok && p.col_cs) ? p.col_cs[c] : 0.f;
+          cs_pn[h * 64 + wg_tid] = (ok && p.col_cpn) ? p.col_cpn[c] : 0.f;
+          cs_neg[h * 64 + wg_tid] = (ok && p.col_neg) ? p.col_neg[c] : 1.f;
+        }
+        named_bar_sync(1 + h, 128);
+        ptx::mbar_wait(&s_full[buf], (it >> 1) & 1);
+        ptx::mbar_wait(&w_empty[h], (it & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128 + h * 64;
+        const bool touches = !(cb + 64 <= wmin || cb >= wmax);
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+          uint32_t v[32];
+          ptx::tmem_ld32(taddr + part * 32, v);
+          ptx::tmem_ld_wait(v);
+          uint32_t packed[16];
+          if (!touches) {
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+              const int j = h * 64 + part * 32 + c;
+              const float w0 = ptx::ex2(__uint_as_float(v[c]) * scale) * (rcs + cs_s[j]);
+              const float w1 = ptx::ex2(__uint_as_float(v[c + 1]) * scale) * (rcs + cs_s[j + 1]);
+              packed[c >> 1] = pack_bf16(w0, w1);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; c += 2) {
+              float w[2];
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const int j = h * 64 + part * 32 + c + q;
+                const int col = cb + part * 32 + c + q;
+                const float e = ptx::ex2(__uint_as_float(v[c + q]) * scale);
+                const bool ispos = (unsigned)(col - p0) < plen;
+                const float wn = e * (rcs + cs_s[j]);
+                const float wp = -(rcpn * ptx::rcp(e + rneg) + cs_pn[j] * ptx::rcp(e + cs_neg[j]));
+                w[q] = ispos ? (col == self_col ? 0.f : wp) : wn;
+              }
+              packed[c >> 1] = pack_bf16(w[0], w[1]);
+            }
+          }
+          // 32 columns = 4 chunks of 16 B; 128-byte swizzle: chunk index XOR (row & 7)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int chunk = (part * 4 + q) ^ (r_loc & 7);
+            *reinterpret_cast<uint4*>(wrow + chunk * 16) =
+                make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { ptx::mbar_arrive(&s_empty[buf]); ptx::mbar_arrive(&w_full[h]); }
+      }
+      // ---- flush dX: this group drains channel half h ----
+      ptx::mbar_wait(df_full, seg & 1);
+      ptx::tc_fence_after();
+      const float sc = p.out_scale * gout;
+      float* drow = p.dF + (size_t)row * p.ld;
+#pragma unroll 1
+      for (int c0 = h * (CP / 2); c0 < (h + 1) * (CP / 2); c0 += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem_dF + ((uint32_t)(quad * 32) << 16) + c0, v);
+        ptx::tmem_ld_wait(v);
+        if (valid) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 4)
+            red_add_v4(drow + c0 + c, __uint_as_float(v[c]) * sc, __uint_as_float(v[c + 1]) * sc,
+                       __uint_as_float(v[c + 2]) * sc, __uint_as_float(v[c + 3]) * sc);
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(df_empty);
+      ++seg;
+    }
+  }
+  __syncwarp();
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace mscs
+
+using namespace mscs;
+
+template <int KB>
+static int launch_bwd(const BwdArgs& args, cudaStream_t st) {
+  const size_t smem = bwd_smem_bytes(KB);
+  MSCS_CUDA(cudaFuncSetAttribute(k_sim_bwd<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_sim_bwd<KB><<<sm_count(), kBwdThreads, smem, st>>>(args);
+  MSCS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mscs_sim_backward(const mscs_sim_job* job, const float* grad_out, float* const* dF_sets,
+                                 const int32_t* dF_ld, void* stream_) {
+  int rc = validate_job(job);
+  if (rc) return rc;
+  MSCS_CHECK_ARG(job->work && grad_out && dF_sets && dF_ld, "null pointer argument");
+  cudaStream_t st = (cudaStream_t)stream_;
+  BwdPass passes[MSCS_MAX_PASSES];
+  const int np = build_passes(job, passes);
+  // the backward work tables live after the two forward tables in job->work
+  size_t fwd_items = 0;
+  for (int t = 0; t < job->num_terms; ++t) fwd_items += (size_t)ceil_div(job->terms[t].N1, 256);
+  char* w = (char*)job->work +
+            2 * (align_up(sizeof(WorkItem) * fwd_items, 64) + align_up(sizeof(int) * (fwd_items + 1), 64));
+  BwdArgs args{};
+  args.grad_out = grad_out;
+  const void* bases[MSCS_MAX_SCALES]; int nmaps = 0;
+  auto map_of = [&](const void* base, int rows) -> int {
+    for (int i = 0; i < nmaps; ++i) if (bases[i] == base) return i;
+    if (nmaps == MSCS_MAX_SCALES) return -1;
+    if (make_tensor_map(&args.maps[nmaps], base, (rows + 255) / 256 * 256, job->C_pad)) return -2;
+    bases[nmaps] = base;
+    return nmaps++;
+  };
+  BuildArgs b{};
+  int nitems = 0;
+  for (int i = 0; i < np; ++i) {
+    const BwdPass& p = passes[i];
+    const int xm = map_of(p.x_bf16, p.n_rows), ym = map_of(p.y_bf16, p.n_cols);
+    if (xm == -2 || ym == -2) return -1;
+    MSCS_CHECK_ARG(xm >= 0 && ym >= 0, "too many distinct operand matrices");
+    MSCS_CHECK_ARG(dF_sets[p.row_set] && dF_ld[p.row_set] >= job->C_pad && dF_ld[p.row_set] % 4 == 0,
+                   "pass %d: dF buffer of set %d missing or leading dimension < C_pad", i, p.row_set);
+    args.p[i] = BwdDev{p.row_cls, p.col_seg, p.row_cs, p.row_cpn, p.row_neg, p.col_cs, p.col_cpn, p.col_neg,
+                       dF_sets[p.row_set], dF_ld[p.row_set], p.n_rows, p.n_cols, p.self_mask, xm, ym,
+                       p.scale_log2, p.out_scale};
+    b.t[i] = BuildTerm{p.row_cls, p.col_seg, p.n_rows, p.n_cols, nitems};
+    nitems += ceil_div(p.n_rows, 128);
+  }
+  b.num_terms = np; b.nitems = nitems; b.rows_per_item = 128; b.mode = 0;
+  b.items = (WorkItem*)w; w += align_up(sizeof(WorkItem) * (size_t)nitems, 64);
+  b.prefix = (int*)w;
+  rc = launch_build_work(b, st);
+  if (rc) return rc;
+  args.work = WorkTable{b.items, b.prefix, nitems};
+  switch (job->C_pad / 64) {
+    case 1: return launch_bwd<1>(args, st);
+    case 2: return launch_bwd<2>(args, st);
+    case 3: return launch_bwd<3>(args, st);
+    default: return launch_bwd<4>(args, st);
+  }
+}

@@ -1,0 +1,56 @@
+// sim_tc.cuh -- pieces shared by the tcgen05 forward and backward kernels: the work table
+// (balanced contiguous tile ranges per CTA), the TMA tensor-map factory, shared-memory carving.
+#pragma once
+#include "ptx.cuh"
+#include "sim_common.cuh"
+
+namespace mscs {
+
+constexpr int kTileN = 128;          // key rows (logit columns) per tile
+constexpr int kKBlk = 64;            // bf16 elements per 128-byte swizzled row
+constexpr int kBlkBytes = 128 * 128; // one [128 rows][64 bf16] operand block = 16 KB
+
+// one unit of work = one (row block, column tile); an item is a run of column tiles of one row block
+struct WorkItem { int owner, rb, ct0, ct1; };
+struct WorkTable { const WorkItem* items; const int* prefix; int nitems; };
+
+struct Segment { int owner, rb, c_begin, c_end; };
+
+struct Walker {
+  const WorkTable& w;
+  int u, u_end, item;
+  __device__ Walker(const WorkTable& wt) : w(wt) {
+    const long long total = wt.prefix[wt.nitems];
+    u = (int)(total * blockIdx.x / gridDim.x);
+    u_end = (int)(total * (blockIdx.x + 1) / gridDim.x);
+    int lo = 0, hi = wt.nitems;        // largest item with prefix[item] <= u
+    while (lo < hi) {
+      int mid = (lo + hi + 1) >> 1;
+      if (wt.prefix[mid] <= u) lo = mid; else hi = mid - 1;
+    }
+    item = lo;
+  }
+  __device__ bool next(Segment& s) {
+    if (u >= u_end) return false;
+    while (w.prefix[item + 1] <= u) ++item;
+    const WorkItem it = w.items[item];
+    const int base = w.prefix[item];
+    const int e = min(u_end, w.prefix[item + 1]);
+    s.owner = it.owner; s.rb = it.rb;
+    s.c_begin = it.ct0 + (u - base);
+    s.c_end = it.ct0 + (e - base);
+    u = e;
+    return true;
+  }
+};
+
+// work-table builder (sim_fwd.cu): one item per (owner, row block)
+struct BuildTerm { const int* a_cls; const int* k_seg; int N1, N2, item_base; };
+struct BuildArgs { BuildTerm t[MSCS_MAX_PASSES]; int num_terms, nitems, rows_per_item, mode; WorkItem* items; int* prefix; };
+int launch_build_work(const BuildArgs& b, cudaStream_t st);
+int sm_count();
+
+// TMA tensor map for a row-major (rows, C_pad) bf16 matrix, box = {64 elements, 128 rows}, 128B swizzle
+int make_tensor_map(CUtensorMap* out, const void* base, int rows, int c_pad);
+
+}  // namespace mscs

@@ -1,0 +1,329 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against
+the CPU oracle and the golden fixtures generated from the executable reference.
+
+Tolerances (BASELINE.json north_star): sampled indices / pair lists / T / V bit-exact; loss within
+1e-3 relative; embedding gradients cosine >= 0.999 (max-abs error printed)."""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import CLASSES, cosine, load_npz, make_module, oracle_cfg_for, small_case_inputs
+
+pytestmark = pytest.mark.gpu
+
+SMALL = ["tiny_ss", "tiny_ms", "tiny_ms_detach", "odd_ss"]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+    import mscs_b200
+    assert mscs_b200.load().mscs_device_ok() == 1, "libmscs.so needs a compute-capability 10.x device"
+    return torch.device("cuda:0")
+
+
+def _sample(meta, labels, feats, z, dev):
+    from mscs_b200 import _ops
+    mod = make_module(meta)
+    torch.set_rng_state(torch.from_numpy(z["rng_state0"]))
+    smp = _ops.sample_anchors(labels.to(dev), [tuple(f.shape[-2:]) for f in feats], mod._spec)
+    return mod, smp
+
+
+def _check_sorted_layout(smp, idx_ref, pairs, plane, A):
+    """The class-sorted kernel layout must hold exactly the reference's sampled set."""
+    pix, cls, seg = smp.pix.cpu().numpy(), smp.cls.cpu().numpy(), smp.seg.cpu().numpy()
+    ref_pix = (pairs[:, 0:1].astype(np.int64) * plane + idx_ref).ravel()
+    ref_cls = np.repeat(pairs[:, 1], idx_ref.shape[1])
+    assert np.array_equal(np.sort(pix), np.sort(ref_pix))
+    assert len(np.unique(pix)) == len(pix)
+    assert np.all(np.diff(cls) >= 0)
+    order = np.argsort(ref_pix)
+    assert np.array_equal(cls[np.argsort(pix)], ref_cls[order])
+    counts = np.bincount(cls, minlength=A)
+    assert np.array_equal(seg, np.concatenate([[0], np.cumsum(counts)]))
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_sampling_bit_exact_small(name, golden, dev):
+    meta = golden[name]
+    labels, feats, z = small_case_inputs(name)
+    mod, smp = _sample(meta, labels, feats, z, dev)
+    for s, sm in enumerate(smp):
+        assert [sm.T, sm.V] == meta["TV"][s]
+        assert np.array_equal(sm.idx_ref.cpu().numpy(), z[f"idx{s}"]), f"scale {s}: sampled indices differ"
+        assert np.array_equal(sm.pair_ref.cpu().numpy(), z[f"pairs{s}"])
+        _check_sorted_layout(sm, z[f"idx{s}"], z[f"pairs{s}"], sm.dl_h * sm.dl_w, mod._spec.num_classes)
+    # the torch CPU generator must end where the reference leaves it
+    assert torch.equal(torch.get_rng_state(), torch.from_numpy(z["rng_state1"]))
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2"])
+def test_sampling_bit_exact_bench_configs(name, golden, dev):
+    from mscs_b200 import synth
+    meta = golden[name]
+    z = load_npz(name)
+    labels, _ = synth.make_inputs(name, with_features=(name == "cfg1"))
+    cfg = synth.CONFIGS[name]
+    hw = [(cfg["H"] // s, cfg["W"] // s) for s in cfg["strides"]]
+    from mscs_b200 import _ops
+    mod = make_module(meta)
+    torch.set_rng_state(torch.from_numpy(z["rng_state0"]))
+    smp = _ops.sample_anchors(labels.to(dev), hw, mod._spec)
+    for s, sm in enumerate(smp):
+        assert [sm.T, sm.V] == meta["TV"][s]
+        assert np.array_equal(sm.idx_ref.cpu().numpy(), z[f"idx{s}"])
+        assert np.array_equal(sm.pair_ref.cpu().numpy(), z[f"pairs{s}"])
+        _check_sorted_layout(sm, z[f"idx{s}"], z[f"pairs{s}"], sm.dl_h * sm.dl_w, mod._spec.num_classes)
+    assert torch.equal(torch.get_rng_state(), torch.from_numpy(z["rng_state1"]))
+
+
+@pytest.mark.parametrize("name", ["cfg3", "cfg4", "cfg4_large", "cfg5"])
+def test_sampling_hashes_big(name, golden, dev):
+    import mscs_b200
+    from mscs_b200 import _ops, synth
+    meta = golden[name + "_sampling"]
+    z = load_npz(name + "_sampling")
+    cfg = synth.CONFIGS[name]
+    labels, _ = synth.make_inputs(name, with_features=False)
+    cls = mscs_b200.DenseContrastiveLossV2 if cfg["single_scale"] else mscs_b200.DenseContrastiveLossV2_ms
+    mod = cls(dict(cfg["loss"]))
+    torch.manual_seed(0)
+    smp = _ops.sample_anchors(labels.to(dev), [(cfg["H"] // s, cfg["W"] // s) for s in cfg["strides"]], mod._spec)
+    for s, sm in enumerate(smp):
+        assert [sm.T, sm.V] == meta["TV"][s]
+        idx = sm.idx_ref.cpu().numpy().astype(np.int64)
+        assert hashlib.sha256(np.ascontiguousarray(idx).tobytes()).hexdigest() == meta["idx_sha"][s]
+        assert np.array_equal(sm.pair_ref.cpu().numpy(), z[f"pairs{s}"])
+    assert torch.equal(torch.get_rng_state(), torch.from_numpy(z["rng_state1"]))
+
+
+def test_sampling_many_views_single_image(dev):
+    """Validation-like shape: one image, few pairs, thousands of views per class (exercises the
+    Fisher-Yates prefix resolution with many collisions) against the oracle."""
+    from mscs_b200 import _ops, synth
+    from oracle.mt19937 import MT19937
+    from oracle.sampling import sample_indices
+    labels = synth.synth_labels(1, 256, 512, 19, 5, 16, 0.05, 9)
+    spec = _ops.LossSpec(num_classes=20, temperature=0.1, cs_temperature=0.1, min_views=5, max_views=2500,
+                         max_total=10000)
+    for seed, fw in [(3, 128), (4, 512)]:
+        torch.manual_seed(seed)
+        gen = MT19937.from_torch_state(torch.get_rng_state().numpy().tobytes())
+        o = sample_indices(labels.numpy(), fw, 20, 5, 2500, 10000, gen)
+        sm = _ops.sample_anchors(labels.to(dev), [(256 * fw // 512, fw)], spec)[0]
+        assert (sm.T, sm.V) == (o["T"], o["V"]) and sm.V >= 1000
+        assert np.array_equal(sm.idx_ref.cpu().numpy(), o["idx"])
+
+
+def test_sampling_errors(dev):
+    from mscs_b200 import _ops
+    spec = _ops.LossSpec(num_classes=20, temperature=0.1, cs_temperature=0.1, min_views=5)
+    labels = torch.full((1, 32, 32), 19, dtype=torch.long, device=dev)     # ignore class only
+    with pytest.raises(RuntimeError):
+        _ops.sample_anchors(labels, [(8, 8)], spec)
+
+
+def _sets_for(meta, labels, feats, z, dev):
+    from mscs_b200 import _ops
+    mod, smp = _sample(meta, labels, feats, z, dev)
+    sets = [_ops.gather_normalize(f.to(dev).contiguous(), s) for f, s in zip(feats, smp)]
+    return mod, smp, sets
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_gather_normalize(name, golden, dev):
+    meta = golden[name]
+    labels, feats, z = small_case_inputs(name)
+    mod, smp, sets = _sets_for(meta, labels, feats, z, dev)
+    for f, sm, st in zip(feats, smp, sets):
+        n, Cc, h, w = f.shape
+        pix = sm.pix.cpu().long()
+        x = f.reshape(n, Cc, -1)[pix // (h * w), :, pix % (h * w)]
+        ref = torch.nn.functional.normalize(x, p=2, dim=1)
+        assert torch.allclose(st.f32.cpu(), ref, atol=2e-7, rtol=1e-6)
+        assert torch.allclose(st.inv_norm.cpu(), 1.0 / x.norm(dim=1).clamp_min(1e-12), rtol=1e-6)
+        bf = st.bf16.cpu()
+        assert torch.equal(bf[:st.N, :Cc], st.f32.cpu().bfloat16())       # same rounding of the same fp32 value
+        assert bf[st.N:].abs().max() == 0 and (Cc == st.C_pad or bf[:, Cc:].abs().max() == 0)
+
+
+def _oracle_terms(spec, smp, rows, single_scale):
+    """fp64 oracle on given unit rows (one matrix per scale, kernel row order)."""
+    from oracle import loss_fp64
+    ys = [s.cls.cpu().numpy() for s in smp]
+    S = len(rows)
+    terms = [(s, s, True, spec.weights[s], spec.temperature, False) for s in range(S)]
+    if spec.cross_scale and not single_scale:
+        terms.append((0, S - 1, False, spec.w_high_low, spec.cs_temperature, not spec.detach_deepest))
+        if S > 2:
+            terms.append((0, S - 2, False, spec.w_high_mid, spec.cs_temperature, not spec.detach_deepest))
+    out, dFs, total = [], [np.zeros_like(r) for r in rows], 0.0
+    for (a, k, sm_, w, tau, need_dk) in terms:
+        l, da, dk, st = loss_fp64.term(rows[a], ys[a], rows[k], ys[k], tau, sm_, True, 512)
+        out.append((l, st))
+        total += w * l
+        dFs[a] += w * da
+        if sm_ or need_dk:
+            dFs[k] += w * dk
+    return out, dFs, total
+
+
+def _pad_f32(st, src):
+    out = torch.zeros((st.N, st.C_pad), dtype=torch.float32, device=src.device)
+    out[:, :src.shape[1]] = src[:st.N, :src.shape[1]]
+    return out
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("name", SMALL)
+def test_similarity_kernels_vs_oracle(name, impl, golden, dev):
+    """Row statistics, per-term losses and d loss/d unit rows of the similarity kernels against the
+    fp64 oracle evaluated on the SAME operand rows (fp32 rows for the SIMT validation kernels, the
+    bf16-rounded rows for the tcgen05 kernels), so only accumulation order / exp2 / bf16 W remain."""
+    from mscs_b200 import _lib, _ops
+    meta = golden[name]
+    labels, feats, z = small_case_inputs(name)
+    mod, smp, sets = _sets_for(meta, labels, feats, z, dev)
+    spec, single = mod._spec, meta["single_scale"]
+    state = _ops.build_job(spec, smp, sets, single)
+    lib = _lib.load()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if impl == "simt":
+        f32 = [_pad_f32(s, s.f32) for s in sets]
+        rows = [s.f32.cpu().double().numpy() for s in sets]
+    else:
+        f32 = None
+        rows = [s.bf16[:s.N, :s.C].float().cpu().double().numpy() for s in sets]
+    g = torch.full((1,), 0.7, dtype=torch.float32, device=dev)
+    dFs = [torch.zeros((s.N, s.C_pad), dtype=torch.float32, device=dev) for s in sets]
+    ptrs = [0] * _lib.MAX_SCALES
+    lds = (C.c_int32 * _lib.MAX_SCALES)()
+    for i, d in enumerate(dFs):
+        ptrs[i], lds[i] = d.data_ptr(), d.shape[1]
+    if impl == "simt":
+        fp = [0] * _lib.MAX_SCALES
+        for i, f in enumerate(f32):
+            fp[i] = f.data_ptr()
+        _lib.check(lib.mscs_debug_sim_forward_simt(C.byref(state.job), _lib.ptr_array(fp), st), "simt fwd")
+        _lib.check(lib.mscs_debug_sim_backward_simt(C.byref(state.job), _lib.ptr_array(fp), g.data_ptr(),
+                                                    _lib.ptr_array(ptrs), lds, st), "simt bwd")
+    else:
+        _lib.check(lib.mscs_sim_forward(C.byref(state.job), st), "tc fwd")
+        _lib.check(lib.mscs_sim_backward(C.byref(state.job), g.data_ptr(), _lib.ptr_array(ptrs), lds, st), "tc bwd")
+    torch.cuda.synchronize()
+    terms, o_dFs, o_total = _oracle_terms(spec, smp, rows, single)
+    stats = state.keep[0].cpu().numpy()
+    off = 0
+    for i, (l, ost) in enumerate(terms):
+        n1 = len(ost["neg"])
+        neg, pos, ssum = stats[off:off + n1], stats[off + n1:off + 2 * n1], stats[off + 2 * n1:off + 3 * n1]
+        off += 3 * n1
+        np.testing.assert_allclose(neg, ost["neg"], rtol=2e-5, err_msg=f"{impl} term {i} neg sums")
+        np.testing.assert_allclose(pos, ost["possum"], rtol=1e-4, atol=1e-4, err_msg=f"{impl} term {i} pos sums")
+        np.testing.assert_allclose(ssum, ost["S"], rtol=1e-4, atol=1e-9, err_msg=f"{impl} term {i} S sums")
+        assert abs(float(state.term_loss[i]) - l) < 2e-5 * abs(l)
+    assert abs(float(state.total) - o_total) < 2e-5 * abs(o_total)
+    for s in range(len(sets)):
+        got = dFs[s][:, :sets[s].C].cpu().double().numpy()
+        want = 0.7 * o_dFs[s]
+        cs = cosine(got, want)
+        err = np.abs(got - want).max()
+        print(f"{name}/{impl} set {s}: dF cosine {cs:.8f} max-abs {err:.3e} (scale {np.abs(want).max():.3e})")
+        assert cs > (0.999999 if impl == "simt" else 0.9999)
+        assert err < (1e-5 if impl == "simt" else 2e-2) * np.abs(want).max()
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_end_to_end_small(name, golden, dev):
+    """Module forward/backward (the drop-in call) against the reference's recorded outputs."""
+    meta = golden[name]
+    labels, feats, z = small_case_inputs(name)
+    mod = make_module(meta)
+    fg = [f.to(dev).requires_grad_(True) for f in feats]
+    torch.set_rng_state(torch.from_numpy(z["rng_state0"]))
+    loss = mod(labels.to(dev), fg[0] if meta["single_scale"] else fg)
+    assert loss.dim() == 0 and loss.requires_grad
+    loss = loss * 1.0
+    loss *= 0.1                       # LossWrapper multiplies in place (LossWrapper.py:90)
+    loss.backward()
+    assert abs(float(loss) / 0.1 - meta["total"]) < 1e-3 * abs(meta["total"])
+    if not meta["single_scale"]:
+        assert len(mod.ms_losses) == len(meta["ms"]) and len(mod.cs_losses) == len(meta["cs"])
+        for a, b in zip(list(mod.ms_losses) + list(mod.cs_losses), meta["ms"] + meta["cs"]):
+            assert abs(float(a) - b) < 1e-3 * abs(b)
+    for s, f in enumerate(fg):
+        got, want = f.grad.cpu().numpy() / 0.1, z[f"grad{s}"]
+        cs, err = cosine(got, want), np.abs(got - want).max()
+        print(f"{name} scale {s}: grad cosine {cs:.7f} max-abs {err:.3e} (ref max {np.abs(want).max():.3e})")
+        assert cs >= 0.999
+        assert np.array_equal(got != 0, want != 0) or np.abs(got[(got != 0) != (want != 0)]).max() < 1e-12
+    assert torch.equal(torch.get_rng_state(), torch.from_numpy(z["rng_state1"]))
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2"])
+def test_end_to_end_bench_configs(name, golden, dev):
+    from mscs_b200 import synth
+    meta = golden[name]
+    z = load_npz(name)
+    labels, feats = synth.make_inputs(name)
+    mod = make_module(meta)
+    fg = [f.to(dev).requires_grad_(True) for f in feats]
+    torch.set_rng_state(torch.from_numpy(z["rng_state0"]))
+    loss = mod(labels.to(dev), fg[0] if meta["single_scale"] else fg)
+    loss.backward()
+    rel = abs(float(loss) - meta["total"]) / abs(meta["total"])
+    print(f"{name}: loss {float(loss):.6f} reference {meta['total']:.6f} rel {rel:.2e}")
+    assert rel < 1e-3
+    if not meta["single_scale"]:
+        for a, b in zip(list(mod.ms_losses) + list(mod.cs_losses), meta["ms"] + meta["cs"]):
+            assert abs(float(a) - b) < 1e-3 * abs(b)
+    for s, f in enumerate(fg):
+        n, Cc, h, w = f.shape
+        g = f.grad.reshape(n, Cc, h * w)
+        idx, pairs = z[f"idx{s}"], z[f"pairs{s}"]
+        T, V = idx.shape
+        ids = z[f"grad_row_ids{s}"]
+        k, v = ids // V, ids % V
+        bsel = torch.from_numpy(pairs[k, 0].astype(np.int64)).to(dev)
+        psel = torch.from_numpy(idx[k, v].astype(np.int64)).to(dev)
+        rows = g[bsel, :, psel].cpu().numpy()
+        cs, err = cosine(rows, z[f"grad_rows{s}"]), np.abs(rows - z[f"grad_rows{s}"]).max()
+        # per-row L2 norms of every sampled pixel + global norm
+        ball = torch.from_numpy(np.repeat(pairs[:, 0], V).astype(np.int64)).to(dev)
+        pall = torch.from_numpy(idx.ravel().astype(np.int64)).to(dev)
+        l2 = g[ball, :, pall].norm(dim=1).cpu().numpy()
+        l2_cos = cosine(l2, z[f"grad_row_l2_{s}"])
+        tot = float(f.grad.double().norm())
+        print(f"{name} scale {s}: grad rows cosine {cs:.7f} max-abs {err:.3e}; row-norm cosine {l2_cos:.7f}; "
+              f"|grad| {tot:.6e} vs {meta['grad_l2'][s]:.6e}")
+        assert cs >= 0.999 and l2_cos >= 0.999
+        assert abs(tot - meta["grad_l2"][s]) < 2e-3 * meta["grad_l2"][s]
+        assert int((f.grad != 0).any(dim=1).sum()) == T * V      # exactly the sampled pixels are touched
+
+
+def test_properties_full_size(dev):
+    """Size-independent properties at the headline size (cfg-2): the gradient of a function of the
+    normalised embedding is orthogonal to the embedding; scaling a feature map by a power of two
+    leaves the loss unchanged; same seed -> same sampled set."""
+    import mscs_b200
+    from mscs_b200 import synth
+    labels, feats = synth.make_inputs("cfg2")
+    mod = mscs_b200.DenseContrastiveLossV2_ms(dict(synth.CONFIGS["cfg2"]["loss"]))
+    fg = [f.to(dev).requires_grad_(True) for f in feats]
+    torch.manual_seed(0)
+    loss = mod(labels.to(dev), fg)
+    loss.backward()
+    pix0 = [s.pix.clone() for s in mod.last_samples]
+    for f in fg:
+        dot = (f.grad * f.detach()).sum(1)
+        scale = (f.grad.norm(dim=1) * f.detach().norm(dim=1)).clamp_min(1e-30)
+        assert float((dot.abs() / scale).max()) < 2e-3
+    torch.manual_seed(0)
+    with torch.no_grad():
+        loss2 = mod(labels.to(dev), [f.detach() * 4.0 for f in fg])
+    assert all(torch.equal(a, s.pix) for a, s in zip(pix0, mod.last_samples))
+    assert abs(float(loss2) - float(loss)) < 1e-5 * abs(float(loss))

@@ -1,0 +1,88 @@
+"""CPU: host-side logic, config rules, and that the C-ABI library loads and exports every
+symbol include/mscs.h declares (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import mscs_b200
+from mscs_b200 import _lib, _ops
+from mscs_b200.datasets import class_facts
+from helpers import ROOT
+
+
+def test_library_exports_header_symbols():
+    lib = mscs_b200.load()
+    header = open(os.path.join(ROOT, "include", "mscs.h")).read()
+    declared = set(re.findall(r"\b(mscs_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in mscs.h but not exported"
+    assert set(_lib.EXPORTS) == declared
+    assert b"sm_100a" in lib.mscs_version()
+
+
+def test_struct_layouts_match_header():
+    # sizes the C side uses (checked against the header by reading the field lists)
+    assert ctypes.sizeof(_lib.ScalePlan) == 48
+    assert ctypes.sizeof(_lib.SampleCfg) == 4 * 4 + 2 * 8 * 4 + 4 * 4
+    assert ctypes.sizeof(_lib.Term) == 6 * 8 + 4 * 4 + 2 * 4 + 2 * 4 + 5 * 8
+
+
+def test_mt_advance_host_matches_torch():
+    lib = mscs_b200.load()
+    for seed, k in [(0, 9), (1, 623), (2, 624), (3, 625), (4, 100000)]:
+        torch.manual_seed(seed)
+        mt, pos = _ops.torch_mt_state()
+        _ops.torch_mt_advance(mt.copy(), pos, k)
+        mine = torch.get_rng_state().clone()
+        torch.manual_seed(seed)
+        torch.randperm(k + 1)          # consumes exactly k draws
+        assert torch.equal(mine, torch.get_rng_state()), (seed, k)
+    assert lib.mscs_last_error() is not None
+
+
+def test_class_facts_table():
+    assert class_facts("CITYSCAPES", 1) == (20, 19, 19)
+    assert class_facts("ADE20K", 1) == (151, 150, 150)
+    assert class_facts("CADIS", 1) == (8, 8, -1)
+    with pytest.raises(KeyError):
+        class_facts("NOPE", 0)
+
+
+def test_config_rules():
+    base = dict(dataset="CITYSCAPES", experiment=1)
+    m = mscs_b200.DenseContrastiveLossV2(base)
+    assert m.temperature == 0.5 and m.min_views_per_class == 5 and m.max_views_per_class == 2500
+    assert m.max_features_total == 10000 and m.cross_scale_contrast is False and m.log_this_step is False
+    ms = mscs_b200.DenseContrastiveLossV2_ms(dict(base, temperature=0.2))
+    assert ms.scales == 2 and ms.weights == [1.0, 1.0] and ms.cross_scale_temperature == pytest.approx(0.2)
+    # Q5: presence of the key switches to the hard-coded 0.1
+    ms = mscs_b200.DenseContrastiveLossV2_ms(dict(base, temperature=0.2, cross_scale_temperature=0.07))
+    assert ms.cross_scale_temperature == pytest.approx(0.1)
+    with pytest.raises(KeyError):
+        mscs_b200.DenseContrastiveLossV2_ms(base)       # neither temperature key (_ms.py:28)
+    with pytest.raises(AssertionError):
+        mscs_b200.DenseContrastiveLossV2_ms(dict(base, temperature=0.1, scales=3, weights=[1.0, 1.0]))
+
+
+def test_no_cpu_fallback():
+    m = mscs_b200.DenseContrastiveLossV2(dict(dataset="CITYSCAPES", experiment=1, temperature=0.1))
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 8, 8, dtype=torch.long), torch.zeros(1, 4, 2, 2))
+
+
+def test_workspace_queries_and_arg_validation():
+    lib = mscs_b200.load()
+    cfg = _lib.SampleCfg()
+    cfg.n, cfg.H, cfg.W, cfg.num_scales = 2, 64, 128, 1
+    cfg.fh[0], cfg.fw[0] = 16, 32
+    cfg.num_classes, cfg.min_views, cfg.max_views, cfg.max_total = 20, 5, 100, 10000
+    assert lib.mscs_sample_workspace_bytes(ctypes.byref(cfg)) > 0
+    assert lib.mscs_sample_max_draws(ctypes.byref(cfg)) == 2 * 16 * 32
+    cfg.fw[0] = 256                      # wider than the label map
+    assert lib.mscs_sample_workspace_bytes(ctypes.byref(cfg)) == 0
+    assert b"wider" in lib.mscs_last_error()
