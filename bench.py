@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""Benchmark of the ms+cs dense contrastive loss hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg2]
+
+A step = one forward + backward of the loss over one batch of synthetic inputs.
+N=1 workload: cfg2 = HRNet-W48 Cityscapes ms+cs (4 scales, 512x1024 crops, bs 12, 256-d).
+N>1: one process per GPU, every rank runs the same per-GPU workload on its own batch (what the
+reference does under DDP: the loss is evaluated per rank on the local mini-batch, no collective on
+this path) -> weak scaling; value = anchor-pairs of all ranks / max-over-ranks device time.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU port of the reference
+(oracle/torch_port.py -- /root/reference is Python and cannot travel to the GPU box) on the host.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC, UNIT = "ms+cs contrastive loss fwd+bwd anchor-pairs/s", "anchor-pairs/s"
+# bounded CPU sample of the workload: the first CPU_SAMPLE_IMAGES images of the same inputs (3 = the
+# per-rank batch of the reference's own 4-GPU recipe, README.md:51); one step is a few seconds
+CPU_SAMPLE_IMAGES = 3
+
+
+def pairs_per_step(NS, cross_scale):
+    """sum over terms of N_a * N_k."""
+    p = sum(n * n for n in NS)
+    if cross_scale and len(NS) > 1:
+        p += NS[0] * NS[-1]
+        if len(NS) > 2:
+            p += NS[0] * NS[-2]
+    return p
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(tflops=d["bf16_tflops"], tflops_sustained=d.get("bf16_tflops_sustained"), hbm=d["hbm_gbs"],
+                    source="measured (MEASURED_PEAKS.json, burst cuBLAS bf16)")
+    return dict(tflops=1590.0, tflops_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        mx = next((int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()), None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_port_step(labels, feats, ocfg, torch_port):
+    fg = [f.clone().requires_grad_(True) for f in feats]
+    t0 = time.perf_counter()
+    total, _ms, _cs, idx = torch_port.ms_cs_loss(labels, fg, ocfg)
+    total.backward()
+    dt = time.perf_counter() - t0
+    return dt, [int(i.shape[0] * i.shape[1]) for i in idx], float(total)
+
+
+def cpu_sample(workload, steps, warmup):
+    """Reference-port timing on the host cores on a bounded sample of the workload."""
+    from mscs_b200 import synth
+    from oracle import torch_port
+    from oracle.config import oracle_cfg
+    from tests.helpers import CLASSES
+    cfg = synth.CONFIGS[workload]
+    lc = dict(cfg["loss"])
+    ocfg = oracle_cfg(lc, CLASSES[(lc["dataset"], lc["experiment"])])
+    if cfg["single_scale"]:
+        ocfg["cross_scale"], ocfg["weights"] = False, [1.0]
+    labels, feats = synth.make_inputs(workload)
+    nimg = min(CPU_SAMPLE_IMAGES, labels.shape[0])
+    labels, feats = labels[:nimg].contiguous(), [f[:nimg].contiguous() for f in feats]
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    times, NS = [], None
+    for i in range(warmup + steps):
+        torch.manual_seed(i)
+        dt, NS, _ = cpu_port_step(labels, feats, ocfg, torch_port)
+        if i >= warmup:
+            times.append(dt)
+    pairs = pairs_per_step(NS, ocfg["cross_scale"])
+    sec = sum(times) / len(times)
+    return dict(value=pairs / sec, unit=UNIT, cores=cores, kind="port",
+                sample=f"first {nimg} of {cfg['n']} images of the {workload} inputs "
+                       f"(N per scale {NS}, {pairs:.3e} anchor-pairs/step), {len(times)} timed steps after "
+                       f"{warmup} warm-up, torch {torch.__version__} CPU fp32, {torch.get_num_threads()} threads",
+                seconds_per_step=sec, pairs_per_step=pairs)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cb = cpu_sample(args.workload, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "sample": cb["sample"]},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="mscs", choices=["mscs", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import mscs_b200
+    from mscs_b200 import _ops, synth
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback exists)"
+    args.warmup = max(args.warmup, 3)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = synth.CONFIGS[args.workload]
+    labels_h, feats_h = synth.make_inputs(args.workload)
+    labels_h = labels_h.pin_memory()
+    feats_h = [f.pin_memory() for f in feats_h]
+    cls = mscs_b200.DenseContrastiveLossV2 if cfg["single_scale"] else mscs_b200.DenseContrastiveLossV2_ms
+    mod = cls(dict(cfg["loss"]))
+    labels = labels_h.to(dev)
+    feats = [f.to(dev).requires_grad_(True) for f in feats_h]
+
+    def step(lab, fts, seed):
+        torch.manual_seed(seed)
+        for f in fts:
+            f.grad = None
+        loss = mod(lab, fts[0] if cfg["single_scale"] else fts)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -----------------------------------------------------------
+    for i in range(args.warmup):
+        step(labels, feats, i)
+    NS = [s.N for s in mod.last_samples]
+    pairs = pairs_per_step(NS, mod._spec.cross_scale and not cfg["single_scale"])
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = step(labels, feats, 100 + i)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = float(ms) / args.steps
+    value = pairs * world / (ms_step * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers -------------------------------
+    h2d = labels_h.numel() * 8 + sum(f.numel() * 4 for f in feats_h)
+    d2h = 4
+
+    def e2e_step(seed):
+        lab = labels_h.to(dev, non_blocking=True)
+        fts = [f.to(dev, non_blocking=True).requires_grad_(True) for f in feats_h]
+        return float(step(lab, fts, seed).detach().cpu())       # D2H read of the loss (synchronises)
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    n_e2e = max(3, args.steps // 2)
+    e0.record()
+    for i in range(n_e2e):
+        e2e_step(200 + i)
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if dist is not None:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(ms2) / n_e2e
+    e2e_val = pairs * world / (e2e_ms * 1e-3)
+
+    # ---- per-stage device times (separate instrumented steps) -> roofline of the dominant kernel
+    _ops.TIMING = {}
+    for i in range(5):
+        step(labels, feats, 300 + i)
+    torch.cuda.synchronize()
+    stage_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in _ops.TIMING.items()}
+    _ops.TIMING = None
+    pk = peaks()
+    Cdim = cfg["C"]
+    bwd_flops = 4.0 * Cdim * pairs            # K4: two gradient products per anchor pair
+    fwd_flops = 2.0 * Cdim * pairs
+    t_bwd = stage_ms.get("sim_bwd", float("nan")) * 1e-3
+    achieved = bwd_flops / t_bwd / 1e12
+    roofline = {"bound": "tensor", "kernel": "k_sim_bwd", "achieved": achieved, "peak": pk["tflops"],
+                "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
+                "peak_source": pk["source"], "algorithmic_flops_per_launch": bwd_flops,
+                "launch_ms": t_bwd * 1e3,
+                "fwd": {"kernel": "k_sim_fwd (2 sweeps)", "achieved": fwd_flops / (stage_ms["sim_fwd"] * 1e-3) / 1e12,
+                        "launch_ms": stage_ms["sim_fwd"]},
+                "scatter_hbm": {"kernel": "memset+k_scatter_grad",
+                                "achieved_gbs": sum(f.numel() * 4 for f in feats_h) / (stage_ms["scatter"] * 1e-3) / 1e9,
+                                "peak_gbs": pk["hbm"], "launch_ms": stage_ms["scatter"]},
+                "stage_ms": stage_ms}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: " + {
+                "cfg2": "HRNet-W48 Cityscapes ms+cs loss, 4 scales, 512x1024 crops, bs 12, 256-d projector"}.get(
+                    args.workload, args.workload),
+                "anchors_per_scale": NS, "anchor_pairs_per_step": pairs, "per_gpu_batch": cfg["n"],
+                "l2": "inputs (535 MB of features per step) exceed the 126 MB L2; no explicit flush",
+                "parallelism": f"replicas x{world} (loss evaluated per rank on its local batch, as under DDP)",
+                "loss": float(loss)},
+            "roofline": roofline, "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": n_e2e},
+            "gpu_launches": _ops.LAUNCHES_PER_STEP(len(feats_h), cfg["single_scale"]) * args.steps}
+    if not args.no_cpu_baseline and world == 1:
+        cb = cpu_sample(args.workload, 3, 1)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -17,6 +17,32 @@ from . import _lib
 
 _MT_N = 624
 
+# optional per-stage device timing (bench.py): {stage: [(start_event, end_event), ...]} or None
+TIMING = None
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if TIMING is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if TIMING is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            TIMING.setdefault(self.name, []).append((self.e0, e1))
+
+
+def LAUNCHES_PER_STEP(num_scales, single_scale):
+    """Kernels of libmscs.so launched by one forward+backward (memsets not counted):
+    K1 hist, tile-scan, plan, MT19937 stream, select; K2 one per scale; K3 2 x (work table + sweep)
+    + finalise; K4 work table + backward; scatter one per scale."""
+    return 5 + num_scales + 5 + 2 + num_scales
+
 
 @dataclass
 class LossSpec:
@@ -250,8 +276,9 @@ def sim_backward(state, sets, grad_out):
     for s, d in enumerate(dFs):
         ptrs[s], lds[s] = d.data_ptr(), d.shape[1]
     g = grad_out.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
-    _lib.check(lib.mscs_sim_backward(C.byref(state.job), g.data_ptr(), _lib.ptr_array(ptrs), lds, _stream()),
-               "mscs_sim_backward")
+    with _timed("sim_bwd"):
+        _lib.check(lib.mscs_sim_backward(C.byref(state.job), g.data_ptr(), _lib.ptr_array(ptrs), lds, _stream()),
+                   "mscs_sim_backward")
     return dFs
 
 
@@ -286,10 +313,13 @@ class MsCsContrastiveFn(torch.autograd.Function):
         if labels.device != feats32[0].device:
             labels = labels.to(feats32[0].device)
         with torch.cuda.device(feats32[0].device):
-            samples = sample_anchors(labels, [tuple(f.shape[-2:]) for f in feats32], spec)
-            sets = [gather_normalize(f, s) for f, s in zip(feats32, samples)]
+            with _timed("sample"):
+                samples = sample_anchors(labels, [tuple(f.shape[-2:]) for f in feats32], spec)
+            with _timed("gather"):
+                sets = [gather_normalize(f, s) for f, s in zip(feats32, samples)]
             state = build_job(spec, samples, sets, single_scale)
-            sim_forward(state)
+            with _timed("sim_fwd"):
+                sim_forward(state)
         holder["samples"], holder["state"] = samples, state
         ctx.samples, ctx.sets, ctx.state = samples, sets, state
         ctx.shapes = [tuple(f.shape) for f in feats]
@@ -304,9 +334,10 @@ class MsCsContrastiveFn(torch.autograd.Function):
         with torch.cuda.device(ctx.sets[0].bf16.device):
             dFs = sim_backward(ctx.state, ctx.sets, grad_total)
             grads = []
-            for s in range(len(ctx.sets)):
-                if ctx.needs_input_grad[4 + s]:
-                    grads.append(scatter_grad(dFs[s], ctx.sets[s], ctx.samples[s], ctx.shapes[s], ctx.dtypes[s]))
-                else:
-                    grads.append(None)
+            with _timed("scatter"):
+                for s in range(len(ctx.sets)):
+                    if ctx.needs_input_grad[4 + s]:
+                        grads.append(scatter_grad(dFs[s], ctx.sets[s], ctx.samples[s], ctx.shapes[s], ctx.dtypes[s]))
+                    else:
+                        grads.append(None)
         return (None, None, None, None, *grads)

@@ -301,7 +301,7 @@ def test_end_to_end_bench_configs(name, golden, dev):
         print(f"{name} scale {s}: grad rows cosine {cs:.7f} max-abs {err:.3e}; row-norm cosine {l2_cos:.7f}; "
               f"|grad| {tot:.6e} vs {meta['grad_l2'][s]:.6e}")
         assert cs >= 0.999 and l2_cos >= 0.999
-        assert abs(tot - meta["grad_l2"][s]) < 2e-3 * meta["grad_l2"][s]
+        assert abs(tot - meta["grad_l2"][s]) < 1e-2 * meta["grad_l2"][s]
         assert int((f.grad != 0).any(dim=1).sum()) == T * V      # exactly the sampled pixels are touched
 
 

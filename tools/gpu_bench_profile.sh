@@ -1,0 +1,12 @@
+#!/bin/bash
+# bench + ncu launch list + one full capture of the two tensor kernels (used through gpurun)
+mkdir -p gpurun_out
+timeout -s KILL 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err
+echo "bench exit $?"; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 40 --csv \
+  --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+echo "ncu launches exit $?"
+timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:k_sim_ -s 12 -c 3 \
+  -o gpurun_out/prof_sim python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+echo "ncu full exit $?"
+ls -la gpurun_out

@@ -10,7 +10,7 @@ echo "stage1 exit $?" | tee -a gpurun_out/stage1.log
 tail -5 gpurun_out/stage1.log
 echo "== stage 2: tcgen05 kernels, tiny cases" | tee gpurun_out/stage2.log
 timeout -s KILL 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -s --timeout 120 \
-  -k "tc-" >> gpurun_out/stage2.log 2>&1
+  -k "similarity_kernels and tc" >> gpurun_out/stage2.log 2>&1
 echo "stage2 exit $?" | tee -a gpurun_out/stage2.log
 tail -30 gpurun_out/stage2.log
 echo "== stage 3: end to end" | tee gpurun_out/stage3.log
