@@ -99,10 +99,10 @@ def cpu_sample(workload, steps, warmup):
     from mscs_b200 import synth
     from oracle import torch_port
     from oracle.config import oracle_cfg
-    from tests.helpers import CLASSES
+    from mscs_b200.datasets import class_facts
     cfg = synth.CONFIGS[workload]
     lc = dict(cfg["loss"])
-    ocfg = oracle_cfg(lc, CLASSES[(lc["dataset"], lc["experiment"])])
+    ocfg = oracle_cfg(lc, class_facts(lc["dataset"], lc["experiment"])[0])
     if cfg["single_scale"]:
         ocfg["cross_scale"], ocfg["weights"] = False, [1.0]
     labels, feats = synth.make_inputs(workload)
@@ -173,8 +173,9 @@ def main():
     labels = labels_h.to(dev)
     feats = [f.to(dev).requires_grad_(True) for f in feats_h]
 
+    torch.manual_seed(0)      # seeded once, like a training run: the generator then only advances
+
     def step(lab, fts, seed):
-        torch.manual_seed(seed)
         for f in fts:
             f.grad = None
         loss = mod(lab, fts[0] if cfg["single_scale"] else fts)

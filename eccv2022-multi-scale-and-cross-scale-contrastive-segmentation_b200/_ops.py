@@ -41,7 +41,7 @@ def LAUNCHES_PER_STEP(num_scales, single_scale):
     """Kernels of libmscs.so launched by one forward+backward (memsets not counted):
     K1 hist, tile-scan, plan, MT19937 stream, select; K2 one per scale; K3 2 x (work table + sweep)
     + finalise; K4 work table + backward; scatter one per scale."""
-    return 5 + num_scales + 5 + 2 + num_scales
+    return 5 + num_scales + 6 + 2 + 2 * num_scales      # + slot maps; finalise is two kernels
 
 
 @dataclass
@@ -98,10 +98,11 @@ def torch_mt_state():
 
 def torch_mt_advance(mt, pos, draws):
     """Advance the torch CPU default generator by ``draws`` 32-bit outputs -- what the reference's
-    per-pair ``torch.randperm`` calls would have consumed (V2.py:121)."""
+    per-pair ``torch.randperm`` calls would have consumed (V2.py:121).  Returns the new (mt, pos)."""
     if draws <= 0:
-        return
+        return mt, pos
     lib = _lib.load()
+    mt = mt.copy()
     cpos = C.c_int(pos)
     _lib.check(lib.mscs_mt19937_advance_host(mt.ctypes.data_as(C.c_void_p), C.byref(cpos), C.c_uint64(draws)),
                "mscs_mt19937_advance_host")
@@ -111,10 +112,68 @@ def torch_mt_advance(mt, pos, draws):
     raw[16:24] = np.frombuffer(struct.pack("<Q", cpos.value), dtype=np.uint8)
     raw[24:24 + 8 * _MT_N] = mt.astype(np.uint64).view(np.uint8)
     torch.set_rng_state(torch.from_numpy(raw))
+    return mt, cpos.value
+
+
+class _StreamCache:
+    """MT19937 output streams produced ahead of time on a side CUDA stream.
+
+    The stream a call needs depends only on the torch CPU generator state, and after a call that
+    state is known (we advance it ourselves), so the next call's stream is generated while this
+    call's tensor kernels run.  A call whose generator state is not the predicted one (first call,
+    reseeding, another consumer of the generator) regenerates inline -- results are identical."""
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.side = torch.cuda.Stream(device=dev)
+        self.bufs = [None, None]
+        self.cur = 0
+        self.key = None          # (state bytes, pos) the buffer `cur` was generated from
+        self.words = 0
+        self.ready = None        # event: buffer `cur` complete
+        self.last_use = [None, None]   # event: last main-stream reader of each buffer
+
+    def _generate(self, which, mt, pos, words):
+        lib = _lib.load()
+        if self.bufs[which] is None or self.bufs[which].numel() < words + 1024:
+            self.bufs[which] = torch.empty(words + 1024, dtype=torch.int32, device=self.dev)
+        main = torch.cuda.current_stream()
+        self.side.wait_stream(main)              # allocator / previous readers of this buffer
+        if self.last_use[which] is not None:
+            self.side.wait_event(self.last_use[which])
+        _lib.check(lib.mscs_mt19937_stream(mt.ctypes.data_as(C.c_void_p), pos, C.c_uint64(words),
+                                           self.bufs[which].data_ptr(), C.c_void_p(self.side.cuda_stream)),
+                   "mscs_mt19937_stream")
+        ev = torch.cuda.Event()
+        ev.record(self.side)
+        self.cur, self.key, self.words, self.ready = which, (mt.tobytes(), pos), words, ev
+
+    def acquire(self, mt, pos, words):
+        """Buffer holding >= words outputs from (mt,pos); the current stream is made to wait for it."""
+        if self.key != (mt.tobytes(), pos) or self.words < words:
+            self._generate(self.cur ^ 1, mt, pos, words)
+        torch.cuda.current_stream().wait_event(self.ready)
+        return self.bufs[self.cur]
+
+    def release_and_prefetch(self, mt_next, pos_next, words):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self.last_use[self.cur] = ev
+        self._generate(self.cur ^ 1, mt_next, pos_next, words)
+
+
+_stream_caches = {}
+
+
+def _stream_cache(dev):
+    c = _stream_caches.get(dev)
+    if c is None:
+        c = _stream_caches[dev] = _StreamCache(dev)
+    return c
 
 
 # ---- K1 -----------------------------------------------------------------------------------
-def sample_anchors(labels, feat_hw, spec, mt_state=None):
+def sample_anchors(labels, feat_hw, spec, mt_state=None, defer_rng=False):
     """All scales of one call.  ``feat_hw``: [(h, w)] per scale.  ``mt_state``: None = consume the
     torch CPU default generator exactly as the reference does, or an explicit (uint32[624], pos)."""
     lib = _lib.load()
@@ -149,8 +208,15 @@ def sample_anchors(labels, feat_hw, spec, mt_state=None):
             raise IndexError(f"scale {s}: a kept class has a single pixel (the reference raises here too)")
     total = sum(int(plan[s].draws) for s in range(S))
     own_rng = mt_state is None
-    mt, pos = torch_mt_state() if own_rng else (np.ascontiguousarray(mt_state[0], dtype=np.uint32), int(mt_state[1]))
-    draws = torch.empty(total + 64 + 1024, dtype=torch.int32, device=dev)
+    max_draws = int(lib.mscs_sample_max_draws(C.byref(cfg)))
+    if own_rng:
+        mt, pos = torch_mt_state()
+        draws = _stream_cache(dev).acquire(mt, pos, max_draws)
+    else:
+        mt, pos = np.ascontiguousarray(mt_state[0], dtype=np.uint32), int(mt_state[1])
+        draws = torch.empty(total + 64 + 1024, dtype=torch.int32, device=dev)
+        _lib.check(lib.mscs_mt19937_stream(mt.ctypes.data_as(C.c_void_p), pos, C.c_uint64(total),
+                                           draws.data_ptr(), st), "mscs_mt19937_stream")
     A = spec.num_classes
     # one int32 slab for every per-scale index array
     sizes = []
@@ -172,11 +238,19 @@ def sample_anchors(labels, feat_hw, spec, mt_state=None):
                                dl_h=plan[s].dl_h, dl_w=plan[s].dl_w,
                                idx_ref=v[0].view(plan[s].T, plan[s].V), pair_ref=v[1].view(plan[s].T, 2),
                                pix=v[2], cls=v[3], seg=v[4]))
-    _lib.check(lib.mscs_sample_select(C.byref(cfg), plan, mt.ctypes.data_as(C.c_void_p), pos, ws.data_ptr(),
-                                      draws.data_ptr(), *[_lib.ptr_array(a) for a in arrs], st),
-               "mscs_sample_select")
-    if own_rng:
-        torch_mt_advance(mt, pos, total)
+    _lib.check(lib.mscs_sample_select(C.byref(cfg), plan, ws.data_ptr(), draws.data_ptr(),
+                                      *[_lib.ptr_array(a) for a in arrs], st), "mscs_sample_select")
+
+    def finish_rng():
+        """Publish the generator state the reference would leave behind and start producing the
+        next call's stream.  Deferred by the caller until the tensor kernels are enqueued."""
+        if own_rng:
+            mt2, pos2 = torch_mt_advance(mt, pos, total)
+            _stream_cache(dev).release_and_prefetch(mt2, pos2, max_draws)
+
+    if defer_rng:
+        return out, finish_rng
+    finish_rng()
     return out
 
 
@@ -282,14 +356,61 @@ def sim_backward(state, sets, grad_out):
     return dFs
 
 
-def scatter_grad(dF, aset, sample, feat_shape, dtype):
+def scatter_grad(dF, aset, sample, feat_shape, dtype, prezeroed=None, slot=None):
+    """Normalisation backward + dense gradient.  With a pre-zeroed buffer and a slot map only the
+    32-byte sectors that hold a sampled pixel are rewritten; otherwise zero-fill + scatter."""
     lib = _lib.load()
     n, Cc, h, w = feat_shape
-    out = torch.empty(feat_shape, dtype=torch.float32, device=dF.device)
-    _lib.check(lib.mscs_scatter_grad(dF.data_ptr(), dF.shape[1], aset.f32.data_ptr(), aset.inv_norm.data_ptr(),
-                                     sample.pix.data_ptr(), aset.N, n, Cc, h * w, out.data_ptr(), 1, _stream()),
-               "mscs_scatter_grad")
+    if prezeroed is not None:
+        out = prezeroed
+        _lib.check(lib.mscs_scatter_sectors(dF.data_ptr(), dF.shape[1], aset.f32.data_ptr(),
+                                            aset.inv_norm.data_ptr(), slot.data_ptr(), n, Cc, h * w,
+                                            out.data_ptr(), _stream()), "mscs_scatter_sectors")
+    else:
+        out = torch.empty(feat_shape, dtype=torch.float32, device=dF.device)
+        _lib.check(lib.mscs_scatter_grad(dF.data_ptr(), dF.shape[1], aset.f32.data_ptr(), aset.inv_norm.data_ptr(),
+                                         sample.pix.data_ptr(), aset.N, n, Cc, h * w, out.data_ptr(), 1, _stream()),
+                   "mscs_scatter_grad")
     return out if dtype == torch.float32 else out.to(dtype)
+
+
+class _GradBuffers:
+    """Dense feature gradients zero-filled ahead of time on a side stream (the zero fill is the
+    largest HBM term of the whole path, SURVEY.md §8d, and does not depend on any result)."""
+    _side = {}
+
+    def __init__(self, feats, samples, needs):
+        dev = feats[0].device
+        lib = _lib.load()
+        side = self._side.get(dev)
+        if side is None:
+            side = self._side[dev] = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream()
+        self.bufs, self.slots = [], []
+        for f, smp, need in zip(feats, samples, needs):
+            n, Cc, h, w = f.shape
+            if not need or (h * w) % 8 != 0:
+                self.bufs.append(None)
+                self.slots.append(None)
+                continue
+            slot = torch.empty(n * h * w, dtype=torch.int32, device=dev)
+            _lib.check(lib.mscs_slot_map(smp.pix.data_ptr(), smp.N, n * h * w, slot.data_ptr(), _stream()),
+                       "mscs_slot_map")
+            self.bufs.append(torch.empty(f.shape, dtype=torch.float32, device=dev))
+            self.slots.append(slot)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for b in self.bufs:
+                if b is not None:
+                    b.zero_()
+                    b.record_stream(side)
+        self.ready = torch.cuda.Event()
+        self.ready.record(side)
+
+    def take(self, s):
+        """The pre-zeroed buffer of scale s (once: a second backward falls back to zero-fill)."""
+        b, self.bufs[s] = self.bufs[s], None
+        return b, self.slots[s]
 
 
 # ---- the autograd.Function ----------------------------------------------------------------
@@ -312,14 +433,18 @@ class MsCsContrastiveFn(torch.autograd.Function):
             feats32.append(f32.contiguous())
         if labels.device != feats32[0].device:
             labels = labels.to(feats32[0].device)
+        needs = [bool(ctx.needs_input_grad[4 + i]) for i in range(len(feats))]
         with torch.cuda.device(feats32[0].device):
             with _timed("sample"):
-                samples = sample_anchors(labels, [tuple(f.shape[-2:]) for f in feats32], spec)
+                samples, finish_rng = sample_anchors(labels, [tuple(f.shape[-2:]) for f in feats32], spec,
+                                                     defer_rng=True)
+            ctx.gradbufs = _GradBuffers(feats32, samples, needs) if any(needs) else None
             with _timed("gather"):
                 sets = [gather_normalize(f, s) for f, s in zip(feats32, samples)]
             state = build_job(spec, samples, sets, single_scale)
             with _timed("sim_fwd"):
                 sim_forward(state)
+            finish_rng()          # host-side generator bookkeeping, off the GPU's critical path
         holder["samples"], holder["state"] = samples, state
         ctx.samples, ctx.sets, ctx.state = samples, sets, state
         ctx.shapes = [tuple(f.shape) for f in feats]
@@ -335,9 +460,13 @@ class MsCsContrastiveFn(torch.autograd.Function):
             dFs = sim_backward(ctx.state, ctx.sets, grad_total)
             grads = []
             with _timed("scatter"):
+                if ctx.gradbufs is not None:
+                    torch.cuda.current_stream().wait_event(ctx.gradbufs.ready)
                 for s in range(len(ctx.sets)):
                     if ctx.needs_input_grad[4 + s]:
-                        grads.append(scatter_grad(dFs[s], ctx.sets[s], ctx.samples[s], ctx.shapes[s], ctx.dtypes[s]))
+                        pre, slot = ctx.gradbufs.take(s) if ctx.gradbufs is not None else (None, None)
+                        grads.append(scatter_grad(dFs[s], ctx.sets[s], ctx.samples[s], ctx.shapes[s], ctx.dtypes[s],
+                                                  pre, slot))
                     else:
                         grads.append(None)
         return (None, None, None, None, *grads)

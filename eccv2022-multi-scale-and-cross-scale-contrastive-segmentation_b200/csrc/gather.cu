@@ -78,9 +78,87 @@ k_scatter_grad(const float* __restrict__ dF, int ldF, const float* __restrict__ 
   }
 }
 
+// slot map: slot[image*plane + pixel] = sorted anchor row sampled there, or -1
+__global__ void k_slot_map(const int* __restrict__ pix, int N, int* __restrict__ slot) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) slot[pix[i]] = i;
+}
+
+// Sector writer: the dense gradient is already zero; one warp per 8-pixel octet (= one 32-byte
+// sector per channel plane) rewrites every sector that holds at least one sampled pixel with
+// full-sector stores (values + explicit zeros), so no partial-sector read-modify-write reaches HBM.
+__global__ void __launch_bounds__(256)
+k_scatter_sectors(const float* __restrict__ dF, int ldF, const float* __restrict__ anc_f32,
+                  const float* __restrict__ inv_norm, const int* __restrict__ slot, int n_octets, int C,
+                  int plane, float* __restrict__ dfeat) {
+  const int lane = threadIdx.x & 31;
+  const int oct = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (oct >= n_octets) return;
+  const int gp = oct * 8;
+  const int s_mine = (lane < 8) ? slot[gp + lane] : -1;
+  if (__ballot_sync(0xffffffffu, s_mine >= 0) == 0) return;
+  const int b = gp / plane, p = gp - b * plane;
+  float dx[8][kMaxC / 32];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int row = __shfl_sync(0xffffffffu, s_mine, j);
+    if (row >= 0) {                                   // warp-uniform
+      const float* g = dF + (size_t)row * ldF;
+      const float* f = anc_f32 + (size_t)row * C;
+      float gv[kMaxC / 32], fv[kMaxC / 32], dot = 0.f;
+#pragma unroll
+      for (int q = 0; q < kMaxC / 32; ++q) {
+        const int c = lane + 32 * q;
+        gv[q] = (c < C) ? g[c] : 0.f;
+        fv[q] = (c < C) ? f[c] : 0.f;
+        dot = fmaf(gv[q], fv[q], dot);
+      }
+      dot = warp_sum(dot);
+      const float inv = inv_norm[row];
+      const bool clamped = inv >= 1e12f;
+#pragma unroll
+      for (int q = 0; q < kMaxC / 32; ++q) dx[j][q] = (clamped ? gv[q] : (gv[q] - fv[q] * dot)) * inv;
+    } else {
+#pragma unroll
+      for (int q = 0; q < kMaxC / 32; ++q) dx[j][q] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kMaxC / 32; ++q) {
+    const int c = lane + 32 * q;
+    if (c < C) {
+      float4* dst = reinterpret_cast<float4*>(dfeat + ((size_t)b * C + c) * plane + p);
+      dst[0] = make_float4(dx[0][q], dx[1][q], dx[2][q], dx[3][q]);
+      dst[1] = make_float4(dx[4][q], dx[5][q], dx[6][q], dx[7][q]);
+    }
+  }
+}
+
 }  // namespace mscs
 
 using namespace mscs;
+
+extern "C" int mscs_slot_map(const int32_t* pix, int N, int n_pixels, int32_t* slot, void* stream_) {
+  MSCS_CHECK_ARG(pix && slot && N >= 1 && n_pixels >= 1, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream_;
+  MSCS_CUDA(cudaMemsetAsync(slot, 0xff, sizeof(int) * (size_t)n_pixels, st));
+  k_slot_map<<<ceil_div(N, 256), 256, 0, st>>>(pix, N, slot);
+  MSCS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mscs_scatter_sectors(const float* dF, int ldF, const float* anc_f32, const float* inv_norm,
+                                    const int32_t* slot, int n, int C, int plane, float* dfeat, void* stream_) {
+  MSCS_CHECK_ARG(dF && anc_f32 && inv_norm && slot && dfeat, "null pointer argument");
+  MSCS_CHECK_ARG(C >= 1 && C <= kMaxC && ldF >= C, "C=%d / ldF=%d unsupported", C, ldF);
+  MSCS_CHECK_ARG(plane % 8 == 0, "plane %d is not a multiple of 8 pixels: use mscs_scatter_grad", plane);
+  const int n_oct = n * (plane / 8);
+  k_scatter_sectors<<<ceil_div(n_oct, 8), 256, 0, (cudaStream_t)stream_>>>(dF, ldF, anc_f32, inv_norm, slot, n_oct,
+                                                                           C, plane, dfeat);
+  MSCS_LAUNCH_CHECK();
+  return 0;
+}
+
 
 extern "C" int mscs_gather_normalize(const float* feat, int n, int C, int plane, const int32_t* pix, int N,
                                      void* anc_bf16, float* anc_f32, float* inv_norm, void* stream_) {

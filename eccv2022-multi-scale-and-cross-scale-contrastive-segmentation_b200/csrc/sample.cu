@@ -6,6 +6,7 @@
 // torch.randperm on the CPU default generator (V2.py:121) = MT19937 + forward Fisher-Yates
 // (ATen, third party; restated in oracle/mt19937.py and pinned there against torch itself).
 #include "common.cuh"
+#include <string.h>
 
 namespace mscs {
 
@@ -288,31 +289,39 @@ k_mt_stream(const uint32_t* __restrict__ state, int pos, long long total, uint32
   const int tid = threadIdx.x;
   for (int i = tid; i < 624; i += 256) buf[0][i] = state[i];
   __syncthreads();
-  long long produced = 0;
   // remaining words of the current block
   for (int j = pos + tid; j < 624; j += 256) {
     long long o = j - pos;
     if (o < total) out[o] = mt_temper(buf[0][j]);
   }
-  produced = 624 - pos;
+  long long produced = 624 - pos;
   int cur = 0;
+  // every thread tempers and stores the word it has just generated: no separate output pass
   while (produced < total) {
     const uint32_t* c = buf[cur];
     uint32_t* nx = buf[cur ^ 1];
-    if (tid < 227) nx[tid] = c[tid + 397] ^ mt_twist(c[tid], c[tid + 1]);
+    uint32_t* o = out + produced;
+    const long long left = total - produced;
+    if (tid < 227) {
+      const uint32_t v = c[tid + 397] ^ mt_twist(c[tid], c[tid + 1]);
+      nx[tid] = v;
+      if (tid < left) o[tid] = mt_temper(v);
+    }
     __syncthreads();
-    if (tid < 227) { int k = 227 + tid; nx[k] = nx[tid] ^ mt_twist(c[k], c[k + 1]); }
+    if (tid < 227) {
+      const int k = 227 + tid;
+      const uint32_t v = nx[tid] ^ mt_twist(c[k], c[k + 1]);
+      nx[k] = v;
+      if (k < left) o[k] = mt_temper(v);
+    }
     __syncthreads();
     if (tid < 170) {
-      int k = 454 + tid;
-      if (k < 623) nx[k] = nx[k - 227] ^ mt_twist(c[k], c[k + 1]);
-      else nx[623] = nx[396] ^ mt_twist(c[623], nx[0]);
+      const int k = 454 + tid;
+      const uint32_t v = (k < 623) ? (nx[k - 227] ^ mt_twist(c[k], c[k + 1])) : (nx[396] ^ mt_twist(c[623], nx[0]));
+      nx[k] = v;
+      if (k < left) o[k] = mt_temper(v);
     }
     __syncthreads();
-    for (int j = tid; j < 624; j += 256) {
-      long long o = produced + j;
-      if (o < total) out[o] = mt_temper(nx[j]);
-    }
     produced += 624;
     cur ^= 1;
   }
@@ -456,19 +465,30 @@ extern "C" int mscs_plan_fetch(const mscs_scale_plan* plan_dev, mscs_scale_plan*
   return 0;
 }
 
-extern "C" int mscs_sample_select(const mscs_sample_cfg* cfg, const mscs_scale_plan* plan_host,
-                                  const uint32_t* mt_state_host, int mt_pos, void* workspace,
-                                  uint32_t* draws_dev, int32_t* const* idx_ref, int32_t* const* pair_ref,
+extern "C" int mscs_mt19937_stream(const uint32_t* mt_state_host, int mt_pos, uint64_t n_words,
+                                   uint32_t* draws_dev, void* stream_) {
+  MSCS_CHECK_ARG(mt_state_host && draws_dev, "null pointer argument");
+  MSCS_CHECK_ARG(mt_pos >= 0 && mt_pos <= 624, "mt_pos %d out of range", mt_pos);
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (n_words == 0) return 0;
+  // the 624 state words are staged behind the stream (the buffer holds n_words + 1024 words)
+  uint32_t* state_dev = draws_dev + align_up((size_t)n_words, 64);
+  MSCS_CUDA(cudaMemcpyAsync(state_dev, mt_state_host, sizeof(uint32_t) * 624, cudaMemcpyHostToDevice, st));
+  k_mt_stream<<<1, 256, 0, st>>>(state_dev, mt_pos, (long long)n_words, draws_dev);
+  MSCS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mscs_sample_select(const mscs_sample_cfg* cfg, const mscs_scale_plan* plan_host, void* workspace,
+                                  const uint32_t* draws_dev, int32_t* const* idx_ref, int32_t* const* pair_ref,
                                   int32_t* const* pix, int32_t* const* cls, int32_t* const* seg,
                                   void* stream_) {
   SampleLayout L;
   int rc = make_layout(cfg, &L);
   if (rc) return rc;
-  MSCS_CHECK_ARG(plan_host && mt_state_host && workspace && draws_dev, "null pointer argument");
-  MSCS_CHECK_ARG(mt_pos >= 0 && mt_pos <= 624, "mt_pos %d out of range", mt_pos);
+  MSCS_CHECK_ARG(plan_host && workspace && draws_dev, "null pointer argument");
   cudaStream_t st = (cudaStream_t)stream_;
   SelectArgs a;
-  long long total = 0;
   int maxT = 0, maxV = 0;
   for (int s = 0; s < L.S; ++s) {
     MSCS_CHECK_ARG(plan_host[s].error == 0, "scale %d: sampling plan reports error %d", s, plan_host[s].error);
@@ -476,16 +496,8 @@ extern "C" int mscs_sample_select(const mscs_sample_cfg* cfg, const mscs_scale_p
                    plan_host[s].V, kMaxV);
     a.draw_base[s] = plan_host[s].draw_base; a.T[s] = plan_host[s].T; a.V[s] = plan_host[s].V;
     a.idx_ref[s] = idx_ref[s]; a.pair_ref[s] = pair_ref[s]; a.pix[s] = pix[s]; a.cls[s] = cls[s]; a.seg[s] = seg[s];
-    total = plan_host[s].draw_base + plan_host[s].draws;
     if (plan_host[s].T > maxT) maxT = plan_host[s].T;
     if (plan_host[s].V > maxV) maxV = plan_host[s].V;
-  }
-  // MT19937 state -> device (624 words at the head of the draws buffer's tail: use a small async copy)
-  uint32_t* state_dev = draws_dev + align_up((size_t)total, 64);
-  MSCS_CUDA(cudaMemcpyAsync(state_dev, mt_state_host, sizeof(uint32_t) * 624, cudaMemcpyHostToDevice, st));
-  if (total > 0) {
-    k_mt_stream<<<1, 256, 0, st>>>(state_dev, mt_pos, total, draws_dev);
-    MSCS_LAUNCH_CHECK();
   }
   size_t smem = sizeof(int) * 3 * (size_t)maxV;
   if (smem > 48 * 1024)
@@ -496,22 +508,34 @@ extern "C" int mscs_sample_select(const mscs_sample_cfg* cfg, const mscs_scale_p
   return 0;
 }
 
+static inline uint32_t host_twist(uint32_t u, uint32_t v) {
+  const uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu);
+  return (y >> 1) ^ ((0u - (v & 1u)) & 0x9908b0dfu);
+}
+// one block regeneration in the three-phase form (old -> new buffer) so the compiler vectorises it
+__attribute__((target_clones("avx2", "default")))
+static void host_regen(const uint32_t* __restrict__ o, uint32_t* __restrict__ n) {
+#pragma GCC ivdep
+  for (int i = 0; i < 227; ++i) n[i] = o[i + 397] ^ host_twist(o[i], o[i + 1]);
+#pragma GCC ivdep
+  for (int i = 0; i < 227; ++i) n[227 + i] = n[i] ^ host_twist(o[227 + i], o[228 + i]);
+#pragma GCC ivdep
+  for (int i = 0; i < 169; ++i) n[454 + i] = n[227 + i] ^ host_twist(o[454 + i], o[455 + i]);
+  n[623] = n[396] ^ host_twist(o[623], n[0]);
+}
+
 extern "C" int mscs_mt19937_advance_host(uint32_t* mt, int* pos, uint64_t k) {
   MSCS_CHECK_ARG(mt && pos && *pos >= 0 && *pos <= 624, "bad MT19937 state");
-  int p = *pos;
+  uint32_t buf[2][624];
+  memcpy(buf[0], mt, sizeof(buf[0]));
+  int cur = 0, p = *pos;
   while (k > 0) {
-    if (p >= 624) {
-      // regenerate in place (the sequential form of the published algorithm)
-      for (int i = 0; i < 624; ++i) {
-        uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
-        mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-      }
-      p = 0;
-    }
-    uint64_t take = (uint64_t)(624 - p) < k ? (uint64_t)(624 - p) : k;
+    if (p >= 624) { host_regen(buf[cur], buf[cur ^ 1]); cur ^= 1; p = 0; }
+    const uint64_t take = (uint64_t)(624 - p) < k ? (uint64_t)(624 - p) : k;
     p += (int)take;
     k -= take;
   }
+  memcpy(mt, buf[cur], sizeof(buf[0]));
   *pos = p;
   return 0;
 }

@@ -308,7 +308,7 @@ extern "C" int mscs_sim_backward(const mscs_sim_job* job, const float* grad_out,
   // the backward work tables live after the two forward tables in job->work
   size_t fwd_items = 0;
   for (int t = 0; t < job->num_terms; ++t) fwd_items += (size_t)ceil_div(job->terms[t].N1, 256);
-  char* w = (char*)job->work +
+  char* w = (char*)job->work + 4096 +
             2 * (align_up(sizeof(WorkItem) * fwd_items, 64) + align_up(sizeof(int) * (fwd_items + 1), 64));
   BwdArgs args{};
   args.grad_out = grad_out;

@@ -328,7 +328,7 @@ extern "C" size_t mscs_sim_workspace_bytes(const mscs_sim_job* job) {
     items += 2 * (size_t)ceil_div(job->terms[t].N1, kFwdRows);                 // forward: two sweeps
     items += (size_t)ceil_div(job->terms[t].N1, 128) + ceil_div(job->terms[t].N2, 128);   // backward passes
   }
-  return 4096 + items * (sizeof(WorkItem) + sizeof(int)) + 3 * 64;
+  return 2 * 4096 + items * (sizeof(WorkItem) + sizeof(int)) + 16 * 64;
 }
 
 extern "C" int mscs_sim_forward(const mscs_sim_job* job, void* stream_) {
@@ -359,7 +359,7 @@ extern "C" int mscs_sim_forward(const mscs_sim_job* job, void* stream_) {
     nitems += ceil_div(m.N1, kFwdRows);
   }
   b.num_terms = job->num_terms; b.nitems = nitems; b.rows_per_item = kFwdRows;
-  char* w = (char*)job->work;
+  char* w = (char*)job->work + 4096;      // [0,4096): finalise accumulators
   for (int mode = 0; mode < 2; ++mode) {
     b.mode = mode;
     b.items = (WorkItem*)w; w += align_up(sizeof(WorkItem) * (size_t)nitems, 64);

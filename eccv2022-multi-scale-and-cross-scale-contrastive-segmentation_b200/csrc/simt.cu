@@ -15,50 +15,67 @@ struct FinTerm {
 };
 struct FinArgs { FinTerm t[MSCS_MAX_TERMS]; int num_terms; float* term_loss; float* total_loss; };
 
-// loss = mean_i(-pos_i / div_i)  (V2.py:187-188, _ms.py:148-156); coefficients for K4
-__global__ void __launch_bounds__(1024) k_finalize(const __grid_constant__ FinArgs a) {
-  __shared__ double red[32];
-  __shared__ double total;
-  if (threadIdx.x == 0) total = 0.0;
-  for (int ti = 0; ti < a.num_terms; ++ti) {
-    const FinTerm& t = a.t[ti];
-    double acc = 0.0;
-    for (int i = threadIdx.x; i < t.N1; i += blockDim.x) {
+// loss = mean_i(-pos_i / div_i)  (V2.py:187-188, _ms.py:148-156); coefficients for K4.
+// grid = (row chunks, terms): per-row work is two dependent loads deep, so it is spread over many CTAs;
+// the per-term sums are reduced in fp64 (order-insensitive to far below fp32 resolution).
+__global__ void __launch_bounds__(256) k_finalize_rows(const __grid_constant__ FinArgs a, double* acc) {
+  const FinTerm& t = a.t[blockIdx.y];
+  __shared__ double red[8];
+  double part = 0.0;
+  const int base = blockIdx.x * 1024;
+  if (base >= t.N1) return;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = base + k * 256 + threadIdx.x;
+    if (i < t.N1) {
       const int y = t.a_cls[i];
       const int P = t.k_seg[y + 1] - t.k_seg[y] - (t.self_mask ? 1 : 0);
       // single-scale: 0/0 -> NaN exactly like the reference; cross-scale: divisor max(P,1)
       const float div = t.self_mask ? (float)P : (float)max(P, 1);
-      acc += (double)(-t.pos[i] / div);
+      part += (double)(-t.pos[i] / div);
       const float invd = 1.f / (div * (float)t.N1);
       t.coef_s[i] = t.ssum[i] * invd;
       t.coef_pn[i] = t.neg[i] * invd;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double s = 0.0;
-      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
-      const float l = (float)(s / (double)t.N1);
-      a.term_loss[ti] = l;
-      total += (double)t.weight * (double)l;
-    }
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
   __syncthreads();
-  if (threadIdx.x == 0) *a.total_loss = (float)total;
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    atomicAdd(&acc[blockIdx.y], s);
+  }
 }
 
+__global__ void k_finalize_total(const __grid_constant__ FinArgs a, const double* acc) {
+  if (threadIdx.x != 0) return;
+  double total = 0.0;
+  for (int ti = 0; ti < a.num_terms; ++ti) {
+    const float l = (float)(acc[ti] / (double)a.t[ti].N1);
+    a.term_loss[ti] = l;
+    total += (double)a.t[ti].weight * (double)l;
+  }
+  *a.total_loss = (float)total;
+}
+
+// job->work: the first 4096 bytes are reserved for these accumulators (zeroed by the forward launcher)
 int launch_finalize(const mscs_sim_job* job, cudaStream_t st) {
   FinArgs a{};
   a.num_terms = job->num_terms; a.term_loss = job->term_loss; a.total_loss = job->total_loss;
+  int maxN = 0;
   for (int t = 0; t < job->num_terms; ++t) {
     const mscs_term& m = job->terms[t];
     a.t[t] = FinTerm{m.a_cls, m.k_seg, m.neg_sum, m.pos_sum, m.s_sum, m.coef_s, m.coef_pn, m.N1, m.self_mask,
                      m.weight};
+    if (m.N1 > maxN) maxN = m.N1;
   }
-  k_finalize<<<1, 1024, 0, st>>>(a);
+  double* acc = (double*)job->work;
+  MSCS_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * MSCS_MAX_TERMS, st));
+  k_finalize_rows<<<dim3(ceil_div(maxN, 1024), job->num_terms), 256, 0, st>>>(a, acc);
+  MSCS_LAUNCH_CHECK();
+  k_finalize_total<<<1, 32, 0, st>>>(a, acc);
   MSCS_LAUNCH_CHECK();
   return 0;
 }
@@ -245,7 +262,7 @@ using namespace mscs;
 extern "C" int mscs_debug_sim_forward_simt(const mscs_sim_job* job, const float* const* f32_sets, void* stream_) {
   int rc = validate_job(job);
   if (rc) return rc;
-  MSCS_CHECK_ARG(f32_sets, "f32_sets is null");
+  MSCS_CHECK_ARG(f32_sets && job->work, "f32_sets / work is null");
   cudaStream_t st = (cudaStream_t)stream_;
   for (int mode = 0; mode < 2; ++mode)
     for (int ti = 0; ti < job->num_terms; ++ti) {

@@ -79,9 +79,14 @@ int mscs_sample_plan(const mscs_sample_cfg* cfg, const int64_t* labels, void* wo
  * the reference has ~1000). */
 int mscs_plan_fetch(const mscs_scale_plan* plan_dev, mscs_scale_plan* plan_host, int num_scales,
                     void* stream);
-/* Phase 2 (async): MT19937 stream + per-pair Fisher-Yates prefix + rank->pixel selection.
- *   mt_state_host : 624 words + position (0..624) of the torch CPU generator (host memory);
- *   draws_dev     : scratch, >= total draws uint32;
+/* MT19937 output stream (async): `n_words` tempered 32-bit outputs of the generator whose state is
+ * (mt_state_host[624], mt_pos in 0..624) -- the torch CPU default generator, which the reference
+ * consumes through torch.randperm (V2.py:121).  draws_dev must hold n_words + 1024 words.  It only
+ * depends on the generator state, so the host side produces it ahead of time on a side stream. */
+int mscs_mt19937_stream(const uint32_t* mt_state_host, int mt_pos, uint64_t n_words, uint32_t* draws_dev,
+                        void* stream);
+/* Phase 2 (async): per-pair Fisher-Yates prefix + rank->pixel selection from a precomputed stream.
+ *   draws_dev : MT19937 stream starting at the generator position of this call;
  * outputs per scale s (arrays of N_s entries, N_s from the fetched plan):
  *   idx_ref[s]  : flat pixel index y*w+x in REFERENCE order k*V+v            (V2.py:122)
  *   pair_ref[s] : (T,2) int32 (image, class) in reference order              (V2.py:106-107)
@@ -89,9 +94,8 @@ int mscs_plan_fetch(const mscs_scale_plan* plan_dev, mscs_scale_plan* plan_host,
  *   cls[s]      : class id of each sorted row
  *   seg[s]      : A+1 int32, seg[c] = first sorted row of class c, seg[A] = N
  */
-int mscs_sample_select(const mscs_sample_cfg* cfg, const mscs_scale_plan* plan_host,
-                       const uint32_t* mt_state_host, int mt_pos, void* workspace,
-                       uint32_t* draws_dev, int32_t* const* idx_ref, int32_t* const* pair_ref,
+int mscs_sample_select(const mscs_sample_cfg* cfg, const mscs_scale_plan* plan_host, void* workspace,
+                       const uint32_t* draws_dev, int32_t* const* idx_ref, int32_t* const* pair_ref,
                        int32_t* const* pix, int32_t* const* cls, int32_t* const* seg, void* stream);
 /* host helper: advance an MT19937 state by k draws exactly as at::mt19937 does */
 int mscs_mt19937_advance_host(uint32_t* mt_state_host, int* mt_pos, uint64_t k);
@@ -165,6 +169,15 @@ int mscs_debug_sim_backward_simt(const mscs_sim_job* job, const float* const* f3
 int mscs_scatter_grad(const float* dF, int ldF, const float* anc_f32, const float* inv_norm,
                       const int32_t* pix, int N, int n, int C, int plane, float* dfeat,
                       int zero_fill, void* stream);
+
+/* Fast path of the scatter when the caller has ALREADY zero-filled dfeat (the host side does that
+ * on a side stream while the tensor kernels run) and plane % 8 == 0:
+ *   mscs_slot_map        slot[image*plane + pixel] = sorted anchor row sampled there, else -1
+ *   mscs_scatter_sectors rewrites, with full 32-byte sector stores, only the sectors of dfeat that
+ *                        hold a sampled pixel (same maths as mscs_scatter_grad). */
+int mscs_slot_map(const int32_t* pix, int N, int n_pixels, int32_t* slot, void* stream);
+int mscs_scatter_sectors(const float* dF, int ldF, const float* anc_f32, const float* inv_norm,
+                         const int32_t* slot, int n, int C, int plane, float* dfeat, void* stream);
 
 #ifdef __cplusplus
 }
