@@ -76,8 +76,22 @@ class ScaleSample:
     seg: torch.Tensor        # (A+1,) int32 class segments of the sorted rows
 
 
+_stream_override = [None]
+
+
 def _stream():
+    """cudaStream_t of the current torch stream (looked up once per forward/backward call)."""
+    if _stream_override[0] is not None:
+        return _stream_override[0]
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _pin_stream:
+    def __enter__(self):
+        _stream_override[0] = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def __exit__(self, *exc):
+        _stream_override[0] = None
 
 
 def _require_device(t):
@@ -434,7 +448,7 @@ class MsCsContrastiveFn(torch.autograd.Function):
         if labels.device != feats32[0].device:
             labels = labels.to(feats32[0].device)
         needs = [bool(ctx.needs_input_grad[4 + i]) for i in range(len(feats))]
-        with torch.cuda.device(feats32[0].device):
+        with torch.cuda.device(feats32[0].device), _pin_stream():
             with _timed("sample"):
                 samples, finish_rng = sample_anchors(labels, [tuple(f.shape[-2:]) for f in feats32], spec,
                                                      defer_rng=True)
@@ -456,7 +470,7 @@ class MsCsContrastiveFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_total, _grad_terms):
-        with torch.cuda.device(ctx.sets[0].bf16.device):
+        with torch.cuda.device(ctx.sets[0].bf16.device), _pin_stream():
             dFs = sim_backward(ctx.state, ctx.sets, grad_total)
             grads = []
             with _timed("scatter"):

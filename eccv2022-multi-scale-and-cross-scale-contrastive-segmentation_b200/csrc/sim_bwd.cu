@@ -13,8 +13,9 @@
 //
 // CTA = 128 rows (X tile resident in smem) x a run of 128-column tiles.  Per tile:
 //   MMA 1  S = X Y^T              (both K-major)        -> TMEM, double buffered
-//   epilogue: W = f(exp2(S)) as bf16 into smem (128-byte swizzled, K-major A operand)
-//   MMA 2  dX += W Y              (Y tile re-used from smem as an MN-major B operand) -> TMEM
+//   epilogue: W = f(exp2(S)) as packed bf16 written back INTO the S columns of TMEM (in place)
+//   MMA 2  dX += W Y              (A operand = W from TMEM; Y tile re-used from smem as an
+//                                  MN-major B operand) -> TMEM
 // dX stays in TMEM for the whole run and is flushed with fp32 reductions at the end.
 #include "sim_tc.cuh"
 
@@ -38,7 +39,7 @@ struct BwdArgs {
 };
 
 __host__ __device__ constexpr size_t bwd_smem_bytes(int KB) {
-  return 1024 + (size_t)(3 * KB + 2) * kBlkBytes + 3 * 128 * sizeof(float) + 256;
+  return 1024 + (size_t)(3 * KB) * kBlkBytes + 3 * 128 * sizeof(float) + 256;
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -60,13 +61,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;                                         // [KB][128][128 B]   X tile
   uint8_t* smB = smA + (size_t)KB * kBlkBytes;                 // [2][KB][128][128 B] Y tiles
-  uint8_t* smW = smB + (size_t)2 * KB * kBlkBytes;             // [2][128][128 B]    W halves (64 columns each)
-  float* cstat = reinterpret_cast<float*>(smW + 2 * kBlkBytes);   // [3][128] column coefficients
+  float* cstat = reinterpret_cast<float*>(smB + (size_t)2 * KB * kBlkBytes);   // [3][128] column coefficients
   uint64_t* bars = reinterpret_cast<uint64_t*>(cstat + 3 * 128);
   uint64_t* a_full = bars;        uint64_t* a_empty = bars + 1;
   uint64_t* b_full = bars + 2;    uint64_t* b_empty = bars + 4;     // [2]
-  uint64_t* s_full = bars + 6;    uint64_t* s_empty = bars + 8;     // [2]
-  uint64_t* w_full = bars + 10;   uint64_t* w_empty = bars + 12;    // [2]
+  uint64_t* s_full = bars + 6;                                      // [2]
+  uint64_t* w_full = bars + 10;                                     // [2] (per 64-column half)
   uint64_t* df_full = bars + 14;  uint64_t* df_empty = bars + 15;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
@@ -75,8 +75,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
     ptx::mbar_init(a_full, 1); ptx::mbar_init(a_empty, 1);
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1);
-      ptx::mbar_init(&s_full[i], 1); ptx::mbar_init(&s_empty[i], 8);
-      ptx::mbar_init(&w_full[i], 4); ptx::mbar_init(&w_empty[i], 1);
+      ptx::mbar_init(&s_full[i], 1);
+      ptx::mbar_init(&w_full[i], 4);
     }
     ptx::mbar_init(df_full, 1); ptx::mbar_init(df_empty, 8);
     ptx::fence_barrier_init();
@@ -116,14 +116,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
       // ================= MMA issuer =================
       constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, kTileN, 0, 0);   // S  = X Y^T
       constexpr uint32_t idesc_d = ptx::umma_idesc_bf16(128, CP, 0, 1);       // dX += W Y (B MN-major)
-      const uint32_t a_addr = ptx::smem_u32(smA), b_addr = ptx::smem_u32(smB), w_addr = ptx::smem_u32(smW);
+      const uint32_t a_addr = ptx::smem_u32(smA), b_addr = ptx::smem_u32(smB);
       Walker wk(args.work);
       Segment sg;
       uint32_t a_phase = 0, it = 0, seg = 0;
       auto issue_s = [&](uint32_t cur) {
         const uint32_t st = cur & 1, ph = (cur >> 1) & 1;
+        // S buffer `st` also holds W of tile cur-2: its consumer (the dX MMAs of tile cur-2) was issued
+        // before this point and tcgen05.mma executes in issue order, so no extra barrier is needed
         ptx::mbar_wait(&b_full[st], ph);
-        ptx::mbar_wait(&s_empty[st], ph ^ 1);
         ptx::tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb)
@@ -150,13 +151,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
             ptx::tc_fence_after();
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint64_t ad = ptx::umma_desc_sw128(w_addr + h * kBlkBytes + k * 32, 16, 1024);
+              // W of column half h lives in columns [64h, 64h+32) of S buffer st, 8 columns per K=16 slice
+              const uint32_t a_tm = tmem_base + st * 128 + h * 64 + k * 8;
               // Y rows h*64 + k*16 .. +16 are the K slice; LBO = next 64-channel block, SBO = next 8 K rows
               const uint64_t bd = ptx::umma_desc_sw128(b_addr + st * KB * kBlkBytes + (h * 64 + k * 16) * 128,
                                                        kBlkBytes, 1024);
-              ptx::umma_ss(tmem_dF, ad, bd, idesc_d, (j | h | k) != 0);
+              ptx::umma_ts(tmem_dF, a_tm, bd, idesc_d, (j | h | k) != 0);
             }
-            ptx::umma_commit(&w_empty[h]);
           }
           ptx::umma_commit(&b_empty[st]);
         }
@@ -171,7 +172,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
     const int wg_tid = threadIdx.x - (4 + 4 * h) * 32;      // 0..127 inside the column-half group
     const int r_loc = quad * 32 + lane;                     // row inside the tile = TMEM lane
     float* cs_s = cstat; float* cs_pn = cstat + 128; float* cs_neg = cstat + 256;
-    uint8_t* wrow = smW + (size_t)h * kBlkBytes + (size_t)r_loc * 128;
     const float gout = *args.grad_out;
     Walker wk(args.work);
     Segment sg;
@@ -207,7 +207,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
         }
         named_bar_sync(1 + h, 128);
         ptx::mbar_wait(&s_full[buf], (it >> 1) & 1);
-        ptx::mbar_wait(&w_empty[h], (it & 1) ^ 1);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128 + h * 64;
         const bool touches = !(cb + 64 <= wmin || cb >= wmax);
@@ -242,18 +241,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
               packed[c >> 1] = pack_bf16(w[0], w[1]);
             }
           }
-          // 32 columns = 4 chunks of 16 B; 128-byte swizzle: chunk index XOR (row & 7)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int chunk = (part * 4 + q) ^ (r_loc & 7);
-            *reinterpret_cast<uint4*>(wrow + chunk * 16) =
-                make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
-          }
+          // 32 logits -> 16 packed columns, written over S columns this thread has already read
+          ptx::tmem_st16(taddr + part * 16, packed);
         }
-        ptx::fence_proxy_async_smem();
+        ptx::tmem_st_wait();
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) { ptx::mbar_arrive(&s_empty[buf]); ptx::mbar_arrive(&w_full[h]); }
+        if (lane == 0) ptx::mbar_arrive(&w_full[h]);
       }
       // ---- flush dX: this group drains channel half h ----
       ptx::mbar_wait(df_full, seg & 1);
