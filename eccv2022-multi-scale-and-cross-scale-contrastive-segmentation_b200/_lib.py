@@ -42,6 +42,7 @@ _SIGNATURES = {
     "mscs_version": (C.c_char_p, []),
     "mscs_last_error": (C.c_char_p, []),
     "mscs_device_ok": (C.c_int, []),
+    "mscs_debug_trap_info": (C.c_int, [C.c_char_p, C.c_int]),
     "mscs_sample_workspace_bytes": (C.c_size_t, [C.POINTER(SampleCfg)]),
     "mscs_sample_max_draws": (C.c_size_t, [C.POINTER(SampleCfg)]),
     "mscs_sample_plan": (C.c_int, [C.POINTER(SampleCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -84,10 +85,16 @@ def load():
     return _lib
 
 
+def trap_info():
+    buf = C.create_string_buffer(4096)
+    n = load().mscs_debug_trap_info(buf, 4096)
+    return buf.value.decode() if n > 0 else ""
+
+
 def check(rc, what):
     if rc != 0:
         msg = load().mscs_last_error().decode()
-        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg} {trap_info()}")
 
 
 def ptr_array(ptrs):

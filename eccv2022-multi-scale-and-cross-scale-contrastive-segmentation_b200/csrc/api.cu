@@ -13,6 +13,37 @@ void set_error(const char* fmt, ...) {
 const char* get_error() { return g_err; }
 }  // namespace mscs
 
+static unsigned long long* g_trap_host = nullptr;
+static unsigned long long* g_trap_dev = nullptr;
+
+// host-mapped deadlock-report buffer shared by the tensor kernels (allocated on first use)
+namespace mscs {
+int trap_buffer_device_ptr(unsigned long long** out) {
+  if (!g_trap_host) {
+    unsigned long long* h = nullptr;
+    MSCS_CUDA(cudaHostAlloc((void**)&h, 64 * sizeof(unsigned long long), cudaHostAllocMapped));
+    memset(h, 0, 64 * sizeof(unsigned long long));
+    MSCS_CUDA(cudaHostGetDevicePointer((void**)&g_trap_dev, h, 0));
+    g_trap_host = h;
+  }
+  *out = g_trap_dev;
+  return 0;
+}
+}  // namespace mscs
+
+extern "C" int mscs_debug_trap_info(char* out, int len) {
+  if (!out || len <= 0) return -1;
+  out[0] = 0;
+  if (!g_trap_host || g_trap_host[0] == 0) return 0;
+  int n = (int)(g_trap_host[0] < 63 ? g_trap_host[0] : 63), off = 0;
+  for (int i = 0; i < n && off < len - 64; ++i) {
+    const unsigned long long r = g_trap_host[1 + i];
+    off += snprintf(out + off, len - off, "[block %llu thread %llu tag %llu parity %llu] ", r >> 40, (r >> 24) & 0xffff,
+                    (r >> 8) & 0xffff, r & 1);
+  }
+  return n;
+}
+
 extern "C" const char* mscs_version(void) { return "mscs 0.1.0 (sm_100a, tcgen05/TMA)"; }
 extern "C" const char* mscs_last_error(void) { return mscs::get_error(); }
 extern "C" int mscs_device_ok(void) {

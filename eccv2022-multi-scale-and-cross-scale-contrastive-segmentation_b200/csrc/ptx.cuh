@@ -38,9 +38,34 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Deadlock guard: a wait that does not complete within ~2 s records (block, thread, tag, parity)
+// in a host-mapped buffer and traps, so a protocol bug surfaces as a launch error with a
+// diagnosis instead of hanging the GPU.  (The record is readable after the trap: it lives in
+// pinned host memory, see mscs_debug_trap_info.)
+static __device__ unsigned long long* g_trap_buf = nullptr;   // one copy per translation unit
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, uint32_t tag) {
+  const unsigned long long t0 = globaltimer_ns();
   while (!mbar_try_wait(bar, parity)) {
+    if (globaltimer_ns() - t0 > 2000000000ull) {
+      if (g_trap_buf != nullptr) {
+        const unsigned long long slot = atomicAdd(&g_trap_buf[0], 1ull);
+        if (slot < 63)
+          g_trap_buf[1 + slot] = ((unsigned long long)blockIdx.x << 40) | ((unsigned long long)threadIdx.x << 24) |
+                                 ((unsigned long long)(tag & 0xffffu) << 8) | (parity & 1u);
+        __threadfence_system();
+      }
+      __trap();
+    }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity, tag);
 }
 
 // ---- fences -----------------------------------------------------------------------------

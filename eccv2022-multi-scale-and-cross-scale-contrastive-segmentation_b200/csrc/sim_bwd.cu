@@ -66,7 +66,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
   uint64_t* a_full = bars;        uint64_t* a_empty = bars + 1;
   uint64_t* b_full = bars + 2;    uint64_t* b_empty = bars + 4;     // [2]
   uint64_t* s_full = bars + 6;                                      // [2]
-  uint64_t* w_full = bars + 10;                                     // [2] (per 64-column half)
+  uint64_t* w_full = bars + 10;                                     // [2 halves][2 S buffers]: one phase per
+                                                                    // two tiles, so a column-half group that runs a
+                                                                    // tile ahead of the MMA thread cannot overrun it
   uint64_t* df_full = bars + 14;  uint64_t* df_empty = bars + 15;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1);
       ptx::mbar_init(&s_full[i], 1);
-      ptx::mbar_init(&w_full[i], 4);
+      ptx::mbar_init(&w_full[i], 4); ptx::mbar_init(&w_full[2 + i], 4);
     }
     ptx::mbar_init(df_full, 1); ptx::mbar_init(df_empty, 8);
     ptx::fence_barrier_init();
@@ -96,14 +98,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
       uint32_t a_phase = 0, it = 0;
       while (wk.next(sg)) {
         const BwdDev& p = args.p[sg.owner];
-        ptx::mbar_wait(a_empty, a_phase ^ 1);
+        ptx::mbar_wait(a_empty, a_phase ^ 1, 201);
         ptx::mbar_expect_tx(a_full, KB * kBlkBytes);
         for (int kb = 0; kb < KB; ++kb)
           ptx::tma_load_2d(smA + (size_t)kb * kBlkBytes, &args.maps[p.x_map], a_full, kb * kKBlk, sg.rb * 128);
         a_phase ^= 1;
         for (int ct = sg.c_begin; ct < sg.c_end; ++ct, ++it) {
           const uint32_t st = it & 1;
-          ptx::mbar_wait(&b_empty[st], ((it >> 1) & 1) ^ 1);
+          ptx::mbar_wait(&b_empty[st], ((it >> 1) & 1) ^ 1, 202);
           ptx::mbar_expect_tx(&b_full[st], KB * kBlkBytes);
           for (int kb = 0; kb < KB; ++kb)
             ptx::tma_load_2d(smB + (size_t)(st * KB + kb) * kBlkBytes, &args.maps[p.y_map], &b_full[st],
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
         const uint32_t st = cur & 1, ph = (cur >> 1) & 1;
         // S buffer `st` also holds W of tile cur-2: its consumer (the dX MMAs of tile cur-2) was issued
         // before this point and tcgen05.mma executes in issue order, so no extra barrier is needed
-        ptx::mbar_wait(&b_full[st], ph);
+        ptx::mbar_wait(&b_full[st], ph, 211);
         ptx::tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb)
@@ -137,8 +139,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
         ptx::umma_commit(&s_full[st]);
       };
       while (wk.next(sg)) {
-        ptx::mbar_wait(a_full, a_phase); a_phase ^= 1;
-        ptx::mbar_wait(df_empty, (seg & 1) ^ 1);
+        ptx::mbar_wait(a_full, a_phase, 212); a_phase ^= 1;
+        ptx::mbar_wait(df_empty, (seg & 1) ^ 1, 213);
         ptx::tc_fence_after();
         const int ntiles = sg.c_end - sg.c_begin;
         issue_s(it);
@@ -147,7 +149,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
           if (j + 1 < ntiles) issue_s(cur + 1);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            ptx::mbar_wait(&w_full[h], cur & 1);
+            ptx::mbar_wait(&w_full[h * 2 + st], (cur >> 1) & 1, 214 + h);
             ptx::tc_fence_after();
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
           cs_neg[h * 64 + wg_tid] = (ok && p.col_neg) ? p.col_neg[c] : 1.f;
         }
         named_bar_sync(1 + h, 128);
-        ptx::mbar_wait(&s_full[buf], (it >> 1) & 1);
+        ptx::mbar_wait(&s_full[buf], (it >> 1) & 1, 221);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128 + h * 64;
         const bool touches = !(cb + 64 <= wmin || cb >= wmax);
@@ -247,10 +249,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&w_full[h]);
+        if (lane == 0) ptx::mbar_arrive(&w_full[h * 2 + buf]);
       }
       // ---- flush dX: this group drains channel half h ----
-      ptx::mbar_wait(df_full, seg & 1);
+      ptx::mbar_wait(df_full, seg & 1, 222);
       ptx::tc_fence_after();
       const float sc = p.out_scale * gout;
       float* drow = p.dF + (size_t)row * p.ld;
@@ -285,6 +287,7 @@ using namespace mscs;
 template <int KB>
 static int launch_bwd(const BwdArgs& args, cudaStream_t st) {
   const size_t smem = bwd_smem_bytes(KB);
+  if (int rc = ensure_trap_buffer()) return rc;
   MSCS_CUDA(cudaFuncSetAttribute(k_sim_bwd<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_sim_bwd<KB><<<sm_count(), kBwdThreads, smem, st>>>(args);
   MSCS_LAUNCH_CHECK();

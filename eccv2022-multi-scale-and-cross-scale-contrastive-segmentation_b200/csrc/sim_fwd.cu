@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
       int stage = 0; uint32_t phase = 0, a_phase = 0;
       while (wk.next(sg)) {
         const FwdTerm& t = args.t[sg.owner];
-        ptx::mbar_wait(a_empty, a_phase ^ 1);
+        ptx::mbar_wait(a_empty, a_phase ^ 1, 101);
         ptx::mbar_expect_tx(a_full, 2 * KB * kBlkBytes);
         for (int h = 0; h < 2; ++h)
           for (int kb = 0; kb < KB; ++kb)
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
         a_phase ^= 1;
         for (int ct = sg.c_begin; ct < sg.c_end; ++ct)
           for (int kb = 0; kb < KB; ++kb) {
-            ptx::mbar_wait(&b_empty[stage], phase ^ 1);
+            ptx::mbar_wait(&b_empty[stage], phase ^ 1, 102);
             ptx::mbar_expect_tx(&b_full[stage], kBlkBytes);
             ptx::tma_load_2d(smB + (size_t)stage * kBlkBytes, &args.maps[t.k_map], &b_full[stage], kb * kKBlk,
                              ct * kTileN);
@@ -99,14 +99,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
       int stage = 0; uint32_t phase = 0, a_phase = 0, it = 0;
       const uint32_t a_addr = ptx::smem_u32(smA), b_addr = ptx::smem_u32(smB);
       while (wk.next(sg)) {
-        ptx::mbar_wait(a_full, a_phase); a_phase ^= 1;
+        ptx::mbar_wait(a_full, a_phase, 111); a_phase ^= 1;
         ptx::tc_fence_after();
         for (int ct = sg.c_begin; ct < sg.c_end; ++ct, ++it) {
           const uint32_t buf = it & 1;
-          ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
+          ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1, 112);
           ptx::tc_fence_after();
           for (int kb = 0; kb < KB; ++kb) {
-            ptx::mbar_wait(&b_full[stage], phase);
+            ptx::mbar_wait(&b_full[stage], phase, 113);
             ptx::tc_fence_after();
             // alternate the two row halves: consecutive MMAs then accumulate into different TMEM tiles,
             // which hides the accumulate-to-accumulate dependency (measured: 114 -> 80 cycles per
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
       float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;   // MODE 0: 4 partial sums; MODE 1: acc0 = pos (log2 units), acc1 = S
       for (int ct = sg.c_begin; ct < sg.c_end; ++ct, ++it) {
         const uint32_t buf = it & 1;
-        ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1);
+        ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1, 121);
         ptx::tc_fence_after();
         const int cb = ct * kTileN;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (buf * 2 + half) * 128;
@@ -309,6 +309,7 @@ int sm_count() {
 template <int KB>
 static int launch_fwd(const FwdArgs& args, int mode, cudaStream_t st) {
   const size_t smem = fwd_smem_bytes(KB);
+  if (int rc = ensure_trap_buffer()) return rc;
   if (mode == 0) {
     MSCS_CUDA(cudaFuncSetAttribute(k_sim_fwd<KB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_sim_fwd<KB, 0><<<sm_count(), kFwdThreads, smem, st>>>(args);

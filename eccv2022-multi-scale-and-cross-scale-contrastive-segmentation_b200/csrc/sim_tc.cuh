@@ -48,6 +48,17 @@ struct Walker {
 struct BuildTerm { const int* a_cls; const int* k_seg; int N1, N2, item_base; };
 struct BuildArgs { BuildTerm t[MSCS_MAX_PASSES]; int num_terms, nitems, rows_per_item, mode; WorkItem* items; int* prefix; };
 int launch_build_work(const BuildArgs& b, cudaStream_t st);
+int trap_buffer_device_ptr(unsigned long long** out);
+// each translation unit with tensor kernels installs the buffer into its own g_trap_buf copy
+static inline int ensure_trap_buffer() {
+  static bool done = false;
+  if (done) return 0;
+  unsigned long long* d = nullptr;
+  if (int rc = trap_buffer_device_ptr(&d)) return rc;
+  MSCS_CUDA(cudaMemcpyToSymbol(ptx::g_trap_buf, &d, sizeof(d)));
+  done = true;
+  return 0;
+}
 int sm_count();
 
 // TMA tensor map for a row-major (rows, C_pad) bf16 matrix, box = {64 elements, 128 rows}, 128B swizzle

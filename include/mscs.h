@@ -33,6 +33,9 @@ extern "C" {
 /* library info ------------------------------------------------------------------------- */
 const char* mscs_version(void);
 const char* mscs_last_error(void);
+/* after a launch failure: textual record of barrier waits that timed out inside the tensor kernels
+ * (block, thread, wait tag); returns the number of records */
+int mscs_debug_trap_info(char* out, int len);
 /* 1 if a CUDA device with compute capability 10.x is present */
 int mscs_device_ok(void);
 

@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
 echo "== stage 1: sampling / gather / SIMT" | tee gpurun_out/stage1.log
-timeout -s KILL 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -s --timeout 600 \
+timeout -s KILL 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -s --timeout 200 \
   -k "sampling or gather or simt" >> gpurun_out/stage1.log 2>&1
 echo "stage1 exit $?" | tee -a gpurun_out/stage1.log
 tail -5 gpurun_out/stage1.log
@@ -14,7 +14,7 @@ timeout -s KILL 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -s --tim
 echo "stage2 exit $?" | tee -a gpurun_out/stage2.log
 tail -30 gpurun_out/stage2.log
 echo "== stage 3: end to end" | tee gpurun_out/stage3.log
-timeout -s KILL 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -s --timeout 300 \
+timeout -s KILL 240 python -m pytest tests/test_gpu_parity.py -m gpu -q -s --timeout 120 \
   -k "end_to_end or properties" >> gpurun_out/stage3.log 2>&1
 echo "stage3 exit $?" | tee -a gpurun_out/stage3.log
 tail -30 gpurun_out/stage3.log
