@@ -6,7 +6,7 @@ import os
 MAX_SCALES, MAX_TERMS = 8, 16
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmscs.so")
+LIB_PATH = os.environ.get("MSCS_LIB") or os.path.join(_HERE, "libmscs.so")   # MSCS_LIB: profiling build
 
 
 class SampleCfg(C.Structure):
@@ -43,6 +43,8 @@ _SIGNATURES = {
     "mscs_last_error": (C.c_char_p, []),
     "mscs_device_ok": (C.c_int, []),
     "mscs_debug_trap_info": (C.c_int, [C.c_char_p, C.c_int]),
+    "mscs_debug_wait_profile_fwd": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mscs_debug_wait_profile_bwd": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mscs_sample_workspace_bytes": (C.c_size_t, [C.POINTER(SampleCfg)]),
     "mscs_sample_max_draws": (C.c_size_t, [C.POINTER(SampleCfg)]),
     "mscs_sample_plan": (C.c_int, [C.POINTER(SampleCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -13,6 +13,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// one lane of a fully active warp (elect.sync): ptxas then knows exactly one lane runs the guarded
+// uniform-datapath instructions (UTCHMMA / UTMALDG) and emits no per-instruction broadcast loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -43,6 +55,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // diagnosis instead of hanging the GPU.  (The record is readable after the trap: it lives in
 // pinned host memory, see mscs_debug_trap_info.)
 static __device__ unsigned long long* g_trap_buf = nullptr;   // one copy per translation unit
+// wait profile: nanoseconds spent in the slow path of mbar_wait per tag (tag % 32), summed over all threads
+static __device__ unsigned long long g_wait_ns[32];
+static __device__ unsigned long long g_wait_cnt[32];
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -62,10 +77,21 @@ static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parit
       __trap();
     }
   }
+#ifndef MSCS_WAIT_PROFILE
+  atomicAdd(&g_wait_ns[tag & 31], globaltimer_ns() - t0);
+  atomicAdd(&g_wait_cnt[tag & 31], 1ull);
+#endif
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
+#ifdef MSCS_WAIT_PROFILE     // profiling build (make prof): time every wait, including the first probe
+  const unsigned long long t0 = globaltimer_ns();
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, 0);
+  atomicAdd(&g_wait_ns[tag & 31], globaltimer_ns() - t0);
+  atomicAdd(&g_wait_cnt[tag & 31], 1ull);
+#else
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(bar, parity, tag);
+#endif
 }
 
 // ---- fences -----------------------------------------------------------------------------

@@ -90,22 +90,25 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_dF = tmem_base + 256;
 
+  // Roles 0 and 1 run on the whole warp with warp-uniform control flow; one lane issues (see sim_fwd.cu)
   if (warp == 0) {
-    if (lane == 0) {
-      // ================= TMA producer =================
-      Walker wk(args.work);
-      Segment sg;
-      uint32_t a_phase = 0, it = 0;
-      while (wk.next(sg)) {
-        const BwdDev& p = args.p[sg.owner];
-        ptx::mbar_wait(a_empty, a_phase ^ 1, 201);
+    // ================= TMA producer =================
+    Walker wk(args.work);
+    Segment sg;
+    uint32_t a_phase = 0, it = 0;
+    while (wk.next(sg)) {
+      const BwdDev& p = args.p[sg.owner];
+      ptx::mbar_wait(a_empty, a_phase ^ 1, 201);
+      if (ptx::elect_one()) {
         ptx::mbar_expect_tx(a_full, KB * kBlkBytes);
         for (int kb = 0; kb < KB; ++kb)
           ptx::tma_load_2d(smA + (size_t)kb * kBlkBytes, &args.maps[p.x_map], a_full, kb * kKBlk, sg.rb * 128);
-        a_phase ^= 1;
-        for (int ct = sg.c_begin; ct < sg.c_end; ++ct, ++it) {
-          const uint32_t st = it & 1;
-          ptx::mbar_wait(&b_empty[st], ((it >> 1) & 1) ^ 1, 202);
+      }
+      a_phase ^= 1;
+      for (int ct = sg.c_begin; ct < sg.c_end; ++ct, ++it) {
+        const uint32_t st = it & 1;
+        ptx::mbar_wait(&b_empty[st], ((it >> 1) & 1) ^ 1, 202);
+        if (ptx::elect_one()) {
           ptx::mbar_expect_tx(&b_full[st], KB * kBlkBytes);
           for (int kb = 0; kb < KB; ++kb)
             ptx::tma_load_2d(smB + (size_t)(st * KB + kb) * kBlkBytes, &args.maps[p.y_map], &b_full[st],
@@ -114,20 +117,20 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================= MMA issuer =================
-      constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, kTileN, 0, 0);   // S  = X Y^T
-      constexpr uint32_t idesc_d = ptx::umma_idesc_bf16(128, CP, 0, 1);       // dX += W Y (B MN-major)
-      const uint32_t a_addr = ptx::smem_u32(smA), b_addr = ptx::smem_u32(smB);
-      Walker wk(args.work);
-      Segment sg;
-      uint32_t a_phase = 0, it = 0, seg = 0;
-      auto issue_s = [&](uint32_t cur) {
-        const uint32_t st = cur & 1, ph = (cur >> 1) & 1;
-        // S buffer `st` also holds W of tile cur-2: its consumer (the dX MMAs of tile cur-2) was issued
-        // before this point and tcgen05.mma executes in issue order, so no extra barrier is needed
-        ptx::mbar_wait(&b_full[st], ph, 211);
-        ptx::tc_fence_after();
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, kTileN, 0, 0);   // S  = X Y^T
+    constexpr uint32_t idesc_d = ptx::umma_idesc_bf16(128, CP, 0, 1);       // dX += W Y (B MN-major)
+    const uint32_t a_addr = ptx::smem_u32(smA), b_addr = ptx::smem_u32(smB);
+    Walker wk(args.work);
+    Segment sg;
+    uint32_t a_phase = 0, it = 0, seg = 0;
+    auto issue_s = [&](uint32_t cur) {
+      const uint32_t st = cur & 1, ph = (cur >> 1) & 1;
+      // S buffer `st` also holds W of tile cur-2: its consumer (the dX MMAs of tile cur-2) was issued
+      // before this point and tcgen05.mma executes in issue order, so no extra barrier is needed
+      ptx::mbar_wait(&b_full[st], ph, 211);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
@@ -137,20 +140,23 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
             ptx::umma_ss(tmem_base + st * 128, ad, bd, idesc_s, (kb | k) != 0);
           }
         ptx::umma_commit(&s_full[st]);
-      };
-      while (wk.next(sg)) {
-        ptx::mbar_wait(a_full, a_phase, 212); a_phase ^= 1;
-        ptx::mbar_wait(df_empty, (seg & 1) ^ 1, 213);
-        ptx::tc_fence_after();
-        const int ntiles = sg.c_end - sg.c_begin;
-        issue_s(it);
-        for (int j = 0; j < ntiles; ++j) {
-          const uint32_t cur = it + j, st = cur & 1;
-          if (j + 1 < ntiles) issue_s(cur + 1);
+      }
+      __syncwarp();
+    };
+    while (wk.next(sg)) {
+      ptx::mbar_wait(a_full, a_phase, 212); a_phase ^= 1;
+      ptx::mbar_wait(df_empty, (seg & 1) ^ 1, 213);
+      ptx::tc_fence_after();
+      const int ntiles = sg.c_end - sg.c_begin;
+      issue_s(it);
+      for (int j = 0; j < ntiles; ++j) {
+        const uint32_t cur = it + j, st = cur & 1;
+        if (j + 1 < ntiles) issue_s(cur + 1);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            ptx::mbar_wait(&w_full[h * 2 + st], (cur >> 1) & 1, 214 + h);
-            ptx::tc_fence_after();
+        for (int h = 0; h < 2; ++h) {
+          ptx::mbar_wait(&w_full[h * 2 + st], (cur >> 1) & 1, 214 + h);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               // W of column half h lives in columns [64h, 64h+32) of S buffer st, 8 columns per K=16 slice
@@ -161,12 +167,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
               ptx::umma_ts(tmem_dF, a_tm, bd, idesc_d, (j | h | k) != 0);
             }
           }
-          ptx::umma_commit(&b_empty[st]);
+          __syncwarp();
         }
-        ptx::umma_commit(df_full);
-        ptx::umma_commit(a_empty);
-        it += ntiles; ++seg;
+        if (ptx::elect_one()) ptx::umma_commit(&b_empty[st]);
+        __syncwarp();
       }
+      if (ptx::elect_one()) { ptx::umma_commit(df_full); ptx::umma_commit(a_empty); }
+      __syncwarp();
+      it += ntiles; ++seg;
     }
   } else if (warp >= 4) {
     // ================= epilogue: thread = (row, 64-column half) =================
@@ -303,9 +311,13 @@ extern "C" int mscs_sim_backward(const mscs_sim_job* job, const float* grad_out,
   BwdPass passes[MSCS_MAX_PASSES];
   const int np = build_passes(job, passes);
   // the backward work tables live after the two forward tables in job->work
-  size_t fwd_items = 0;
-  for (int t = 0; t < job->num_terms; ++t) fwd_items += (size_t)ceil_div(job->terms[t].N1, 256);
-  char* w = (char*)job->work + 4096 +
+  size_t fwd_items = 0, ranges = 0;
+  for (int t = 0; t < job->num_terms; ++t) {
+    fwd_items += (size_t)ceil_div(job->terms[t].N2, 256);
+    ranges += align_up(sizeof(int2) * (size_t)job->terms[t].N1, 64) +
+              align_up(sizeof(int2) * (size_t)ceil_div(job->terms[t].N1, 128) * 4, 64);
+  }
+  char* w = (char*)job->work + 4096 + ranges +
             2 * (align_up(sizeof(WorkItem) * fwd_items, 64) + align_up(sizeof(int) * (fwd_items + 1), 64));
   BwdArgs args{};
   args.grad_out = grad_out;
@@ -344,4 +356,15 @@ extern "C" int mscs_sim_backward(const mscs_sim_job* job, const float* grad_out,
     case 3: return launch_bwd<3>(args, st);
     default: return launch_bwd<4>(args, st);
   }
+}
+
+// debug: read and reset the barrier wait profile of this translation unit (ns and count per tag % 32)
+extern "C" int mscs_debug_wait_profile_bwd(unsigned long long* ns_out, unsigned long long* cnt_out) {
+  MSCS_CUDA(cudaDeviceSynchronize());
+  MSCS_CUDA(cudaMemcpyFromSymbol(ns_out, ptx::g_wait_ns, sizeof(unsigned long long) * 32));
+  MSCS_CUDA(cudaMemcpyFromSymbol(cnt_out, ptx::g_wait_cnt, sizeof(unsigned long long) * 32));
+  unsigned long long zero[32] = {};
+  MSCS_CUDA(cudaMemcpyToSymbol(ptx::g_wait_ns, zero, sizeof(zero)));
+  MSCS_CUDA(cudaMemcpyToSymbol(ptx::g_wait_cnt, zero, sizeof(zero)));
+  return 0;
 }

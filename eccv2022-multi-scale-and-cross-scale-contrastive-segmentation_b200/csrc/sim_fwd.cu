@@ -4,24 +4,30 @@
 //   normalised anchors x keys^T / tau, the positive / negative masks, exp, the row sums and the
 //   per-pair log-probabilities -- without ever materialising the N1 x N2 logits.
 // Two sweeps of the same kernel (the positive terms need the complete negative sums):
-//   MODE 0  all column tiles:        neg_i  = sum_{y_j != y_i} exp(l_ij)
+//   MODE 0  all tiles:               neg_i  = sum_{y_j != y_i} exp(l_ij)
 //   MODE 1  class-diagonal tiles:    pos_i  = sum_{j in P_i} [l_ij - log(exp(l_ij) + neg_i)],
 //                                    S_i    = sum_{j in P_i} 1/(exp(l_ij) + neg_i)
 //
-// CTA = 256 anchor rows (two 128-row UMMA halves, resident in smem) x a run of 128-key tiles
-// streamed through a TMA ring; accumulators double-buffered in TMEM (2 x 2 x 128 columns).
-// Warp roles: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..11 epilogue (one thread per
-// anchor row: row sums stay in a register for the whole run, one atomicAdd per row at the end).
+// CTA = a block of 256 KEYS resident in smem (the N = 256 operand of the MMA) x a run of 128-ANCHOR
+// tiles streamed through a TMA ring (the M = 128 operand).  One 128x256x16 MMA per K step: the
+// shared-memory operand traffic per FLOP is 25% lower than with 128x128 MMAs (which measured at
+// ~45% of the tensor peak here, shared-memory bound) and the accumulate dependency is hidden.
+// Accumulators (128 lanes x 256 columns) are double-buffered in TMEM.
+// Warp roles: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..11 epilogue: thread = (anchor row
+// of the streamed tile, 128-key half); partial row sums go out with one atomicAdd per row and tile.
 #include "sim_tc.cuh"
+#include <stdlib.h>
 
 namespace mscs {
 
-constexpr int kFwdRows = 256;
+constexpr int kFwdKeys = 256;       // resident key block = N of the MMA
 constexpr int kFwdThreads = 384;
 constexpr int kFwdStages = 5;
 
 struct FwdTerm {
   const int* a_cls; const int* k_seg;
+  const int2* row_range;   // per anchor row: [first, last+1) positive key rows   (k_row_ranges)
+  const int2* grp_range;   // per group of 32 anchor rows: union of the above
   float* neg; float* pos; float* ssum;
   int N1, N2, self_mask, a_map, k_map;
   float scale_log2;
@@ -30,6 +36,7 @@ struct FwdArgs {
   alignas(64) CUtensorMap maps[MSCS_MAX_SCALES];
   FwdTerm t[MSCS_MAX_TERMS];
   WorkTable work;
+  int debug_flags;     // experiments only (MSCS_DEBUG_FLAGS): 1 = epilogue skips the math
 };
 
 __host__ __device__ constexpr size_t fwd_smem_bytes(int KB) {
@@ -40,22 +47,22 @@ template <int KB, int MODE>
 __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constant__ FwdArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smA = smem;                                   // [2 halves][KB][128 rows][128 B]
-  uint8_t* smB = smem + (size_t)2 * KB * kBlkBytes;      // [stages][128 rows][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smB + (size_t)kFwdStages * kBlkBytes);
-  uint64_t* b_full = bars;                    // [stages]
-  uint64_t* b_empty = bars + kFwdStages;      // [stages]
-  uint64_t* a_full = bars + 2 * kFwdStages;
-  uint64_t* a_empty = a_full + 1;
-  uint64_t* acc_full = a_full + 2;            // [2]
-  uint64_t* acc_empty = a_full + 4;           // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 6);
+  uint8_t* smK = smem;                                   // resident keys  [KB][256 rows][128 B]
+  uint8_t* smA = smem + (size_t)2 * KB * kBlkBytes;      // anchor ring    [stages][128 rows][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smA + (size_t)kFwdStages * kBlkBytes);
+  uint64_t* a_full = bars;                    // [stages]  streamed anchor K-blocks
+  uint64_t* a_empty = bars + kFwdStages;      // [stages]
+  uint64_t* k_full = bars + 2 * kFwdStages;   // resident key block
+  uint64_t* k_empty = k_full + 1;
+  uint64_t* acc_full = k_full + 2;            // [2]
+  uint64_t* acc_empty = k_full + 4;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(k_full + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < kFwdStages; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
-    ptx::mbar_init(a_full, 1); ptx::mbar_init(a_empty, 1);
+    for (int i = 0; i < kFwdStages; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
+    ptx::mbar_init(k_full, 1); ptx::mbar_init(k_empty, 1);
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 8); }
     ptx::fence_barrier_init();
   }
@@ -65,155 +72,170 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Roles 0 and 1 are executed by the WHOLE warp (waits, loop control and descriptor arithmetic stay
+  // warp-uniform); only the TMA / MMA instructions themselves are issued by one elected lane.
   if (warp == 0) {
-    if (lane == 0) {
-      // ================= TMA producer =================
-      Walker wk(args.work);
-      Segment sg;
-      int stage = 0; uint32_t phase = 0, a_phase = 0;
-      while (wk.next(sg)) {
-        const FwdTerm& t = args.t[sg.owner];
-        ptx::mbar_wait(a_empty, a_phase ^ 1, 101);
-        ptx::mbar_expect_tx(a_full, 2 * KB * kBlkBytes);
-        for (int h = 0; h < 2; ++h)
-          for (int kb = 0; kb < KB; ++kb)
-            ptx::tma_load_2d(smA + (size_t)(h * KB + kb) * kBlkBytes, &args.maps[t.a_map], a_full, kb * kKBlk,
-                             sg.rb * kFwdRows + h * 128);
-        a_phase ^= 1;
-        for (int ct = sg.c_begin; ct < sg.c_end; ++ct)
-          for (int kb = 0; kb < KB; ++kb) {
-            ptx::mbar_wait(&b_empty[stage], phase ^ 1, 102);
-            ptx::mbar_expect_tx(&b_full[stage], kBlkBytes);
-            ptx::tma_load_2d(smB + (size_t)stage * kBlkBytes, &args.maps[t.k_map], &b_full[stage], kb * kKBlk,
-                             ct * kTileN);
-            if (++stage == kFwdStages) { stage = 0; phase ^= 1; }
-          }
+    // ================= TMA producer =================
+    Walker wk(args.work);
+    Segment sg;
+    int stage = 0; uint32_t phase = 0, k_phase = 0;
+    while (wk.next(sg)) {
+      const FwdTerm& t = args.t[sg.owner];
+      ptx::mbar_wait(k_empty, k_phase ^ 1, 101);
+      if (ptx::elect_one()) {
+        ptx::mbar_expect_tx(k_full, 2 * KB * kBlkBytes);
+        for (int kb = 0; kb < KB; ++kb)
+          for (int h = 0; h < 2; ++h)
+            ptx::tma_load_2d(smK + (size_t)(kb * 2 + h) * kBlkBytes, &args.maps[t.k_map], k_full, kb * kKBlk,
+                             sg.rb * kFwdKeys + h * 128);
       }
+      k_phase ^= 1;
+      for (int rt = sg.c_begin; rt < sg.c_end; ++rt)
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::mbar_wait(&a_empty[stage], phase ^ 1, 102);
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(&a_full[stage], kBlkBytes);
+            ptx::tma_load_2d(smA + (size_t)stage * kBlkBytes, &args.maps[t.a_map], &a_full[stage], kb * kKBlk,
+                             rt * 128);
+          }
+          if (++stage == kFwdStages) { stage = 0; phase ^= 1; }
+        }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================= MMA issuer =================
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, kTileN, 0, 0);
-      Walker wk(args.work);
-      Segment sg;
-      int stage = 0; uint32_t phase = 0, a_phase = 0, it = 0;
-      const uint32_t a_addr = ptx::smem_u32(smA), b_addr = ptx::smem_u32(smB);
-      while (wk.next(sg)) {
-        ptx::mbar_wait(a_full, a_phase, 111); a_phase ^= 1;
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, kFwdKeys, 0, 0);
+    Walker wk(args.work);
+    Segment sg;
+    int stage = 0; uint32_t phase = 0, k_phase = 0, it = 0;
+    const uint32_t k_addr = ptx::smem_u32(smK), a_addr = ptx::smem_u32(smA);
+    while (wk.next(sg)) {
+      ptx::mbar_wait(k_full, k_phase, 111); k_phase ^= 1;
+      ptx::tc_fence_after();
+      for (int rt = sg.c_begin; rt < sg.c_end; ++rt, ++it) {
+        const uint32_t buf = it & 1;
+        ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1, 112);
         ptx::tc_fence_after();
-        for (int ct = sg.c_begin; ct < sg.c_end; ++ct, ++it) {
-          const uint32_t buf = it & 1;
-          ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1, 112);
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::mbar_wait(&a_full[stage], phase, 113);
           ptx::tc_fence_after();
-          for (int kb = 0; kb < KB; ++kb) {
-            ptx::mbar_wait(&b_full[stage], phase, 113);
-            ptx::tc_fence_after();
-            // alternate the two row halves: consecutive MMAs then accumulate into different TMEM tiles,
-            // which hides the accumulate-to-accumulate dependency (measured: 114 -> 80 cycles per
-            // 128x128x16 MMA, tools/umma_probe.cu)
+          if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                const uint64_t ad = ptx::umma_desc_sw128(a_addr + (h * KB + kb) * kBlkBytes + k * 32, 16, 1024);
-                const uint64_t bd = ptx::umma_desc_sw128(b_addr + stage * kBlkBytes + k * 32, 16, 1024);
-                ptx::umma_ss(tmem_base + (buf * 2 + h) * 128, ad, bd, idesc, (kb | k) != 0);
-              }
-            ptx::umma_commit(&b_empty[stage]);
-            if (++stage == kFwdStages) { stage = 0; phase ^= 1; }
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = ptx::umma_desc_sw128(a_addr + stage * kBlkBytes + k * 32, 16, 1024);
+              const uint64_t bd = ptx::umma_desc_sw128(k_addr + kb * 2 * kBlkBytes + k * 32, 16, 1024);
+              ptx::umma_ss(tmem_base + buf * kFwdKeys, ad, bd, idesc, (kb | k) != 0);
+            }
+            ptx::umma_commit(&a_empty[stage]);
           }
-          ptx::umma_commit(&acc_full[buf]);
+          __syncwarp();
+          if (++stage == kFwdStages) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(a_empty);
+        if (ptx::elect_one()) ptx::umma_commit(&acc_full[buf]);
+        __syncwarp();
       }
+      if (ptx::elect_one()) ptx::umma_commit(k_empty);
+      __syncwarp();
     }
   } else if (warp >= 4) {
-    // ================= epilogue: one thread per anchor row =================
-    const int half = (warp - 4) >> 2, quad = warp & 3;
+    // ================= epilogue: thread = (anchor row of the tile, 128-key half) =================
+    const int ch = (warp - 4) >> 2, quad = warp & 3;
     Walker wk(args.work);
     Segment sg;
     uint32_t it = 0;
     while (wk.next(sg)) {
       const FwdTerm& t = args.t[sg.owner];
-      const int row = sg.rb * kFwdRows + half * 128 + quad * 32 + lane;
-      const bool valid = row < t.N1;
-      int p0 = 0, p1 = 0;
-      if (valid) { const int y = t.a_cls[row]; p0 = t.k_seg[y]; p1 = t.k_seg[y + 1]; }
-      const unsigned plen = (unsigned)(p1 - p0);
-      int wmin = valid ? p0 : 0x7fffffff, wmax = valid ? p1 : 0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        wmin = min(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
-        wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-      }
+      const int cb = sg.rb * kFwdKeys + ch * 128;          // first key column of this thread's half
       const float scale = t.scale_log2;
-      const float negi = (MODE == 1 && valid) ? t.neg[row] : 1.f;
-      const int self_col = t.self_mask ? row : -1;
-      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;   // MODE 0: 4 partial sums; MODE 1: acc0 = pos (log2 units), acc1 = S
-      for (int ct = sg.c_begin; ct < sg.c_end; ++ct, ++it) {
+      // positive key range of each row (and of its 32-row group) comes precomputed from k_row_ranges;
+      // the values of the NEXT tile are fetched one tile ahead so no load sits on the critical path
+      int2 n_rr = make_int2(0, 0), n_gr = make_int2(0x7fffffff, 0); float n_neg = 1.f;
+      auto fetch_row = [&](int rt_) {
+        const int r = rt_ * 128 + quad * 32 + lane;
+        n_rr = make_int2(0, 0); n_gr = make_int2(0x7fffffff, 0); n_neg = 1.f;
+        if (rt_ < sg.c_end) {
+          n_gr = t.grp_range[rt_ * 4 + quad];
+          if (r < t.N1) {
+            n_rr = t.row_range[r];
+            if (MODE == 1) n_neg = t.neg[r];
+          }
+        }
+      };
+      fetch_row(sg.c_begin);
+      for (int rt = sg.c_begin; rt < sg.c_end; ++rt, ++it) {
         const uint32_t buf = it & 1;
+        const int row = rt * 128 + quad * 32 + lane;
+        const bool valid = row < t.N1;
+        const int p0 = n_rr.x, p1 = n_rr.y, wmin = n_gr.x, wmax = n_gr.y;
+        const float negi = n_neg;
+        fetch_row(rt + 1);
+        const unsigned plen = (unsigned)(p1 - p0);
+        const int self_col = t.self_mask ? row : -1;
+        const bool touches = !(cb + 128 <= wmin || cb >= wmax);
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;   // MODE 1: acc0 = pos (log2 units), acc1 = S
         ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1, 121);
         ptx::tc_fence_after();
-        const int cb = ct * kTileN;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (buf * 2 + half) * 128;
-        const bool touches = !(cb + kTileN <= wmin || cb >= wmax);
-        if (MODE == 0) {
-          const bool fast = !touches && (cb + kTileN <= t.N2);
-          uint32_t va[32], vb[32];
-          ptx::tmem_ld32(taddr, va);
-          ptx::tmem_ld_wait(va);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kFwdKeys + ch * 128;
+        if (args.debug_flags & 1) {
+          // experiment: no TMEM reads / math
+        } else if (MODE == 0) {
+          if (cb < t.N2) {      // a half that lies entirely in the zero padding of the key block has no work
+            uint32_t va[32], vb[32];
+            ptx::tmem_ld32(taddr, va);
+            ptx::tmem_ld_wait(va);
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            uint32_t (&cur)[32] = (ch & 1) ? vb : va;
-            uint32_t (&nxt)[32] = (ch & 1) ? va : vb;
-            if (ch < 3) ptx::tmem_ld32(taddr + (ch + 1) * 32, nxt);
-            if (fast) {
+            for (int c4 = 0; c4 < 4; ++c4) {
+              uint32_t (&cur)[32] = (c4 & 1) ? vb : va;
+              uint32_t (&nxt)[32] = (c4 & 1) ? va : vb;
+              if (c4 < 3) ptx::tmem_ld32(taddr + (c4 + 1) * 32, nxt);
+              const int c0 = cb + c4 * 32;
+              // 32-column chunk without positives of any row of this warp and inside the key set: no masks
+              const bool fast = (c0 + 32 <= wmin || c0 >= wmax) && (c0 + 32 <= t.N2);
+              if (fast) {
 #pragma unroll
-              for (int c = 0; c < 32; c += 4) {
-                acc0 += ptx::ex2(__uint_as_float(cur[c]) * scale);
-                acc1 += ptx::ex2(__uint_as_float(cur[c + 1]) * scale);
-                acc2 += ptx::ex2(__uint_as_float(cur[c + 2]) * scale);
-                acc3 += ptx::ex2(__uint_as_float(cur[c + 3]) * scale);
+                for (int c = 0; c < 32; c += 4) {
+                  acc0 += ptx::ex2(__uint_as_float(cur[c]) * scale);
+                  acc1 += ptx::ex2(__uint_as_float(cur[c + 1]) * scale);
+                  acc2 += ptx::ex2(__uint_as_float(cur[c + 2]) * scale);
+                  acc3 += ptx::ex2(__uint_as_float(cur[c + 3]) * scale);
+                }
+              } else if (c0 < t.N2) {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                  const int col = c0 + c;
+                  const float e = ptx::ex2(__uint_as_float(cur[c]) * scale);
+                  const bool isneg = ((unsigned)(col - p0) >= plen) && (col < t.N2);
+                  acc0 += isneg ? e : 0.f;
+                }
               }
-            } else {
-#pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                const int col = cb + ch * 32 + c;
-                const float e = ptx::ex2(__uint_as_float(cur[c]) * scale);
-                const bool isneg = ((unsigned)(col - p0) >= plen) && (col < t.N2);
-                acc0 += isneg ? e : 0.f;
-              }
+              if (c4 < 3) ptx::tmem_ld_wait(nxt);
             }
-            if (ch < 3) ptx::tmem_ld_wait(nxt);
           }
-        } else {
-          if (touches) {
+        } else if (touches) {
 #pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
-              const int c0 = cb + ch * 32;
-              if (c0 + 32 <= wmin || c0 >= wmax) continue;      // warp-uniform
-              uint32_t v[32];
-              ptx::tmem_ld32(taddr + ch * 32, v);
-              ptx::tmem_ld_wait(v);
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const int c0 = cb + c4 * 32;
+            if (c0 + 32 <= wmin || c0 >= wmax) continue;      // warp-uniform
+            uint32_t v[32];
+            ptx::tmem_ld32(taddr + c4 * 32, v);
+            ptx::tmem_ld_wait(v);
 #pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                const int col = c0 + c;
-                const bool ispos = ((unsigned)(col - p0) < plen) && (col != self_col);
-                const float x = __uint_as_float(v[c]) * scale;      // logit in log2 units
-                const float den = ptx::ex2(x) + negi;
-                acc0 += ispos ? (x - ptx::lg2(den)) : 0.f;
-                acc1 += ispos ? ptx::rcp(den) : 0.f;
-              }
+            for (int c = 0; c < 32; ++c) {
+              const int col = c0 + c;
+              const bool ispos = ((unsigned)(col - p0) < plen) && (col != self_col);
+              const float x = __uint_as_float(v[c]) * scale;      // logit in log2 units
+              const float den = ptx::ex2(x) + negi;
+              acc0 += ispos ? (x - ptx::lg2(den)) : 0.f;
+              acc1 += ispos ? ptx::rcp(den) : 0.f;
             }
           }
         }
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
-      }
-      if (valid) {
-        if (MODE == 0) atomicAdd(&t.neg[row], (acc0 + acc1) + (acc2 + acc3));
-        else { atomicAdd(&t.pos[row], acc0 * kLn2); atomicAdd(&t.ssum[row], acc1); }
+        if (valid) {
+          if (MODE == 0) atomicAdd(&t.neg[row], (acc0 + acc1) + (acc2 + acc3));
+          else if (touches) { atomicAdd(&t.pos[row], acc0 * kLn2); atomicAdd(&t.ssum[row], acc1); }
+        }
       }
     }
   }
@@ -223,9 +245,31 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
   if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
 }
 
+// per anchor row: positive key range [k_seg[y], k_seg[y+1]); per 32-row group: the union (groups are
+// padded to whole 128-row tiles so the epilogue can index them by tile)
+struct RangeTerm { const int* a_cls; const int* k_seg; int2* row_range; int2* grp_range; int N1; };
+struct RangeArgs { RangeTerm t[MSCS_MAX_TERMS]; };
+__global__ void __launch_bounds__(256) k_row_ranges(const __grid_constant__ RangeArgs a) {
+  const RangeTerm& t = a.t[blockIdx.y];
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  if (blockIdx.x * 256 >= (t.N1 + 127) / 128 * 128) return;
+  int p0 = 0x7fffffff, p1 = 0;
+  if (r < t.N1) {
+    const int y = t.a_cls[r];
+    p0 = t.k_seg[y]; p1 = t.k_seg[y + 1];
+    t.row_range[r] = make_int2(p0, p1);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    p0 = min(p0, __shfl_xor_sync(0xffffffffu, p0, o));
+    p1 = max(p1, __shfl_xor_sync(0xffffffffu, p1, o));
+  }
+  if ((threadIdx.x & 31) == 0 && r < (t.N1 + 127) / 128 * 128) t.grp_range[r >> 5] = make_int2(p0, p1);
+}
+
 // ---------------------------------------------------------------------------------------
-// work table builder: one item per (term, 256-row block).  MODE 0: every column tile;
-// MODE 1: the column tiles that overlap the class segments of the block's rows.
+// work table builder: one item per (owner, block).  MODE 0: every streamed tile; MODE 1: the
+// streamed tiles whose classes overlap the classes of the block (both sides are class-sorted).
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_build_work(const __grid_constant__ BuildArgs a) {
   __shared__ int carry;
@@ -327,12 +371,14 @@ using namespace mscs;
 
 extern "C" size_t mscs_sim_workspace_bytes(const mscs_sim_job* job) {
   if (!job) return 0;
-  size_t items = 0;
+  size_t items = 0, ranges = 0;
   for (int t = 0; t < job->num_terms; ++t) {
-    items += 2 * (size_t)ceil_div(job->terms[t].N1, kFwdRows);                 // forward: two sweeps
+    ranges += align_up(sizeof(int2) * (size_t)job->terms[t].N1, 64) +
+              align_up(sizeof(int2) * (size_t)ceil_div(job->terms[t].N1, 128) * 4, 64);
+    items += 2 * (size_t)ceil_div(job->terms[t].N2, kFwdKeys);                 // forward: two sweeps
     items += (size_t)ceil_div(job->terms[t].N1, 128) + ceil_div(job->terms[t].N2, 128);   // backward passes
   }
-  return 2 * 4096 + items * (sizeof(WorkItem) + sizeof(int)) + 16 * 64;
+  return 2 * 4096 + ranges + items * (sizeof(WorkItem) + sizeof(int)) + 16 * 64;
 }
 
 extern "C" int mscs_sim_forward(const mscs_sim_job* job, void* stream_) {
@@ -341,6 +387,7 @@ extern "C" int mscs_sim_forward(const mscs_sim_job* job, void* stream_) {
   MSCS_CHECK_ARG(job->work, "work buffer is null");
   cudaStream_t st = (cudaStream_t)stream_;
   FwdArgs args{};
+  if (const char* e = getenv("MSCS_DEBUG_FLAGS")) args.debug_flags = atoi(e);
   // one tensor map per distinct operand matrix
   const void* bases[MSCS_MAX_SCALES]; int nmaps = 0;
   auto map_of = [&](const void* base, int rows) -> int {
@@ -351,19 +398,27 @@ extern "C" int mscs_sim_forward(const mscs_sim_job* job, void* stream_) {
     return nmaps++;
   };
   BuildArgs b{};
-  int nitems = 0;
+  RangeArgs ra{};
+  int nitems = 0, maxN1 = 0;
+  char* w = (char*)job->work + 4096;      // [0,4096): finalise accumulators
   for (int t = 0; t < job->num_terms; ++t) {
     const mscs_term& m = job->terms[t];
     const int am = map_of(m.a_bf16, m.N1), km = map_of(m.k_bf16, m.N2);
     if (am == -2 || km == -2) return -1;
     MSCS_CHECK_ARG(am >= 0 && km >= 0, "too many distinct operand matrices");
-    args.t[t] = FwdTerm{m.a_cls, m.k_seg, m.neg_sum, m.pos_sum, m.s_sum, m.N1, m.N2, m.self_mask, am, km,
+    int2* rr = (int2*)w; w += align_up(sizeof(int2) * (size_t)m.N1, 64);
+    int2* gr = (int2*)w; w += align_up(sizeof(int2) * (size_t)ceil_div(m.N1, 128) * 4, 64);
+    ra.t[t] = RangeTerm{m.a_cls, m.k_seg, rr, gr, m.N1};
+    if (m.N1 > maxN1) maxN1 = m.N1;
+    args.t[t] = FwdTerm{m.a_cls, m.k_seg, rr, gr, m.neg_sum, m.pos_sum, m.s_sum, m.N1, m.N2, m.self_mask, am, km,
                         kLog2e / m.temperature};
-    b.t[t] = BuildTerm{m.a_cls, m.k_seg, m.N1, m.N2, nitems};
-    nitems += ceil_div(m.N1, kFwdRows);
+    // blocks are on the KEY side (256 keys), the streamed 128-row tiles on the ANCHOR side
+    b.t[t] = BuildTerm{m.k_cls, m.a_seg, m.N2, m.N1, nitems};
+    nitems += ceil_div(m.N2, kFwdKeys);
   }
-  b.num_terms = job->num_terms; b.nitems = nitems; b.rows_per_item = kFwdRows;
-  char* w = (char*)job->work + 4096;      // [0,4096): finalise accumulators
+  k_row_ranges<<<dim3(ceil_div(maxN1 + 127, 256), job->num_terms), 256, 0, st>>>(ra);
+  MSCS_LAUNCH_CHECK();
+  b.num_terms = job->num_terms; b.nitems = nitems; b.rows_per_item = kFwdKeys;
   for (int mode = 0; mode < 2; ++mode) {
     b.mode = mode;
     b.items = (WorkItem*)w; w += align_up(sizeof(WorkItem) * (size_t)nitems, 64);
@@ -380,4 +435,15 @@ extern "C" int mscs_sim_forward(const mscs_sim_job* job, void* stream_) {
     if (rc) return rc;
   }
   return launch_finalize(job, st);
+}
+
+// debug: read and reset the barrier wait profile of this translation unit (ns and count per tag % 32)
+extern "C" int mscs_debug_wait_profile_fwd(unsigned long long* ns_out, unsigned long long* cnt_out) {
+  MSCS_CUDA(cudaDeviceSynchronize());
+  MSCS_CUDA(cudaMemcpyFromSymbol(ns_out, ptx::g_wait_ns, sizeof(unsigned long long) * 32));
+  MSCS_CUDA(cudaMemcpyFromSymbol(cnt_out, ptx::g_wait_cnt, sizeof(unsigned long long) * 32));
+  unsigned long long zero[32] = {};
+  MSCS_CUDA(cudaMemcpyToSymbol(ptx::g_wait_ns, zero, sizeof(zero)));
+  MSCS_CUDA(cudaMemcpyToSymbol(ptx::g_wait_cnt, zero, sizeof(zero)));
+  return 0;
 }

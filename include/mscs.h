@@ -36,6 +36,10 @@ const char* mscs_last_error(void);
 /* after a launch failure: textual record of barrier waits that timed out inside the tensor kernels
  * (block, thread, wait tag); returns the number of records */
 int mscs_debug_trap_info(char* out, int len);
+/* debug: read + reset the time spent in barrier waits inside the forward / backward tensor kernels,
+ * 32 entries indexed by wait tag % 32 (nanoseconds summed over threads, and wait counts) */
+int mscs_debug_wait_profile_fwd(unsigned long long* ns_out, unsigned long long* cnt_out);
+int mscs_debug_wait_profile_bwd(unsigned long long* ns_out, unsigned long long* cnt_out);
 /* 1 if a CUDA device with compute capability 10.x is present */
 int mscs_device_ok(void);
 

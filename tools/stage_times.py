@@ -1,0 +1,22 @@
+"""Per-stage device times of cfg2 steps (run on the GPU box); honours MSCS_DEBUG_FLAGS experiments."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import mscs_b200
+from mscs_b200 import synth, _ops
+dev = torch.device("cuda:0")
+name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
+cfg = synth.CONFIGS[name]
+labels, feats = synth.make_inputs(name)
+cls = mscs_b200.DenseContrastiveLossV2 if cfg["single_scale"] else mscs_b200.DenseContrastiveLossV2_ms
+mod = cls(dict(cfg["loss"]))
+labels = labels.to(dev); fg = [f.to(dev).requires_grad_(True) for f in feats]
+torch.manual_seed(0)
+def step():
+    for f in fg: f.grad = None
+    mod(labels, fg[0] if cfg["single_scale"] else fg).backward()
+for _ in range(3): step()
+_ops.TIMING = {}
+for _ in range(10): step()
+torch.cuda.synchronize()
+print(os.environ.get("MSCS_DEBUG_FLAGS", "0"), {k: round(sum(a.elapsed_time(b) for a, b in v) / len(v), 4) for k, v in _ops.TIMING.items()})
