@@ -39,7 +39,7 @@ struct BwdArgs {
 };
 
 __host__ __device__ constexpr size_t bwd_smem_bytes(int KB) {
-  return 1024 + (size_t)(3 * KB) * kBlkBytes + 3 * 128 * sizeof(float) + 256;
+  return 1024 + (size_t)(3 * KB) * kBlkBytes + 2 * 3 * 128 * sizeof(float) + 256;   // 21 barriers + TMEM slot < 256 B
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -61,22 +61,25 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;                                         // [KB][128][128 B]   X tile
   uint8_t* smB = smA + (size_t)KB * kBlkBytes;                 // [2][KB][128][128 B] Y tiles
-  float* cstat = reinterpret_cast<float*>(smB + (size_t)2 * KB * kBlkBytes);   // [3][128] column coefficients
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cstat + 3 * 128);
+  float* cstat = reinterpret_cast<float*>(smB + (size_t)2 * KB * kBlkBytes);   // [2 buffers][3][128] column coefficients
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cstat + 2 * 3 * 128);
   uint64_t* a_full = bars;        uint64_t* a_empty = bars + 1;
-  uint64_t* b_full = bars + 2;    uint64_t* b_empty = bars + 4;     // [2]
-  uint64_t* s_full = bars + 6;                                      // [2]
-  uint64_t* w_full = bars + 10;                                     // [2 halves][2 S buffers]: one phase per
+  uint64_t* b_empty = bars + 2;                                     // [2]
+  uint64_t* s_full = bars + 4;                                      // [2]
+  uint64_t* w_full = bars + 6;                                      // [2 halves][2 S buffers]: one phase per
                                                                     // two tiles, so a column-half group that runs a
                                                                     // tile ahead of the MMA thread cannot overrun it
-  uint64_t* df_full = bars + 14;  uint64_t* df_empty = bars + 15;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* df_full = bars + 10;  uint64_t* df_empty = bars + 11;
+  uint64_t* b_full = bars + 12;                                     // [2 stages][4 K-blocks]: the S MMAs start on
+                                                                    // the first 16 KB of a tile, not the whole 64 KB
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     ptx::mbar_init(a_full, 1); ptx::mbar_init(a_empty, 1);
     for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1);
+      ptx::mbar_init(&b_empty[i], 1);
+      for (int kb = 0; kb < 4; ++kb) ptx::mbar_init(&b_full[i * 4 + kb], 1);
       ptx::mbar_init(&s_full[i], 1);
       ptx::mbar_init(&w_full[i], 4); ptx::mbar_init(&w_full[2 + i], 4);
     }
@@ -109,10 +112,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
         const uint32_t st = it & 1;
         ptx::mbar_wait(&b_empty[st], ((it >> 1) & 1) ^ 1, 202);
         if (ptx::elect_one()) {
-          ptx::mbar_expect_tx(&b_full[st], KB * kBlkBytes);
-          for (int kb = 0; kb < KB; ++kb)
-            ptx::tma_load_2d(smB + (size_t)(st * KB + kb) * kBlkBytes, &args.maps[p.y_map], &b_full[st],
+          for (int kb = 0; kb < KB; ++kb) {
+            ptx::mbar_expect_tx(&b_full[st * 4 + kb], kBlkBytes);
+            ptx::tma_load_2d(smB + (size_t)(st * KB + kb) * kBlkBytes, &args.maps[p.y_map], &b_full[st * 4 + kb],
                              kb * kKBlk, ct * kTileN);
+          }
         }
       }
     }
@@ -124,34 +128,38 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
     Walker wk(args.work);
     Segment sg;
     uint32_t a_phase = 0, it = 0, seg = 0;
-    auto issue_s = [&](uint32_t cur) {
+    // S MMAs of tile `cur` for K-blocks [kb0, kb1)
+    auto issue_s = [&](uint32_t cur, int kb0, int kb1) {
       const uint32_t st = cur & 1, ph = (cur >> 1) & 1;
       // S buffer `st` also holds W of tile cur-2: its consumer (the dX MMAs of tile cur-2) was issued
       // before this point and tcgen05.mma executes in issue order, so no extra barrier is needed
-      ptx::mbar_wait(&b_full[st], ph, 211);
-      ptx::tc_fence_after();
-      if (ptx::elect_one()) {
-#pragma unroll
-        for (int kb = 0; kb < KB; ++kb)
+      for (int kb = kb0; kb < kb1; ++kb) {
+        ptx::mbar_wait(&b_full[st * 4 + kb], ph, 211);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t ad = ptx::umma_desc_sw128(a_addr + kb * kBlkBytes + k * 32, 16, 1024);
             const uint64_t bd = ptx::umma_desc_sw128(b_addr + (st * KB + kb) * kBlkBytes + k * 32, 16, 1024);
             ptx::umma_ss(tmem_base + st * 128, ad, bd, idesc_s, (kb | k) != 0);
           }
-        ptx::umma_commit(&s_full[st]);
+          if (kb == KB - 1) ptx::umma_commit(&s_full[st]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     };
     while (wk.next(sg)) {
       ptx::mbar_wait(a_full, a_phase, 212); a_phase ^= 1;
       ptx::mbar_wait(df_empty, (seg & 1) ^ 1, 213);
       ptx::tc_fence_after();
       const int ntiles = sg.c_end - sg.c_begin;
-      issue_s(it);
+      issue_s(it, 0, KB);
       for (int j = 0; j < ntiles; ++j) {
         const uint32_t cur = it + j, st = cur & 1;
-        if (j + 1 < ntiles) issue_s(cur + 1);
+        // Issue order S(cur+1) | dX(cur): the whole S chain of the next tile runs while the epilogue
+        // turns S(cur) into W(cur).  (Splitting S(cur+1) around dX(cur) to release the Y stage earlier
+        // measured slower: 0.585 vs 0.513 ms at cfg-2 -- the dX MMAs then wait for W.)
+        if (j + 1 < ntiles) issue_s(cur + 1, 0, KB);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           ptx::mbar_wait(&w_full[h * 2 + st], (cur >> 1) & 1, 214 + h);
@@ -181,7 +189,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
     const int h = (warp - 4) >> 2, quad = warp & 3;
     const int wg_tid = threadIdx.x - (4 + 4 * h) * 32;      // 0..127 inside the column-half group
     const int r_loc = quad * 32 + lane;                     // row inside the tile = TMEM lane
-    float* cs_s = cstat; float* cs_pn = cstat + 128; float* cs_neg = cstat + 256;
     const float gout = *args.grad_out;
     Walker wk(args.work);
     Segment sg;
@@ -204,18 +211,34 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
       const float rneg = (valid && p.row_neg) ? p.row_neg[row] : 1.f;
       const int self_col = p.self_mask ? row : -1;
       const float scale = p.scale_log2;
+      // column coefficients of a tile are staged in smem one tile ahead (double buffered): the global
+      // loads of tile t+1 are issued before tile t is processed and parked in registers meanwhile
+      float pf_s = 0.f, pf_pn = 0.f, pf_neg = 1.f;
+      auto prefetch_cols = [&](int ct_) {
+        pf_s = 0.f; pf_pn = 0.f; pf_neg = 1.f;
+        if (wg_tid < 64 && ct_ < sg.c_end) {
+          const int c = ct_ * kTileN + h * 64 + wg_tid;
+          if (c < p.n_cols) {
+            if (p.col_cs) pf_s = p.col_cs[c];
+            if (p.col_cpn) pf_pn = p.col_cpn[c];
+            if (p.col_neg) pf_neg = p.col_neg[c];
+          }
+        }
+      };
+      auto publish_cols = [&](uint32_t b_) {
+        if (wg_tid < 64) {
+          float* cs = cstat + b_ * 384;
+          cs[h * 64 + wg_tid] = pf_s; cs[128 + h * 64 + wg_tid] = pf_pn; cs[256 + h * 64 + wg_tid] = pf_neg;
+        }
+        named_bar_sync(1 + h, 128);
+      };
+      prefetch_cols(sg.c_begin);
+      publish_cols(it & 1);
       for (int ct = sg.c_begin; ct < sg.c_end; ++ct, ++it) {
         const uint32_t buf = it & 1;
         const int cb = ct * kTileN + h * 64;               // first global column of this thread's half
-        // stage the column coefficients of this half (64 columns) in smem
-        named_bar_sync(1 + h, 128);
-        if (wg_tid < 64) {
-          const int c = cb + wg_tid; const bool ok = c < p.n_cols;
-          cs_s[h * 64 + wg_tid] = (ok && p.col_cs) ? p.col_cs[c] : 0.f;
-          cs_pn[h * 64 + wg_tid] = (ok && p.col_cpn) ? p.col_cpn[c] : 0.f;
-          cs_neg[h * 64 + wg_tid] = (ok && p.col_neg) ? p.col_neg[c] : 1.f;
-        }
-        named_bar_sync(1 + h, 128);
+        const float* cs_s = cstat + buf * 384; const float* cs_pn = cs_s + 128; const float* cs_neg = cs_s + 256;
+        prefetch_cols(ct + 1);
         ptx::mbar_wait(&s_full[buf], (it >> 1) & 1, 221);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128 + h * 64;
@@ -258,6 +281,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&w_full[h * 2 + buf]);
+        publish_cols(buf ^ 1);       // also: every thread of the group is done reading cstat[buf]
       }
       // ---- flush dX: this group drains channel half h ----
       ptx::mbar_wait(df_full, seg & 1, 222);
