@@ -6,6 +6,7 @@ feature gradients out" is a libmscs.so kernel.  Nothing in this module computes 
 there is no fallback: a missing library or a non-sm_100 device raises.
 """
 import ctypes as C
+import os
 import struct
 from dataclasses import dataclass, field
 from typing import List, Optional
@@ -60,20 +61,31 @@ class LossSpec:
     w_high_mid: float = 1.0
 
 
-@dataclass
 class ScaleSample:
-    """Sampling result of one scale (device tensors unless noted)."""
-    T: int
-    V: int
-    N: int
-    log_flag: bool
-    dl_h: int
-    dl_w: int
-    idx_ref: torch.Tensor    # (T, V) int32 flat pixel index in REFERENCE order (V2.py:122)
-    pair_ref: torch.Tensor   # (T, 2) int32 (image, class) in reference order (V2.py:106-107)
-    pix: torch.Tensor        # (N,) int32 image*plane + pixel, rows sorted by class
-    cls: torch.Tensor        # (N,) int32 class of each sorted row
-    seg: torch.Tensor        # (A+1,) int32 class segments of the sorted rows
+    """Sampling result of one scale.  The arrays live in one int32 slab; views are made on demand.
+
+      idx_ref  (T, V) int32  flat pixel index in REFERENCE order (V2.py:122)
+      pair_ref (T, 2) int32  (image, class) in reference order (V2.py:106-107)
+      pix (N,) int32 image*plane + pixel, rows sorted by class;  cls (N,) class of each sorted row
+      seg (A+1,) int32 class segments of the sorted rows
+    """
+    __slots__ = ("T", "V", "N", "log_flag", "dl_h", "dl_w", "_slab", "_off", "_A")
+
+    def __init__(self, T, V, N, log_flag, dl_h, dl_w, slab, off, A):
+        self.T, self.V, self.N, self.log_flag, self.dl_h, self.dl_w = T, V, N, log_flag, dl_h, dl_w
+        self._slab, self._off, self._A = slab, off, A
+
+    def _view(self, k, n):
+        return self._slab[self._off[k]:self._off[k] + n]
+
+    idx_ref = property(lambda self: self._view(0, self.N).view(self.T, self.V))
+    pair_ref = property(lambda self: self._view(1, 2 * self.T).view(self.T, 2))
+    pix = property(lambda self: self._view(2, self.N))
+    cls = property(lambda self: self._view(3, self.N))
+    seg = property(lambda self: self._view(4, self._A + 1))
+
+    def ptr(self, k):
+        return self._slab.data_ptr() + 4 * self._off[k]
 
 
 _stream_override = [None]
@@ -151,8 +163,10 @@ class _StreamCache:
         lib = _lib.load()
         if self.bufs[which] is None or self.bufs[which].numel() < words + 1024:
             self.bufs[which] = torch.empty(words + 1024, dtype=torch.int32, device=self.dev)
-        main = torch.cuda.current_stream()
-        self.side.wait_stream(main)              # allocator / previous readers of this buffer
+            self.bufs[which].record_stream(self.side)
+            self.side.wait_stream(torch.cuda.current_stream())      # fresh allocation: order after its previous users
+        # the stream depends only on the host-side generator state: it is NOT ordered after the main
+        # stream, only after the last reader of this buffer (the selection kernel two calls ago)
         if self.last_use[which] is not None:
             self.side.wait_event(self.last_use[which])
         _lib.check(lib.mscs_mt19937_stream(mt.ctypes.data_as(C.c_void_p), pos, C.c_uint64(words),
@@ -170,6 +184,8 @@ class _StreamCache:
         return self.bufs[self.cur]
 
     def release_and_prefetch(self, mt_next, pos_next, words):
+        if os.environ.get("MSCS_NO_PREFETCH"):      # experiment switch: regenerate inline at the next call
+            return
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
         self.last_use[self.cur] = ev
@@ -233,25 +249,18 @@ def sample_anchors(labels, feat_hw, spec, mt_state=None, defer_rng=False):
                                            draws.data_ptr(), st), "mscs_mt19937_stream")
     A = spec.num_classes
     # one int32 slab for every per-scale index array
-    sizes = []
+    offs, off = [], 0
     for s in range(S):
         N, T = plan[s].N, plan[s].T
-        sizes += [N, 2 * T, N, N, A + 1]
-    slab = torch.empty(sum((x + 15) // 16 * 16 for x in sizes), dtype=torch.int32, device=dev)
-    views, off = [], 0
-    for x in sizes:
-        views.append(slab[off:off + x])
-        off += (x + 15) // 16 * 16
-    out = []
-    arrs = [[], [], [], [], []]
-    for s in range(S):
-        v = views[5 * s:5 * s + 5]
-        for k in range(5):
-            arrs[k].append(v[k].data_ptr())
-        out.append(ScaleSample(T=plan[s].T, V=plan[s].V, N=plan[s].N, log_flag=bool(plan[s].log_flag),
-                               dl_h=plan[s].dl_h, dl_w=plan[s].dl_w,
-                               idx_ref=v[0].view(plan[s].T, plan[s].V), pair_ref=v[1].view(plan[s].T, 2),
-                               pix=v[2], cls=v[3], seg=v[4]))
+        cur = []
+        for x in (N, 2 * T, N, N, A + 1):
+            cur.append(off)
+            off += (x + 15) // 16 * 16
+        offs.append(cur)
+    slab = torch.empty(off, dtype=torch.int32, device=dev)
+    out = [ScaleSample(plan[s].T, plan[s].V, plan[s].N, bool(plan[s].log_flag), plan[s].dl_h, plan[s].dl_w,
+                       slab, offs[s], A) for s in range(S)]
+    arrs = [[out[s].ptr(k) for s in range(S)] for k in range(5)]
     _lib.check(lib.mscs_sample_select(C.byref(cfg), plan, ws.data_ptr(), draws.data_ptr(),
                                       *[_lib.ptr_array(a) for a in arrs], st), "mscs_sample_select")
 
@@ -393,25 +402,21 @@ class _GradBuffers:
     largest HBM term of the whole path, SURVEY.md §8d, and does not depend on any result)."""
     _side = {}
 
-    def __init__(self, feats, samples, needs):
+    def __init__(self, feats, needs):
         dev = feats[0].device
-        lib = _lib.load()
         side = self._side.get(dev)
         if side is None:
             side = self._side[dev] = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream()
         self.bufs, self.slots = [], []
-        for f, smp, need in zip(feats, samples, needs):
+        for f, need in zip(feats, needs):
             n, Cc, h, w = f.shape
             if not need or (h * w) % 8 != 0:
                 self.bufs.append(None)
                 self.slots.append(None)
                 continue
-            slot = torch.empty(n * h * w, dtype=torch.int32, device=dev)
-            _lib.check(lib.mscs_slot_map(smp.pix.data_ptr(), smp.N, n * h * w, slot.data_ptr(), _stream()),
-                       "mscs_slot_map")
+            self.slots.append(torch.empty(n * h * w, dtype=torch.int32, device=dev))   # filled by mscs_slot_map
             self.bufs.append(torch.empty(f.shape, dtype=torch.float32, device=dev))
-            self.slots.append(slot)
         side.wait_stream(main)
         with torch.cuda.stream(side):
             for b in self.bufs:
@@ -425,6 +430,239 @@ class _GradBuffers:
         """The pre-zeroed buffer of scale s (once: a second backward falls back to zero-fill)."""
         b, self.bufs[s] = self.bufs[s], None
         return b, self.slots[s]
+
+
+
+# ---- fused host path of the autograd Function -------------------------------------------------
+class _StepPlan:
+    """Everything of a call that depends only on shapes and configuration, computed once and cached:
+    C structs, buffer layouts sized by upper bounds (N <= max_features_total), the term list.  With it
+    every allocation and the MT19937 stream lookup happen BEFORE the one host sync of the forward
+    pass, and only three kinds of C calls remain after it (select, gather, similarity forward)."""
+
+    def __init__(self, dev, label_shape, feat_shapes, spec, single_scale):
+        lib = _lib.load()
+        self.dev, self.spec, self.single_scale = dev, spec, single_scale
+        n, H, W = label_shape
+        self.S = S = len(feat_shapes)
+        self.A = A = spec.num_classes
+        self.feat_shapes = feat_shapes
+        cfg = self.cfg = _lib.SampleCfg()
+        cfg.n, cfg.H, cfg.W, cfg.num_scales = n, H, W, S
+        for s, shp in enumerate(feat_shapes):
+            cfg.fh[s], cfg.fw[s] = shp[2], shp[3]
+        cfg.num_classes, cfg.min_views = A, spec.min_views
+        cfg.max_views, cfg.max_total = spec.max_views, spec.max_total
+        self.ws_bytes = lib.mscs_sample_workspace_bytes(C.byref(cfg))
+        if self.ws_bytes == 0:
+            raise RuntimeError("mscs_sample_workspace_bytes: " + lib.mscs_last_error().decode())
+        self.max_draws = int(lib.mscs_sample_max_draws(C.byref(cfg)))
+        self.C = Cc = feat_shapes[0][1]
+        for shp in feat_shapes:
+            if shp[1] != Cc:
+                raise ValueError("all feature maps must have the same number of channels")
+        self.C_pad = (Cc + 63) // 64 * 64
+        Tcap = n * (A - 1)
+        self.Ncap = [min(spec.max_total, n * shp[2] * shp[3]) for shp in feat_shapes]
+        al = lambda x, a=16: (x + a - 1) // a * a
+        # int32 slab: idx_ref, pair_ref, pix, cls, seg per scale
+        self.ioff, off = [], 0
+        for s in range(S):
+            cur = []
+            for x in (self.Ncap[s], 2 * Tcap, self.Ncap[s], self.Ncap[s], A + 1):
+                cur.append(off)
+                off += al(x)
+            self.ioff.append(cur)
+        self.islab_n = off
+        # fp32 slab: unit rows + inverse norms per scale;  bf16 slab: padded operand matrices
+        self.foff, off = [], 0
+        for s in range(S):
+            self.foff.append((off, off + al(self.Ncap[s] * Cc)))
+            off += al(self.Ncap[s] * Cc) + al(self.Ncap[s])
+        self.fslab_n = off
+        self.boff, off = [], 0
+        for s in range(S):
+            self.boff.append(off)
+            off += al(self.Ncap[s], 256) * self.C_pad
+        self.bslab_n = off
+        # terms (V2.py:55 via _ms.py:53-59; cross-scale _ms.py:62-80)
+        terms = [(s, s, True, spec.weights[s], spec.temperature, False) for s in range(S)]
+        self.cs_logged = []
+        if spec.cross_scale and not single_scale:
+            assert S > 1, "cross_scale_contrast needs at least two scales (_ms.py:63-64)"
+            need_dk = not spec.detach_deepest
+            terms.append((0, S - 1, False, spec.w_high_low, spec.cs_temperature, need_dk))
+            if not spec.detach_deepest:
+                self.cs_logged.append(len(terms) - 1)
+            if S > 2:
+                terms.append((0, S - 2, False, spec.w_high_mid, spec.cs_temperature, need_dk))
+                self.cs_logged.append(len(terms) - 1)
+        if len(terms) > _lib.MAX_TERMS:
+            raise ValueError(f"{len(terms)} loss terms exceed the supported {_lib.MAX_TERMS}")
+        self.terms = terms
+        self.soff, off = [], 0          # stats: neg, pos, S per term (zero-initialised)
+        for a, *_ in terms:
+            self.soff.append(off)
+            off += 3 * al(self.Ncap[a])
+        self.stats_n = off
+        self.coff, off = [], 0          # coefficients + per-term losses + total
+        for a, *_ in terms:
+            self.coff.append(off)
+            off += 2 * al(self.Ncap[a])
+        self.out_off = off
+        self.misc_n = off + al(len(terms) + 1)
+        job = _lib.SimJob()
+        job.num_terms, job.C_pad, job.num_classes = len(terms), self.C_pad, A
+        for i, (a, k, self_mask, weight, tau, need_dk) in enumerate(terms):
+            t = job.terms[i]
+            t.N1, t.N2 = self.Ncap[a], self.Ncap[k]
+            t.self_mask, t.need_dk, t.temperature, t.weight, t.a_set, t.k_set = int(self_mask), int(need_dk), tau, \
+                weight, a, k
+        self.work_bytes = lib.mscs_sim_workspace_bytes(C.byref(job))
+        self.dF_off, off = [], 0
+        for s in range(S):
+            self.dF_off.append(off)
+            off += self.Ncap[s] * self.C_pad
+        self.dF_n = off
+
+
+_step_plans = {}
+
+
+def _step_plan(dev, label_shape, feat_shapes, spec, single_scale):
+    key = (dev, tuple(label_shape), tuple(feat_shapes), spec.num_classes, spec.temperature, spec.cs_temperature,
+           spec.min_views, spec.max_views, spec.max_total, tuple(spec.weights), spec.cross_scale,
+           spec.detach_deepest, spec.w_high_low, spec.w_high_mid, single_scale)
+    p = _step_plans.get(key)
+    if p is None:
+        p = _step_plans[key] = _StepPlan(dev, label_shape, feat_shapes, spec, single_scale)
+    return p
+
+
+class _StepState:
+    """Buffers of one call (kept alive for the backward)."""
+    pass
+
+
+def run_forward(sp, labels, feats32, needs):
+    lib = _lib.load()
+    dev, S, A, spec = sp.dev, sp.S, sp.A, sp.spec
+    st = _stream()
+    i32, f32, u8 = torch.int32, torch.float32, torch.uint8
+    # ---- everything that does not need the plan: before the sync ----
+    ws = torch.empty(sp.ws_bytes, dtype=u8, device=dev)
+    plan_dev = torch.empty(S * C.sizeof(_lib.ScalePlan), dtype=u8, device=dev)
+    with _timed("sample"):
+        _lib.check(lib.mscs_sample_plan(C.byref(sp.cfg), labels.data_ptr(), ws.data_ptr(), plan_dev.data_ptr(), st),
+                   "mscs_sample_plan")
+        islab = torch.empty(sp.islab_n, dtype=i32, device=dev)
+        fslab = torch.empty(sp.fslab_n, dtype=f32, device=dev)
+        bslab = torch.empty(sp.bslab_n, dtype=torch.bfloat16, device=dev)
+        stats = torch.zeros(sp.stats_n, dtype=f32, device=dev)
+        misc = torch.empty(sp.misc_n, dtype=f32, device=dev)
+        work = torch.empty(sp.work_bytes, dtype=u8, device=dev)
+        gradbufs = _GradBuffers(feats32, needs) if any(needs) else None
+        mt, pos = torch_mt_state()
+        draws = _stream_cache(dev).acquire(mt, pos, sp.max_draws)
+        plan = (_lib.ScalePlan * S)()
+        _lib.check(lib.mscs_plan_fetch(plan_dev.data_ptr(), plan, S, st), "mscs_plan_fetch")     # the host sync
+        # ---- after the sync: three kinds of calls ----
+        for s in range(S):
+            if plan[s].error == 1:   # reference: torch.min() of an empty tensor raises (V2.py:110)
+                raise RuntimeError(f"scale {s}: no (image, class) pair has >= min_views_per_class="
+                                   f"{spec.min_views} pixels (the reference raises here too, V2.py:110)")
+            if plan[s].error == 2:   # reference: 0-d squeeze then .shape[0] raises (V2.py:119-121)
+                raise IndexError(f"scale {s}: a kept class has a single pixel (the reference raises here too)")
+        total = sum(int(plan[s].draws) for s in range(S))
+        ibase = islab.data_ptr()
+        arrs = [_lib.ptr_array([ibase + 4 * sp.ioff[s][k] for s in range(S)]) for k in range(5)]
+        _lib.check(lib.mscs_sample_select(C.byref(sp.cfg), plan, ws.data_ptr(), draws.data_ptr(), *arrs, st),
+                   "mscs_sample_select")
+    samples = [ScaleSample(plan[s].T, plan[s].V, plan[s].N, bool(plan[s].log_flag), plan[s].dl_h, plan[s].dl_w,
+                           islab, sp.ioff[s], A) for s in range(S)]
+    fbase, bbase = fslab.data_ptr(), bslab.data_ptr()
+    with _timed("gather"):
+        for s in range(S):
+            n, Cc, h, w = sp.feat_shapes[s]
+            if gradbufs is not None and gradbufs.slots[s] is not None:
+                _lib.check(lib.mscs_slot_map(samples[s].ptr(2), samples[s].N, n * h * w,
+                                             gradbufs.slots[s].data_ptr(), st), "mscs_slot_map")
+            _lib.check(lib.mscs_gather_normalize(feats32[s].data_ptr(), n, Cc, h * w, samples[s].ptr(2), samples[s].N,
+                                                 bbase + 2 * sp.boff[s], fbase + 4 * sp.foff[s][0],
+                                                 fbase + 4 * sp.foff[s][1], st), "mscs_gather_normalize")
+    job = _lib.SimJob()
+    job.num_terms, job.C_pad, job.num_classes = len(sp.terms), sp.C_pad, A
+    sbase, mbase = stats.data_ptr(), misc.data_ptr()
+    for i, (a, k, self_mask, weight, tau, need_dk) in enumerate(sp.terms):
+        t = job.terms[i]
+        t.a_bf16, t.k_bf16 = bbase + 2 * sp.boff[a], bbase + 2 * sp.boff[k]
+        t.a_cls, t.k_seg = samples[a].ptr(3), samples[k].ptr(4)
+        t.k_cls, t.a_seg = samples[k].ptr(3), samples[a].ptr(4)
+        t.N1, t.N2, t.self_mask, t.need_dk = samples[a].N, samples[k].N, int(self_mask), int(need_dk)
+        t.temperature, t.weight, t.a_set, t.k_set = tau, weight, a, k
+        n1 = (sp.Ncap[a] + 15) // 16 * 16
+        t.neg_sum = sbase + 4 * sp.soff[i]
+        t.pos_sum = sbase + 4 * (sp.soff[i] + n1)
+        t.s_sum = sbase + 4 * (sp.soff[i] + 2 * n1)
+        t.coef_s = mbase + 4 * sp.coff[i]
+        t.coef_pn = mbase + 4 * (sp.coff[i] + n1)
+    nt = len(sp.terms)
+    job.term_loss, job.total_loss = mbase + 4 * sp.out_off, mbase + 4 * (sp.out_off + nt)
+    job.work = work.data_ptr()
+    with _timed("sim_fwd"):
+        _lib.check(lib.mscs_sim_forward(C.byref(job), st), "mscs_sim_forward")
+    # host-side generator bookkeeping, off the GPU's critical path
+    mt2, pos2 = torch_mt_advance(mt, pos, total)
+    _stream_cache(dev).release_and_prefetch(mt2, pos2, sp.max_draws)
+    state = _StepState()
+    state.sp, state.job, state.samples, state.gradbufs = sp, job, samples, gradbufs
+    state.keep = (ws, islab, fslab, bslab, stats, misc, work)
+    state.fslab, state.term_loss = fslab, misc[sp.out_off:sp.out_off + nt]
+    state.total = misc[sp.out_off + nt]
+    state.num_ms, state.cs_logged = S, sp.cs_logged
+    return state
+
+
+def run_backward(state, grad_out, needs, shapes, dtypes):
+    lib = _lib.load()
+    sp = state.sp
+    dev, S = sp.dev, sp.S
+    st = _stream()
+    dF = torch.zeros(sp.dF_n, dtype=torch.float32, device=dev)
+    base = dF.data_ptr()
+    ptrs = [0] * _lib.MAX_SCALES
+    lds = (C.c_int32 * _lib.MAX_SCALES)()
+    for s in range(S):
+        ptrs[s], lds[s] = base + 4 * sp.dF_off[s], sp.C_pad
+    g = grad_out.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+    with _timed("sim_bwd"):
+        _lib.check(lib.mscs_sim_backward(C.byref(state.job), g.data_ptr(), _lib.ptr_array(ptrs), lds, st),
+                   "mscs_sim_backward")
+    grads = []
+    fbase = state.fslab.data_ptr()
+    with _timed("scatter"):
+        gb = state.gradbufs
+        if gb is not None:
+            torch.cuda.current_stream().wait_event(gb.ready)
+        for s in range(S):
+            if not needs[s]:
+                grads.append(None)
+                continue
+            n, Cc, h, w = shapes[s]
+            smp = state.samples[s]
+            pre, slot = gb.take(s) if gb is not None else (None, None)
+            if pre is not None:
+                out = pre
+                _lib.check(lib.mscs_scatter_sectors(ptrs[s], sp.C_pad, fbase + 4 * sp.foff[s][0],
+                                                    fbase + 4 * sp.foff[s][1], slot.data_ptr(), n, Cc, h * w,
+                                                    out.data_ptr(), st), "mscs_scatter_sectors")
+            else:
+                out = torch.empty(shapes[s], dtype=torch.float32, device=dev)
+                _lib.check(lib.mscs_scatter_grad(ptrs[s], sp.C_pad, fbase + 4 * sp.foff[s][0],
+                                                 fbase + 4 * sp.foff[s][1], smp.ptr(2), smp.N, n, Cc, h * w,
+                                                 out.data_ptr(), 1, st), "mscs_scatter_grad")
+            grads.append(out if dtypes[s] == torch.float32 else out.to(dtypes[s]))
+    return grads
 
 
 # ---- the autograd.Function ----------------------------------------------------------------
@@ -448,19 +686,14 @@ class MsCsContrastiveFn(torch.autograd.Function):
         if labels.device != feats32[0].device:
             labels = labels.to(feats32[0].device)
         needs = [bool(ctx.needs_input_grad[4 + i]) for i in range(len(feats))]
+        if labels.dtype != torch.int64:
+            labels = labels.long()
+        labels = labels.contiguous()
         with torch.cuda.device(feats32[0].device), _pin_stream():
-            with _timed("sample"):
-                samples, finish_rng = sample_anchors(labels, [tuple(f.shape[-2:]) for f in feats32], spec,
-                                                     defer_rng=True)
-            ctx.gradbufs = _GradBuffers(feats32, samples, needs) if any(needs) else None
-            with _timed("gather"):
-                sets = [gather_normalize(f, s) for f, s in zip(feats32, samples)]
-            state = build_job(spec, samples, sets, single_scale)
-            with _timed("sim_fwd"):
-                sim_forward(state)
-            finish_rng()          # host-side generator bookkeeping, off the GPU's critical path
-        holder["samples"], holder["state"] = samples, state
-        ctx.samples, ctx.sets, ctx.state = samples, sets, state
+            sp = _step_plan(feats32[0].device, labels.shape, [tuple(f.shape) for f in feats32], spec, single_scale)
+            state = run_forward(sp, labels, feats32, needs)
+        holder["samples"], holder["state"] = state.samples, state
+        ctx.state, ctx.needs = state, needs
         ctx.shapes = [tuple(f.shape) for f in feats]
         ctx.dtypes = [f.dtype for f in feats]
         total = state.total.reshape(())
@@ -470,17 +703,6 @@ class MsCsContrastiveFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_total, _grad_terms):
-        with torch.cuda.device(ctx.sets[0].bf16.device), _pin_stream():
-            dFs = sim_backward(ctx.state, ctx.sets, grad_total)
-            grads = []
-            with _timed("scatter"):
-                if ctx.gradbufs is not None:
-                    torch.cuda.current_stream().wait_event(ctx.gradbufs.ready)
-                for s in range(len(ctx.sets)):
-                    if ctx.needs_input_grad[4 + s]:
-                        pre, slot = ctx.gradbufs.take(s) if ctx.gradbufs is not None else (None, None)
-                        grads.append(scatter_grad(dFs[s], ctx.sets[s], ctx.samples[s], ctx.shapes[s], ctx.dtypes[s],
-                                                  pre, slot))
-                    else:
-                        grads.append(None)
+        with torch.cuda.device(ctx.state.sp.dev), _pin_stream():
+            grads = run_backward(ctx.state, grad_total, ctx.needs, ctx.shapes, ctx.dtypes)
         return (None, None, None, None, *grads)

@@ -283,46 +283,45 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
   return y;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_mt_stream(const uint32_t* __restrict__ state, int pos, long long total, uint32_t* __restrict__ out) {
   __shared__ uint32_t buf[2][624];
   const int tid = threadIdx.x;
-  for (int i = tid; i < 624; i += 256) buf[0][i] = state[i];
+  for (int i = tid; i < 624; i += 1024) buf[0][i] = state[i];
   __syncthreads();
-  // remaining words of the current block
-  for (int j = pos + tid; j < 624; j += 256) {
-    long long o = j - pos;
-    if (o < total) out[o] = mt_temper(buf[0][j]);
-  }
-  long long produced = 624 - pos;
-  int cur = 0;
-  // every thread tempers and stores the word it has just generated: no separate output pass
+  // Two warp groups, one barrier per 624-word block:
+  //  * threads 0..226 regenerate the NEXT block.  Thread t owns the words t, t+227 and t+454:
+  //    new[t] needs only the old block, new[t+227] = new[t] ^ twist(old[t+227], old[t+228]) and
+  //    new[t+454] = new[t+227] ^ twist(old[t+454], old[t+455]) chain inside the thread, so the three
+  //    dependent phases of the textbook regeneration need no inter-thread synchronisation (word 623
+  //    needs new[0], which its owner recomputes);
+  //  * threads 256..879 store the CURRENT block meanwhile (one raw word each; tempering is left to
+  //    the consumer, which touches only V of the count-1 words of a pair).
+  long long produced = 0;
+  int first = pos, cur = 0;          // words [first, 624) of buf[cur] are the next outputs
   while (produced < total) {
     const uint32_t* c = buf[cur];
-    uint32_t* nx = buf[cur ^ 1];
-    uint32_t* o = out + produced;
-    const long long left = total - produced;
     if (tid < 227) {
-      const uint32_t v = c[tid + 397] ^ mt_twist(c[tid], c[tid + 1]);
-      nx[tid] = v;
-      if (tid < left) o[tid] = mt_temper(v);
+      uint32_t* nx = buf[cur ^ 1];
+      const uint32_t a = c[tid + 397] ^ mt_twist(c[tid], c[tid + 1]);
+      const uint32_t b = a ^ mt_twist(c[tid + 227], c[tid + 228]);
+      nx[tid] = a;
+      nx[tid + 227] = b;
+      if (tid < 169) {
+        nx[tid + 454] = b ^ mt_twist(c[tid + 454], c[tid + 455]);
+      } else if (tid == 169) {
+        const uint32_t n0 = c[397] ^ mt_twist(c[0], c[1]);
+        nx[623] = b ^ mt_twist(c[623], n0);
+      }
+    } else if (tid >= 256) {
+      const long long left = total - produced;
+      const int n = (int)(left < (long long)(624 - first) ? left : (long long)(624 - first));
+      const int j = tid - 256;
+      if (j < n) out[produced + j] = c[first + j];      // raw state word: k_fy_select tempers what it uses
     }
     __syncthreads();
-    if (tid < 227) {
-      const int k = 227 + tid;
-      const uint32_t v = nx[tid] ^ mt_twist(c[k], c[k + 1]);
-      nx[k] = v;
-      if (k < left) o[k] = mt_temper(v);
-    }
-    __syncthreads();
-    if (tid < 170) {
-      const int k = 454 + tid;
-      const uint32_t v = (k < 623) ? (nx[k - 227] ^ mt_twist(c[k], c[k + 1])) : (nx[396] ^ mt_twist(c[623], nx[0]));
-      nx[k] = v;
-      if (k < left) o[k] = mt_temper(v);
-    }
-    __syncthreads();
-    produced += 624;
+    produced += 624 - first;
+    first = 0;
     cur ^= 1;
   }
 }
@@ -364,7 +363,7 @@ k_fy_select(const __grid_constant__ SampleLayout L, const __grid_constant__ Sele
   }
   for (int i = tid; i < V; i += blockDim.x) {
     int t = i;
-    if (i < cnt - 1) t = i + (int)(u[i] % (uint32_t)(cnt - i));
+    if (i < cnt - 1) t = i + (int)(mt_temper(u[i]) % (uint32_t)(cnt - i));
     t_arr[i] = t;
     w_arr[i] = -1;
   }
@@ -474,7 +473,7 @@ extern "C" int mscs_mt19937_stream(const uint32_t* mt_state_host, int mt_pos, ui
   // the 624 state words are staged behind the stream (the buffer holds n_words + 1024 words)
   uint32_t* state_dev = draws_dev + align_up((size_t)n_words, 64);
   MSCS_CUDA(cudaMemcpyAsync(state_dev, mt_state_host, sizeof(uint32_t) * 624, cudaMemcpyHostToDevice, st));
-  k_mt_stream<<<1, 256, 0, st>>>(state_dev, mt_pos, (long long)n_words, draws_dev);
+  k_mt_stream<<<1, 1024, 0, st>>>(state_dev, mt_pos, (long long)n_words, draws_dev);
   MSCS_LAUNCH_CHECK();
   return 0;
 }

@@ -55,7 +55,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 }
 
 template <int KB>
-__global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constant__ BwdArgs args) {
+__global__ void __maxnreg__(152) k_sim_bwd(const __grid_constant__ BwdArgs args) {
   constexpr int CP = KB * 64;                       // padded channel count = N of the second MMA
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));

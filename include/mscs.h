@@ -86,7 +86,8 @@ int mscs_sample_plan(const mscs_sample_cfg* cfg, const int64_t* labels, void* wo
  * the reference has ~1000). */
 int mscs_plan_fetch(const mscs_scale_plan* plan_dev, mscs_scale_plan* plan_host, int num_scales,
                     void* stream);
-/* MT19937 output stream (async): `n_words` tempered 32-bit outputs of the generator whose state is
+/* MT19937 stream (async): `n_words` consecutive UNTEMPERED state words (the consumer applies the
+ * tempering) of the generator whose state is
  * (mt_state_host[624], mt_pos in 0..624) -- the torch CPU default generator, which the reference
  * consumes through torch.randperm (V2.py:121).  draws_dev must hold n_words + 1024 words.  It only
  * depends on the generator state, so the host side produces it ahead of time on a side stream. */
