@@ -8,6 +8,8 @@ N=1 workload: cfg2 = HRNet-W48 Cityscapes ms+cs (4 scales, 512x1024 crops, bs 12
 N>1: one process per GPU, every rank runs the same per-GPU workload on its own batch (what the
 reference does under DDP: the loss is evaluated per rank on the local mini-batch, no collective on
 this path) -> weak scaling; value = anchor-pairs of all ranks / max-over-ranks device time.
+`--workload cfg5` is the POOLED cross-batch configuration instead (64 images in total, anchor rows
+sharded over the ranks, keys exchanged over NCCL): total work fixed -> strong scaling.
 
 Prints ONE JSON line (rank 0).  `--impl reference` times the CPU port of the reference
 (oracle/torch_port.py -- /root/reference is Python and cannot travel to the GPU box) on the host.
@@ -182,10 +184,17 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     cfg = synth.CONFIGS[args.workload]
     labels_h, feats_h = synth.make_inputs(args.workload)
+    pooled = args.workload == "cfg5"
+    comm = None
+    if pooled and world > 1:        # every rank owns a contiguous block of the 64 images
+        nl = cfg["n"] // world
+        labels_h = labels_h[rank * nl:(rank + 1) * nl].contiguous()
+        feats_h = [f[rank * nl:(rank + 1) * nl].contiguous() for f in feats_h]
+        comm = mscs_b200.TorchDistComm()
     labels_h = labels_h.pin_memory()
     feats_h = [f.pin_memory() for f in feats_h]
     cls = mscs_b200.DenseContrastiveLossV2 if cfg["single_scale"] else mscs_b200.DenseContrastiveLossV2_ms
-    mod = cls(dict(cfg["loss"]))
+    mod = cls(dict(cfg["loss"]), comm=comm) if comm is not None else cls(dict(cfg["loss"]))
     labels = labels_h.to(dev)
     feats = [f.to(dev).requires_grad_(True) for f in feats_h]
 
@@ -223,7 +232,8 @@ def main():
     if dist is not None:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = float(ms) / args.steps
-    value = pairs * world / (ms_step * 1e-3)
+    share = 1 if pooled else world       # pooled: `pairs` already is the whole job
+    value = pairs * share / (ms_step * 1e-3)
 
     # ---- end to end through the public API with HOST buffers -------------------------------
     h2d = labels_h.numel() * 8 + sum(f.numel() * 4 for f in feats_h)
@@ -247,7 +257,7 @@ def main():
     if dist is not None:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_ms = float(ms2) / n_e2e
-    e2e_val = pairs * world / (e2e_ms * 1e-3)
+    e2e_val = pairs * share / (e2e_ms * 1e-3)
 
     # ---- per-stage device times (separate instrumented steps) -> roofline of the dominant kernel
     _ops.TIMING = {}
@@ -258,8 +268,9 @@ def main():
     _ops.TIMING = None
     pk = peaks()
     Cdim = cfg["C"]
-    bwd_flops = 4.0 * Cdim * pairs            # K4: two gradient products per anchor pair
-    fwd_flops = 2.0 * Cdim * pairs
+    per_gpu = pairs / world if pooled else pairs
+    bwd_flops = 4.0 * Cdim * per_gpu          # K4: two gradient products per anchor pair
+    fwd_flops = 2.0 * Cdim * per_gpu
     t_bwd = stage_ms.get("sim_bwd", float("nan")) * 1e-3
     achieved = bwd_flops / t_bwd / 1e12
     roofline = {"bound": "tensor", "kernel": "k_sim_bwd", "achieved": achieved, "peak": pk["tflops"],
@@ -278,14 +289,18 @@ def main():
             dist.destroy_process_group()
         return
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong" if pooled else "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{args.workload}: " + {
-                "cfg2": "HRNet-W48 Cityscapes ms+cs loss, 4 scales, 512x1024 crops, bs 12, 256-d projector"}.get(
+                "cfg2": "HRNet-W48 Cityscapes ms+cs loss, 4 scales, 512x1024 crops, bs 12, 256-d projector",
+                "cfg5": "pooled cross-batch anchors, bs 64 in total, ms+cs, max_features_total 65536"}.get(
                     args.workload, args.workload),
                 "anchors_per_scale": NS, "anchor_pairs_per_step": pairs, "per_gpu_batch": cfg["n"],
                 "l2": "inputs (535 MB of features per step) exceed the 126 MB L2; no explicit flush",
-                "parallelism": f"replicas x{world} (loss evaluated per rank on its local batch, as under DDP)",
+                "parallelism": (f"pooled anchors, rows sharded x{world}, keys/statistics/gradient rows exchanged "
+                                f"with NCCL all-reduce" if pooled else
+                                f"replicas x{world} (loss evaluated per rank on its local batch, as under DDP)"),
                 "loss": float(loss)},
             "roofline": roofline, "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,

@@ -13,7 +13,7 @@ class SampleCfg(C.Structure):
     _fields_ = [("n", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("num_scales", C.c_int32),
                 ("fh", C.c_int32 * MAX_SCALES), ("fw", C.c_int32 * MAX_SCALES),
                 ("num_classes", C.c_int32), ("min_views", C.c_int32), ("max_views", C.c_int32),
-                ("max_total", C.c_int32)]
+                ("max_total", C.c_int32), ("n_global", C.c_int32), ("image_base", C.c_int32)]
 
 
 class ScalePlan(C.Structure):
@@ -27,6 +27,7 @@ class Term(C.Structure):
                 ("a_cls", C.c_void_p), ("k_seg", C.c_void_p), ("k_cls", C.c_void_p), ("a_seg", C.c_void_p),
                 ("N1", C.c_int32), ("N2", C.c_int32), ("self_mask", C.c_int32), ("need_dk", C.c_int32),
                 ("temperature", C.c_float), ("weight", C.c_float), ("a_set", C.c_int32), ("k_set", C.c_int32),
+                ("row_begin", C.c_int32), ("row_end", C.c_int32), ("krow_begin", C.c_int32), ("krow_end", C.c_int32),
                 ("neg_sum", C.c_void_p), ("pos_sum", C.c_void_p), ("s_sum", C.c_void_p),
                 ("coef_s", C.c_void_p), ("coef_pn", C.c_void_p)]
 
@@ -48,6 +49,9 @@ _SIGNATURES = {
     "mscs_sample_workspace_bytes": (C.c_size_t, [C.POINTER(SampleCfg)]),
     "mscs_sample_max_draws": (C.c_size_t, [C.POINTER(SampleCfg)]),
     "mscs_sample_plan": (C.c_int, [C.POINTER(SampleCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mscs_sample_counts_offset": (C.c_size_t, [C.POINTER(SampleCfg), C.c_int]),
+    "mscs_sample_hist": (C.c_int, [C.POINTER(SampleCfg), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mscs_sample_plan_from_counts": (C.c_int, [C.POINTER(SampleCfg), _PTRS, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mscs_plan_fetch": (C.c_int, [C.c_void_p, C.POINTER(ScalePlan), C.c_int, C.c_void_p]),
     "mscs_mt19937_stream": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]),
     "mscs_sample_select": (C.c_int, [C.POINTER(SampleCfg), C.POINTER(ScalePlan), C.c_void_p, C.c_void_p,
@@ -57,6 +61,8 @@ _SIGNATURES = {
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "mscs_sim_workspace_bytes": (C.c_size_t, [C.POINTER(SimJob)]),
     "mscs_sim_forward": (C.c_int, [C.POINTER(SimJob), C.c_void_p]),
+    "mscs_sim_forward_sweeps": (C.c_int, [C.POINTER(SimJob), C.c_void_p]),
+    "mscs_sim_finalize": (C.c_int, [C.POINTER(SimJob), C.c_void_p]),
     "mscs_sim_backward": (C.c_int, [C.POINTER(SimJob), C.c_void_p, _PTRS, C.POINTER(C.c_int32), C.c_void_p]),
     "mscs_debug_sim_forward_simt": (C.c_int, [C.POINTER(SimJob), _PTRS, C.c_void_p]),
     "mscs_debug_sim_backward_simt": (C.c_int, [C.POINTER(SimJob), _PTRS, C.c_void_p, _PTRS, C.POINTER(C.c_int32),

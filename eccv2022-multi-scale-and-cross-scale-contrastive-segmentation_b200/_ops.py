@@ -8,6 +8,7 @@ there is no fallback: a missing library or a non-sm_100 device raises.
 import ctypes as C
 import os
 import struct
+import threading
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -158,6 +159,7 @@ class _StreamCache:
         self.words = 0
         self.ready = None        # event: buffer `cur` complete
         self.last_use = [None, None]   # event: last main-stream reader of each buffer
+        self.lock = threading.Lock()
 
     def _generate(self, which, mt, pos, words):
         lib = _lib.load()
@@ -178,18 +180,20 @@ class _StreamCache:
 
     def acquire(self, mt, pos, words):
         """Buffer holding >= words outputs from (mt,pos); the current stream is made to wait for it."""
-        if self.key != (mt.tobytes(), pos) or self.words < words:
-            self._generate(self.cur ^ 1, mt, pos, words)
-        torch.cuda.current_stream().wait_event(self.ready)
-        return self.bufs[self.cur]
+        with self.lock:
+            if self.key != (mt.tobytes(), pos) or self.words < words:
+                self._generate(self.cur ^ 1, mt, pos, words)
+            torch.cuda.current_stream().wait_event(self.ready)
+            return self.bufs[self.cur]
 
     def release_and_prefetch(self, mt_next, pos_next, words):
         if os.environ.get("MSCS_NO_PREFETCH"):      # experiment switch: regenerate inline at the next call
             return
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream())
-        self.last_use[self.cur] = ev
-        self._generate(self.cur ^ 1, mt_next, pos_next, words)
+        with self.lock:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self.last_use[self.cur] = ev
+            self._generate(self.cur ^ 1, mt_next, pos_next, words)
 
 
 _stream_caches = {}
@@ -433,6 +437,68 @@ class _GradBuffers:
 
 
 
+# ---- pooled cross-batch mode: collectives -----------------------------------------------------
+class TorchDistComm:
+    """torch.distributed (NCCL over NVLink) collectives of the pooled mode: one process per GPU."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.owns_rng = True
+
+    def all_reduce(self, t):
+        self.dist.all_reduce(t, group=self.group)
+
+    def all_gather(self, t):
+        out = torch.empty(self.world * t.numel(), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, t.reshape(-1), group=self.group)
+        return out
+
+
+class ThreadComm:
+    """In-process emulation of `world` ranks on ONE device (one Python thread per rank, lock-step
+    collectives).  Test infrastructure for the pooled mode's host logic and row-range kernels."""
+
+    class _Shared:
+        def __init__(self, world):
+            import threading
+            self.world, self.slots, self.result = world, [None] * world, None
+            self.barrier = threading.Barrier(world)
+
+    def __init__(self, shared, rank):
+        self.sh, self.rank, self.world = shared, rank, shared.world
+        self.owns_rng = rank == 0          # the CPU generator is process-global: one rank publishes it
+
+    def _exchange(self, t, combine):
+        sh = self.sh
+        sh.slots[self.rank] = t
+        sh.barrier.wait()
+        if self.rank == 0:
+            torch.cuda.synchronize()
+            sh.result = combine(sh.slots)
+            torch.cuda.synchronize()
+        sh.barrier.wait()
+        res = sh.result
+        sh.barrier.wait()
+        return res
+
+    def all_reduce(self, t):
+        res = self._exchange(t, lambda ts: torch.stack([x.clone() for x in ts]).sum(0).to(ts[0].dtype))
+        t.copy_(res)
+
+    def all_gather(self, t):
+        return self._exchange(t, lambda ts: torch.cat([x.reshape(-1) for x in ts])).clone()
+
+
+def shard_rows(N, world, rank):
+    """128-aligned row range of `rank` among `world` ranks over N sorted anchor rows."""
+    per = ((N + 127) // 128 + world - 1) // world * 128
+    b = min(N, rank * per)
+    e = min(N, b + per)
+    return b, e
+
+
 # ---- fused host path of the autograd Function -------------------------------------------------
 class _StepPlan:
     """Everything of a call that depends only on shapes and configuration, computed once and cached:
@@ -440,10 +506,12 @@ class _StepPlan:
     every allocation and the MT19937 stream lookup happen BEFORE the one host sync of the forward
     pass, and only three kinds of C calls remain after it (select, gather, similarity forward)."""
 
-    def __init__(self, dev, label_shape, feat_shapes, spec, single_scale):
+    def __init__(self, dev, label_shape, feat_shapes, spec, single_scale, world=1, rank=0):
         lib = _lib.load()
         self.dev, self.spec, self.single_scale = dev, spec, single_scale
+        self.world, self.rank = world, rank
         n, H, W = label_shape
+        self.n_local, self.n_global = n, n * world
         self.S = S = len(feat_shapes)
         self.A = A = spec.num_classes
         self.feat_shapes = feat_shapes
@@ -453,6 +521,8 @@ class _StepPlan:
             cfg.fh[s], cfg.fw[s] = shp[2], shp[3]
         cfg.num_classes, cfg.min_views = A, spec.min_views
         cfg.max_views, cfg.max_total = spec.max_views, spec.max_total
+        if world > 1:
+            cfg.n_global, cfg.image_base = n * world, n * rank
         self.ws_bytes = lib.mscs_sample_workspace_bytes(C.byref(cfg))
         if self.ws_bytes == 0:
             raise RuntimeError("mscs_sample_workspace_bytes: " + lib.mscs_last_error().decode())
@@ -462,17 +532,18 @@ class _StepPlan:
             if shp[1] != Cc:
                 raise ValueError("all feature maps must have the same number of channels")
         self.C_pad = (Cc + 63) // 64 * 64
-        Tcap = n * (A - 1)
-        self.Ncap = [min(spec.max_total, n * shp[2] * shp[3]) for shp in feat_shapes]
+        Tcap = n * world * (A - 1)
+        self.Ncap = [min(spec.max_total, n * world * shp[2] * shp[3]) for shp in feat_shapes]
+        self.counts_off = [int(lib.mscs_sample_counts_offset(C.byref(cfg), s)) for s in range(S)]
         al = lambda x, a=16: (x + a - 1) // a * a
         # int32 slab: idx_ref, pair_ref, pix, cls, seg per scale
-        self.ioff, off = [], 0
-        for s in range(S):
-            cur = []
-            for x in (self.Ncap[s], 2 * Tcap, self.Ncap[s], self.Ncap[s], A + 1):
-                cur.append(off)
-                off += al(x)
-            self.ioff.append(cur)
+        self.ioff, off = [[0] * 5 for _ in range(S)], 0
+        for k in (0, 1, 2, 4, 3):           # the class arrays (k = 3) last and adjacent: one all-reduce in pooled mode
+            if k == 3:
+                self.cls_begin = off
+            for s in range(S):
+                self.ioff[s][k] = off
+                off += al((self.Ncap[s], 2 * Tcap, self.Ncap[s], self.Ncap[s], A + 1)[k])
         self.islab_n = off
         # fp32 slab: unit rows + inverse norms per scale;  bf16 slab: padded operand matrices
         self.foff, off = [], 0
@@ -529,13 +600,13 @@ class _StepPlan:
 _step_plans = {}
 
 
-def _step_plan(dev, label_shape, feat_shapes, spec, single_scale):
+def _step_plan(dev, label_shape, feat_shapes, spec, single_scale, world=1, rank=0):
     key = (dev, tuple(label_shape), tuple(feat_shapes), spec.num_classes, spec.temperature, spec.cs_temperature,
            spec.min_views, spec.max_views, spec.max_total, tuple(spec.weights), spec.cross_scale,
-           spec.detach_deepest, spec.w_high_low, spec.w_high_mid, single_scale)
+           spec.detach_deepest, spec.w_high_low, spec.w_high_mid, single_scale, world, rank)
     p = _step_plans.get(key)
     if p is None:
-        p = _step_plans[key] = _StepPlan(dev, label_shape, feat_shapes, spec, single_scale)
+        p = _step_plans[key] = _StepPlan(dev, label_shape, feat_shapes, spec, single_scale, world, rank)
     return p
 
 
@@ -544,7 +615,7 @@ class _StepState:
     pass
 
 
-def run_forward(sp, labels, feats32, needs):
+def run_forward(sp, labels, feats32, needs, comm=None):
     lib = _lib.load()
     dev, S, A, spec = sp.dev, sp.S, sp.A, sp.spec
     st = _stream()
@@ -552,10 +623,23 @@ def run_forward(sp, labels, feats32, needs):
     # ---- everything that does not need the plan: before the sync ----
     ws = torch.empty(sp.ws_bytes, dtype=u8, device=dev)
     plan_dev = torch.empty(S * C.sizeof(_lib.ScalePlan), dtype=u8, device=dev)
+    pooled = comm is not None and comm.world > 1
     with _timed("sample"):
-        _lib.check(lib.mscs_sample_plan(C.byref(sp.cfg), labels.data_ptr(), ws.data_ptr(), plan_dev.data_ptr(), st),
-                   "mscs_sample_plan")
-        islab = torch.empty(sp.islab_n, dtype=i32, device=dev)
+        if not pooled:
+            _lib.check(lib.mscs_sample_plan(C.byref(sp.cfg), labels.data_ptr(), ws.data_ptr(), plan_dev.data_ptr(),
+                                            st), "mscs_sample_plan")
+        else:
+            # local histograms -> all-gather of the (image, class) counts -> identical global plan on every rank
+            _lib.check(lib.mscs_sample_hist(C.byref(sp.cfg), labels.data_ptr(), ws.data_ptr(), st), "mscs_sample_hist")
+            nA = sp.n_local * A
+            local = torch.cat([ws[sp.counts_off[s]:sp.counts_off[s] + 4 * nA].view(i32) for s in range(S)])
+            gathered = comm.all_gather(local).view(comm.world, S, nA)
+            counts_g = gathered.permute(1, 0, 2).contiguous()          # [S][n_global][A]
+            cptr = _lib.ptr_array([counts_g[s].data_ptr() for s in range(S)])
+            _lib.check(lib.mscs_sample_plan_from_counts(C.byref(sp.cfg), cptr, ws.data_ptr(), plan_dev.data_ptr(),
+                                                        st), "mscs_sample_plan_from_counts")
+        islab = torch.empty(sp.islab_n, dtype=i32, device=dev) if not pooled else \
+            torch.zeros(sp.islab_n, dtype=i32, device=dev)
         fslab = torch.empty(sp.fslab_n, dtype=f32, device=dev)
         bslab = torch.empty(sp.bslab_n, dtype=torch.bfloat16, device=dev)
         stats = torch.zeros(sp.stats_n, dtype=f32, device=dev)
@@ -575,11 +659,16 @@ def run_forward(sp, labels, feats32, needs):
                 raise IndexError(f"scale {s}: a kept class has a single pixel (the reference raises here too)")
         total = sum(int(plan[s].draws) for s in range(S))
         ibase = islab.data_ptr()
+        if pooled:       # rows of other ranks keep pix = -1 (not gathered / scattered here)
+            for s in range(S):
+                islab[sp.ioff[s][2]:sp.ioff[s][2] + sp.Ncap[s]].fill_(-1)
         arrs = [_lib.ptr_array([ibase + 4 * sp.ioff[s][k] for s in range(S)]) for k in range(5)]
         _lib.check(lib.mscs_sample_select(C.byref(sp.cfg), plan, ws.data_ptr(), draws.data_ptr(), *arrs, st),
                    "mscs_sample_select")
     samples = [ScaleSample(plan[s].T, plan[s].V, plan[s].N, bool(plan[s].log_flag), plan[s].dl_h, plan[s].dl_w,
                            islab, sp.ioff[s], A) for s in range(S)]
+    if pooled:           # class of every row on every rank (disjoint supports: the sum is the union)
+        comm.all_reduce(islab[sp.cls_begin:])
     fbase, bbase = fslab.data_ptr(), bslab.data_ptr()
     with _timed("gather"):
         for s in range(S):
@@ -590,6 +679,8 @@ def run_forward(sp, labels, feats32, needs):
             _lib.check(lib.mscs_gather_normalize(feats32[s].data_ptr(), n, Cc, h * w, samples[s].ptr(2), samples[s].N,
                                                  bbase + 2 * sp.boff[s], fbase + 4 * sp.foff[s][0],
                                                  fbase + 4 * sp.foff[s][1], st), "mscs_gather_normalize")
+    if pooled:           # normalised rows of all ranks: all-gather expressed as a sum of disjoint supports
+        comm.all_reduce(bslab)
     job = _lib.SimJob()
     job.num_terms, job.C_pad, job.num_classes = len(sp.terms), sp.C_pad, A
     sbase, mbase = stats.data_ptr(), misc.data_ptr()
@@ -600,6 +691,9 @@ def run_forward(sp, labels, feats32, needs):
         t.k_cls, t.a_seg = samples[k].ptr(3), samples[a].ptr(4)
         t.N1, t.N2, t.self_mask, t.need_dk = samples[a].N, samples[k].N, int(self_mask), int(need_dk)
         t.temperature, t.weight, t.a_set, t.k_set = tau, weight, a, k
+        if pooled:       # anchor (and key) rows are sharded over the ranks in 128-row granules
+            t.row_begin, t.row_end = shard_rows(samples[a].N, comm.world, comm.rank)
+            t.krow_begin, t.krow_end = shard_rows(samples[k].N, comm.world, comm.rank)
         n1 = (sp.Ncap[a] + 15) // 16 * 16
         t.neg_sum = sbase + 4 * sp.soff[i]
         t.pos_sum = sbase + 4 * (sp.soff[i] + n1)
@@ -610,16 +704,22 @@ def run_forward(sp, labels, feats32, needs):
     job.term_loss, job.total_loss = mbase + 4 * sp.out_off, mbase + 4 * (sp.out_off + nt)
     job.work = work.data_ptr()
     with _timed("sim_fwd"):
-        _lib.check(lib.mscs_sim_forward(C.byref(job), st), "mscs_sim_forward")
+        if not pooled:
+            _lib.check(lib.mscs_sim_forward(C.byref(job), st), "mscs_sim_forward")
+        else:
+            _lib.check(lib.mscs_sim_forward_sweeps(C.byref(job), st), "mscs_sim_forward_sweeps")
+            comm.all_reduce(stats)       # row statistics of all ranks' rows
+            _lib.check(lib.mscs_sim_finalize(C.byref(job), st), "mscs_sim_finalize")
     # host-side generator bookkeeping, off the GPU's critical path
-    mt2, pos2 = torch_mt_advance(mt, pos, total)
-    _stream_cache(dev).release_and_prefetch(mt2, pos2, sp.max_draws)
+    if comm is None or comm.owns_rng:
+        mt2, pos2 = torch_mt_advance(mt, pos, total)
+        _stream_cache(dev).release_and_prefetch(mt2, pos2, sp.max_draws)
     state = _StepState()
     state.sp, state.job, state.samples, state.gradbufs = sp, job, samples, gradbufs
     state.keep = (ws, islab, fslab, bslab, stats, misc, work)
     state.fslab, state.term_loss = fslab, misc[sp.out_off:sp.out_off + nt]
     state.total = misc[sp.out_off + nt]
-    state.num_ms, state.cs_logged = S, sp.cs_logged
+    state.num_ms, state.cs_logged, state.comm = S, sp.cs_logged, comm if pooled else None
     return state
 
 
@@ -638,6 +738,8 @@ def run_backward(state, grad_out, needs, shapes, dtypes):
     with _timed("sim_bwd"):
         _lib.check(lib.mscs_sim_backward(C.byref(state.job), g.data_ptr(), _lib.ptr_array(ptrs), lds, st),
                    "mscs_sim_backward")
+    if state.comm is not None:      # every rank computed the rows of its range; owners need their rows
+        state.comm.all_reduce(dF)
     grads = []
     fbase = state.fslab.data_ptr()
     with _timed("scatter"):
@@ -674,6 +776,7 @@ class MsCsContrastiveFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, labels, spec, single_scale, holder, *feats):
+        comm = holder.get("comm")
         if not _lib.load().mscs_device_ok():
             raise RuntimeError("mscs_b200 needs a compute-capability 10.x (B200) device; no fallback exists")
         feats32 = []
@@ -690,8 +793,10 @@ class MsCsContrastiveFn(torch.autograd.Function):
             labels = labels.long()
         labels = labels.contiguous()
         with torch.cuda.device(feats32[0].device), _pin_stream():
-            sp = _step_plan(feats32[0].device, labels.shape, [tuple(f.shape) for f in feats32], spec, single_scale)
-            state = run_forward(sp, labels, feats32, needs)
+            world, rank = (comm.world, comm.rank) if comm is not None else (1, 0)
+            sp = _step_plan(feats32[0].device, labels.shape, [tuple(f.shape) for f in feats32], spec, single_scale,
+                            world, rank)
+            state = run_forward(sp, labels, feats32, needs, comm)
         holder["samples"], holder["state"] = state.samples, state
         ctx.state, ctx.needs = state, needs
         ctx.shapes = [tuple(f.shape) for f in feats]

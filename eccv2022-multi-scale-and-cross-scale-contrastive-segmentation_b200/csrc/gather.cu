@@ -24,6 +24,10 @@ k_gather_normalize(const float* __restrict__ feat, int C, int C_pad, int plane, 
     return;
   }
   const int gp = pix[row];
+  if (gp < 0) {                         // pooled mode: the row is owned by another rank (all-reduced later)
+    for (int c = lane; c < C_pad; c += 32) orow[c] = __float2bfloat16(0.f);
+    return;
+  }
   const int b = gp / plane, p = gp - b * plane;
   const float* src = feat + ((size_t)b * C) * plane + p;
   float v[kMaxC / 32];
@@ -69,6 +73,7 @@ k_scatter_grad(const float* __restrict__ dF, int ldF, const float* __restrict__ 
   const float inv = inv_norm[row];
   const bool clamped = inv >= 1e12f;        // ||x|| <= eps: F.normalize divides by the constant eps
   const int gp = pix[row];
+  if (gp < 0) return;
   const int b = gp / plane, p = gp - b * plane;
   float* dst = dfeat + ((size_t)b * C) * plane + p;
 #pragma unroll
@@ -81,7 +86,7 @@ k_scatter_grad(const float* __restrict__ dF, int ldF, const float* __restrict__ 
 // slot map: slot[image*plane + pixel] = sorted anchor row sampled there, or -1
 __global__ void k_slot_map(const int* __restrict__ pix, int N, int* __restrict__ slot) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < N) slot[pix[i]] = i;
+  if (i < N && pix[i] >= 0) slot[pix[i]] = i;      // negative: row owned by another rank (pooled mode)
 }
 
 // Sector writer: the dense gradient is already zero; one warp per 8-pixel octet (= one 32-byte

@@ -24,6 +24,7 @@ struct ScaleGeo {
 
 struct SampleLayout {
   int S, n, H, W, A;
+  int ng, b0;                    // pooled mode: images of all ranks / global index of this rank's first image
   ScaleGeo g[MSCS_MAX_SCALES];
   int total_tiles;
   size_t counts_begin, counts_bytes;   // contiguous region holding every scale's counts
@@ -53,6 +54,9 @@ static int make_layout(const mscs_sample_cfg* cfg, SampleLayout* L) {
   MSCS_CHECK_ARG(cfg->num_classes >= 2 && cfg->num_classes <= 32767, "num_classes %d out of range",
                  cfg->num_classes);
   L->S = cfg->num_scales; L->n = cfg->n; L->H = cfg->H; L->W = cfg->W; L->A = cfg->num_classes;
+  L->ng = cfg->n_global > 0 ? cfg->n_global : cfg->n;
+  L->b0 = cfg->n_global > 0 ? cfg->image_base : 0;
+  MSCS_CHECK_ARG(L->b0 >= 0 && L->b0 + L->n <= L->ng, "image_base/n_global inconsistent");
   size_t off = 0;
   int tile_base = 0;
   // counts first, contiguous, so one memset clears them all
@@ -80,7 +84,7 @@ static int make_layout(const mscs_sample_cfg* cfg, SampleLayout* L) {
     g.ident_y = (g.dl_h == cfg->H); g.ident_x = (g.dl_w == cfg->W);
     g.sy = (float)cfg->H / (float)g.dl_h;
     g.sx = (float)cfg->W / (float)g.dl_w;
-    g.pair_cap = L->n * (L->A - 1);
+    g.pair_cap = L->ng * (L->A - 1);
     g.off_dlab = off;    off += align_up(sizeof(short) * (size_t)L->n * g.hw, 256);
     g.off_tilecnt = off; off += align_up(sizeof(int) * (size_t)L->n * g.tiles * L->A, 256);
     g.off_kmap = off;    off += align_up(sizeof(int) * (size_t)g.pair_cap, 256);
@@ -165,14 +169,14 @@ __global__ void k_tile_scan(const __grid_constant__ SampleLayout L, char* ws) {
 // count (V2.py:110), views-per-class rule (V2.py:64-84), MT19937 stream offsets (one
 // randperm(count) = count-1 draws per pair, V2.py:121), and the class-sorted row layout.
 // ---------------------------------------------------------------------------------------
-struct PlanCfg { int min_views, max_views, max_total; };
+struct PlanCfg { int min_views, max_views, max_total; const int* counts[MSCS_MAX_SCALES]; };
 
 __global__ void __launch_bounds__(1024)
 k_plan(const __grid_constant__ SampleLayout L, PlanCfg pc, char* ws, mscs_scale_plan* plan) {
   const int s = blockIdx.x;
   const ScaleGeo& g = L.g[s];
-  const int A = L.A, n = L.n;
-  const int* counts = reinterpret_cast<const int*>(ws + g.off_counts);
+  const int A = L.A, n = L.ng;
+  const int* counts = pc.counts[s] ? pc.counts[s] : reinterpret_cast<const int*>(ws + g.off_counts);
   int* kmap = reinterpret_cast<int*>(ws + g.off_kmap);
   int* seg = reinterpret_cast<int*>(ws + g.off_seg);
   PairArrays pa = pair_arrays(ws, g);
@@ -350,7 +354,11 @@ k_fy_select(const __grid_constant__ SampleLayout L, const __grid_constant__ Sele
   const ScaleGeo& g = L.g[s];
   const int V = a.V[s], A = L.A;
   PairArrays pa = pair_arrays(ws, g);
-  const int b = pa.b[k], c = pa.c[k], cnt = pa.cnt[k], dst = pa.dst[k];
+  if (k == 0)                                   // class segments: identical on every rank
+    for (int i = threadIdx.x; i <= A; i += blockDim.x) a.seg[s][i] = reinterpret_cast<const int*>(ws + g.off_seg)[i];
+  const int bg = pa.b[k], c = pa.c[k], cnt = pa.cnt[k], dst = pa.dst[k];
+  const int b = bg - L.b0;                      // local image index; other ranks' pairs are skipped
+  if (b < 0 || b >= L.n) return;
   const uint32_t* u = draws + a.draw_base[s] + pa.off[k];
   extern __shared__ int sm[];
   int* t_arr = sm;            // t_i = i + z_i : position swapped with i at step i
@@ -358,8 +366,8 @@ k_fy_select(const __grid_constant__ SampleLayout L, const __grid_constant__ Sele
   int* r_arr = sm + 2 * V;    // resolved rank perm[i]
   const int tid = threadIdx.x;
   if (tid == 0) {
-    a.pair_ref[s][2 * k] = b; a.pair_ref[s][2 * k + 1] = c;
-    if (k == 0) for (int i = 0; i <= A; ++i) a.seg[s][i] = reinterpret_cast<const int*>(ws + g.off_seg)[i];
+    a.pair_ref[s][2 * k] = bg; a.pair_ref[s][2 * k + 1] = c;
+
   }
   for (int i = tid; i < V; i += blockDim.x) {
     int t = i;
@@ -428,17 +436,21 @@ extern "C" size_t mscs_sample_max_draws(const mscs_sample_cfg* cfg) {
   SampleLayout L;
   if (make_layout(cfg, &L) != 0) return 0;
   size_t d = 0;
-  for (int s = 0; s < L.S; ++s) d += (size_t)L.n * L.g[s].hw;
+  for (int s = 0; s < L.S; ++s) d += (size_t)L.ng * L.g[s].hw;      // the stream covers the pairs of ALL ranks
   return d;
 }
 
-extern "C" int mscs_sample_plan(const mscs_sample_cfg* cfg, const int64_t* labels, void* workspace,
-                                mscs_scale_plan* plan_dev, void* stream_) {
+extern "C" size_t mscs_sample_counts_offset(const mscs_sample_cfg* cfg, int scale) {
+  SampleLayout L;
+  if (make_layout(cfg, &L) != 0 || scale < 0 || scale >= L.S) return (size_t)-1;
+  return L.g[scale].off_counts;
+}
+
+extern "C" int mscs_sample_hist(const mscs_sample_cfg* cfg, const int64_t* labels, void* workspace, void* stream_) {
   SampleLayout L;
   int rc = make_layout(cfg, &L);
   if (rc) return rc;
-  MSCS_CHECK_ARG(labels && workspace && plan_dev, "null pointer argument");
-  MSCS_CHECK_ARG(cfg->min_views >= 0 && cfg->max_views >= 1 && cfg->max_total >= 1, "bad sampling limits");
+  MSCS_CHECK_ARG(labels && workspace, "null pointer argument");
   cudaStream_t st = (cudaStream_t)stream_;
   char* ws = (char*)workspace;
   MSCS_CUDA(cudaMemsetAsync(ws + L.counts_begin, 0, L.counts_bytes, st));
@@ -447,10 +459,29 @@ extern "C" int mscs_sample_plan(const mscs_sample_cfg* cfg, const int64_t* label
   dim3 gs(ceil_div(L.n * L.A, 128), L.S);
   k_tile_scan<<<gs, 128, 0, st>>>(L, ws);
   MSCS_LAUNCH_CHECK();
-  PlanCfg pc{cfg->min_views, cfg->max_views, cfg->max_total};
-  k_plan<<<L.S, 1024, sizeof(int) * (L.A + 1), st>>>(L, pc, ws, plan_dev);
+  return 0;
+}
+
+extern "C" int mscs_sample_plan_from_counts(const mscs_sample_cfg* cfg, const int32_t* const* counts_global,
+                                            void* workspace, mscs_scale_plan* plan_dev, void* stream_) {
+  SampleLayout L;
+  int rc = make_layout(cfg, &L);
+  if (rc) return rc;
+  MSCS_CHECK_ARG(workspace && plan_dev, "null pointer argument");
+  MSCS_CHECK_ARG(cfg->min_views >= 0 && cfg->max_views >= 1 && cfg->max_total >= 1, "bad sampling limits");
+  MSCS_CHECK_ARG(L.ng == L.n || counts_global, "pooled mode needs the all-gathered counts");
+  PlanCfg pc{cfg->min_views, cfg->max_views, cfg->max_total, {}};
+  for (int s = 0; s < L.S; ++s) pc.counts[s] = counts_global ? counts_global[s] : nullptr;
+  k_plan<<<L.S, 1024, sizeof(int) * (L.A + 1), (cudaStream_t)stream_>>>(L, pc, (char*)workspace, plan_dev);
   MSCS_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int mscs_sample_plan(const mscs_sample_cfg* cfg, const int64_t* labels, void* workspace,
+                                mscs_scale_plan* plan_dev, void* stream_) {
+  int rc = mscs_sample_hist(cfg, labels, workspace, stream_);
+  if (rc) return rc;
+  return mscs_sample_plan_from_counts(cfg, nullptr, workspace, plan_dev, stream_);
 }
 
 extern "C" int mscs_plan_fetch(const mscs_scale_plan* plan_dev, mscs_scale_plan* plan_host, int num_scales,

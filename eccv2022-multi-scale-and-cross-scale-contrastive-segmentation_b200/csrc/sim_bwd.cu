@@ -365,8 +365,8 @@ extern "C" int mscs_sim_backward(const mscs_sim_job* job, const float* grad_out,
     args.p[i] = BwdDev{p.row_cls, p.col_seg, p.row_cs, p.row_cpn, p.row_neg, p.col_cs, p.col_cpn, p.col_neg,
                        dF_sets[p.row_set], dF_ld[p.row_set], p.n_rows, p.n_cols, p.self_mask, xm, ym,
                        p.scale_log2, p.out_scale};
-    b.t[i] = BuildTerm{p.row_cls, p.col_seg, p.n_rows, p.n_cols, nitems};
-    nitems += ceil_div(p.n_rows, 128);
+    b.t[i] = BuildTerm{p.row_cls, p.col_seg, p.n_rows, p.n_cols, nitems, p.rb_lo, 0, 1 << 30};
+    nitems += p.rb_hi - p.rb_lo;
   }
   b.num_terms = np; b.nitems = nitems; b.rows_per_item = 128; b.mode = 0;
   b.items = (WorkItem*)w; w += align_up(sizeof(WorkItem) * (size_t)nitems, 64);

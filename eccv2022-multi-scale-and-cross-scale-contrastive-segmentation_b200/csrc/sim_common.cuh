@@ -27,6 +27,7 @@ struct BwdPass {
   const float* row_cs; const float* row_cpn; const float* row_neg;   // row-side coefficients or null
   const float* col_cs; const float* col_cpn; const float* col_neg;   // col-side coefficients or null
   int n_rows, n_cols;
+  int rb_lo, rb_hi;       // row tiles (128 rows) this rank handles
   int self_mask;
   int row_set, col_set;
   float scale_log2;      // log2(e)/tau
@@ -42,6 +43,9 @@ static inline int build_passes(const mscs_sim_job* job, BwdPass* out) {
     p.row_cs = m.coef_s; p.row_cpn = m.coef_pn; p.row_neg = m.neg_sum;
     p.n_rows = m.N1; p.n_cols = m.N2; p.self_mask = m.self_mask; p.row_set = m.a_set; p.col_set = m.k_set;
     p.scale_log2 = kLog2e / m.temperature; p.out_scale = m.weight / m.temperature;
+    { const bool all = m.row_begin == 0 && m.row_end == 0;      // 0,0 = every row; begin == end = none
+      p.rb_lo = (all ? 0 : m.row_begin) / 128; p.rb_hi = ((all ? m.N1 : m.row_end) + 127) / 128;
+      if (!all && m.row_end == m.row_begin) p.rb_hi = p.rb_lo; }
     if (m.self_mask) { p.col_cs = m.coef_s; p.col_cpn = m.coef_pn; p.col_neg = m.neg_sum; }
     out[np++] = p;
     if (!m.self_mask && m.need_dk) {
@@ -50,6 +54,9 @@ static inline int build_passes(const mscs_sim_job* job, BwdPass* out) {
       q.col_cs = m.coef_s; q.col_cpn = m.coef_pn; q.col_neg = m.neg_sum;
       q.n_rows = m.N2; q.n_cols = m.N1; q.self_mask = 0; q.row_set = m.k_set; q.col_set = m.a_set;
       q.scale_log2 = p.scale_log2; q.out_scale = p.out_scale;
+      { const bool all = m.krow_begin == 0 && m.krow_end == 0;
+        q.rb_lo = (all ? 0 : m.krow_begin) / 128; q.rb_hi = ((all ? m.N2 : m.krow_end) + 127) / 128;
+        if (!all && m.krow_end == m.krow_begin) q.rb_hi = q.rb_lo; }
       out[np++] = q;
     }
   }
@@ -70,6 +77,12 @@ static inline int validate_job(const mscs_sim_job* job) {
     MSCS_CHECK_ARG(m.N1 >= 1 && m.N2 >= 1, "term %d: empty", t);
     MSCS_CHECK_ARG(m.temperature > 0.f, "term %d: temperature must be positive", t);
     MSCS_CHECK_ARG(!m.self_mask || (m.a_bf16 == m.k_bf16 && m.N1 == m.N2), "term %d: self term needs a == k", t);
+    MSCS_CHECK_ARG(m.row_begin >= 0 && m.row_begin <= m.row_end && m.row_end <= m.N1 &&
+                   (m.row_begin % 128 == 0 || m.row_begin == m.N1) && (m.row_end % 128 == 0 || m.row_end == m.N1),
+                   "term %d: bad anchor row range [%d,%d)", t, m.row_begin, m.row_end);
+    MSCS_CHECK_ARG(m.krow_begin >= 0 && m.krow_begin <= m.krow_end && m.krow_end <= m.N2 &&
+                   (m.krow_begin % 128 == 0 || m.krow_begin == m.N2) && (m.krow_end % 128 == 0 || m.krow_end == m.N2),
+                   "term %d: bad key row range [%d,%d)", t, m.krow_begin, m.krow_end);
     MSCS_CHECK_ARG(m.a_set >= 0 && m.a_set < MSCS_MAX_SCALES && m.k_set >= 0 && m.k_set < MSCS_MAX_SCALES,
                    "term %d: bad set index", t);
   }

@@ -283,13 +283,14 @@ __global__ void __launch_bounds__(1024) k_build_work(const __grid_constant__ Bui
       int ti = 0;
       for (int q = 1; q < a.num_terms; ++q) if (i >= a.t[q].item_base) ti = q;
       const BuildTerm& t = a.t[ti];
-      const int rb = i - t.item_base;
+      const int rb = t.blk_lo + i - t.item_base;
       int ct0 = 0, ct1 = (t.N2 + kTileN - 1) / kTileN;
       if (a.mode == 1) {
         const int r0 = rb * a.rows_per_item, r1 = min(t.N1, r0 + a.rows_per_item) - 1;
         const int p0 = t.k_seg[t.a_cls[r0]], p1 = t.k_seg[t.a_cls[r1] + 1];
         if (p1 > p0) { ct0 = p0 / kTileN; ct1 = (p1 + kTileN - 1) / kTileN; } else { ct0 = ct1 = 0; }
       }
+      ct0 = max(ct0, t.ct_lo); ct1 = max(ct0, min(ct1, t.ct_hi));      // pooled mode: this rank's streamed tiles
       a.items[i] = WorkItem{ti, rb, ct0, ct1};
       len = ct1 - ct0;
     }
@@ -381,7 +382,7 @@ extern "C" size_t mscs_sim_workspace_bytes(const mscs_sim_job* job) {
   return 2 * 4096 + ranges + items * (sizeof(WorkItem) + sizeof(int)) + 16 * 64;
 }
 
-extern "C" int mscs_sim_forward(const mscs_sim_job* job, void* stream_) {
+extern "C" int mscs_sim_forward_sweeps(const mscs_sim_job* job, void* stream_) {
   int rc = validate_job(job);
   if (rc) return rc;
   MSCS_CHECK_ARG(job->work, "work buffer is null");
@@ -413,7 +414,9 @@ extern "C" int mscs_sim_forward(const mscs_sim_job* job, void* stream_) {
     args.t[t] = FwdTerm{m.a_cls, m.k_seg, rr, gr, m.neg_sum, m.pos_sum, m.s_sum, m.N1, m.N2, m.self_mask, am, km,
                         kLog2e / m.temperature};
     // blocks are on the KEY side (256 keys), the streamed 128-row tiles on the ANCHOR side
-    b.t[t] = BuildTerm{m.k_cls, m.a_seg, m.N2, m.N1, nitems};
+    const bool all_rows = m.row_begin == 0 && m.row_end == 0;     // 0,0 = every row; begin == end = none
+    const int r_lo = all_rows ? 0 : m.row_begin, r_hi = all_rows ? m.N1 : m.row_end;
+    b.t[t] = BuildTerm{m.k_cls, m.a_seg, m.N2, m.N1, nitems, 0, r_lo / 128, r_hi > r_lo ? ceil_div(r_hi, 128) : r_lo / 128};
     nitems += ceil_div(m.N2, kFwdKeys);
   }
   k_row_ranges<<<dim3(ceil_div(maxN1 + 127, 256), job->num_terms), 256, 0, st>>>(ra);
@@ -434,7 +437,20 @@ extern "C" int mscs_sim_forward(const mscs_sim_job* job, void* stream_) {
     }
     if (rc) return rc;
   }
-  return launch_finalize(job, st);
+  return 0;
+}
+
+extern "C" int mscs_sim_finalize(const mscs_sim_job* job, void* stream_) {
+  int rc = validate_job(job);
+  if (rc) return rc;
+  MSCS_CHECK_ARG(job->work, "work buffer is null");
+  return launch_finalize(job, (cudaStream_t)stream_);
+}
+
+extern "C" int mscs_sim_forward(const mscs_sim_job* job, void* stream_) {
+  int rc = mscs_sim_forward_sweeps(job, stream_);
+  if (rc) return rc;
+  return launch_finalize(job, (cudaStream_t)stream_);
 }
 
 // debug: read and reset the barrier wait profile of this translation unit (ns and count per tag % 32)

@@ -45,7 +45,7 @@ struct Walker {
 };
 
 // work-table builder (sim_fwd.cu): one item per (owner, row block)
-struct BuildTerm { const int* a_cls; const int* k_seg; int N1, N2, item_base; };
+struct BuildTerm { const int* a_cls; const int* k_seg; int N1, N2, item_base, blk_lo, ct_lo, ct_hi; };
 struct BuildArgs { BuildTerm t[MSCS_MAX_PASSES]; int num_terms, nitems, rows_per_item, mode; WorkItem* items; int* prefix; };
 int launch_build_work(const BuildArgs& b, cudaStream_t st);
 int trap_buffer_device_ptr(unsigned long long** out);

@@ -81,10 +81,16 @@ class DenseContrastiveLossV2(nn.Module):
 
 
 class DenseContrastiveLossV2_ms(nn.Module):
-    """Multi-scale + cross-scale loss.  ``forward(label, features: list)`` (_ms.py:44)."""
+    """Multi-scale + cross-scale loss.  ``forward(label, features: list)`` (_ms.py:44).
 
-    def __init__(self, config):
+    ``comm`` (not a reference argument) switches on the POOLED cross-batch mode: the loss is then the
+    reference loss of the concatenated batch of all ranks (one process per GPU, each passing its local
+    images); anchor rows are sharded over the ranks, the normalised key set is exchanged over NCCL.
+    Pass ``mscs_b200.TorchDistComm(process_group)``; every rank's CPU generator must be in the same state."""
+
+    def __init__(self, config, comm=None):
         super().__init__()
+        self.comm = comm
         self.experiment = config["experiment"]
         self.dataset = config["dataset"]
         self.num_all_classes, self.num_real_classes, self.ignore_class = class_facts(self.dataset, self.experiment)
@@ -109,10 +115,10 @@ class DenseContrastiveLossV2_ms(nn.Module):
             raise IndexError("list index out of range")     # features[s] in the reference (_ms.py:53)
         if self.cross_scale_contrast:
             assert len(feats) > 1                            # _ms.py:63
-        holder = {}
+        holder = {"comm": self.comm}
         total, terms = MsCsContrastiveFn.apply(label, self._spec, False, holder, *feats)
         state = holder["state"]
-        self.last_samples = holder["samples"]
+        self.last_samples, self.last_state = holder["samples"], state
         self.ms_losses = [terms[s] for s in range(state.num_ms)]
         self.cs_losses = [terms[i] for i in state.cs_logged]
         if any(s.log_flag for s in holder["samples"]):

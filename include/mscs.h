@@ -58,6 +58,10 @@ typedef struct {
   int32_t min_views;             /* min_views_per_class (V2.py:21)                         */
   int32_t max_views;             /* max_views_per_class (V2.py:27); 1 = no cap (V2.py:65)  */
   int32_t max_total;             /* max_features_total (V2.py:28)                          */
+  /* pooled cross-batch mode (one process per GPU, each with n local images): total number of
+   * images over all ranks and the global index of this rank's first image.  0/0 = single process. */
+  int32_t n_global;
+  int32_t image_base;
 } mscs_sample_cfg;
 
 /* per-scale result header, written by the plan kernel, fetched by mscs_plan_fetch */
@@ -82,6 +86,14 @@ size_t mscs_sample_max_draws(const mscs_sample_cfg* cfg);
  * mscs_scale_plan records. */
 int mscs_sample_plan(const mscs_sample_cfg* cfg, const int64_t* labels, void* workspace,
                      mscs_scale_plan* plan_dev, void* stream);
+/* The two halves of mscs_sample_plan, for the pooled mode: (1) local down-sampling + histograms;
+ * the per-(image,class) counts of scale s sit at byte offset mscs_sample_counts_offset(cfg, s) of the
+ * workspace as int32 [n][A], to be all-gathered by the caller; (2) the plan from the all-gathered
+ * counts int32 [n_global][A] per scale (NULL = use the local counts, single process). */
+size_t mscs_sample_counts_offset(const mscs_sample_cfg* cfg, int scale);
+int mscs_sample_hist(const mscs_sample_cfg* cfg, const int64_t* labels, void* workspace, void* stream);
+int mscs_sample_plan_from_counts(const mscs_sample_cfg* cfg, const int32_t* const* counts_global, void* workspace,
+                                 mscs_scale_plan* plan_dev, void* stream);
 /* D2H of the plan records + stream synchronise (the one host sync of the forward pass;
  * the reference has ~1000). */
 int mscs_plan_fetch(const mscs_scale_plan* plan_dev, mscs_scale_plan* plan_host, int num_scales,
@@ -137,6 +149,10 @@ typedef struct {
   float temperature;
   float weight;           /* weights[s] / w_high_low / w_high_mid  (_ms.py:54,72,79)     */
   int32_t a_set, k_set;   /* which anchor set (scale) rows/cols belong to: grads accumulate per set */
+  /* pooled mode: the anchor rows [row_begin, row_end) this rank computes statistics and gradients for,
+   * and the key rows [krow_begin, krow_end) whose key-side gradient it computes (cross-scale terms).
+   * Multiples of 128 (the ends may equal N1 / N2).  0,0 = all rows. */
+  int32_t row_begin, row_end, krow_begin, krow_end;
   /* per-anchor statistics, N1 floats each, zero-initialised by the caller */
   float* neg_sum;   /* sum_k neg exp(l_ik)                          (V2.py:183-184) */
   float* pos_sum;   /* sum_j pos [l_ij - log(e^l_ij + neg_i)]       (V2.py:186-187) */
@@ -158,6 +174,10 @@ typedef struct {
 size_t mscs_sim_workspace_bytes(const mscs_sim_job* job);
 /* forward: negative sweep, positive sweep, finalise (loss + backward coefficients) */
 int mscs_sim_forward(const mscs_sim_job* job, void* stream);
+/* the same in two halves for the pooled mode: the sweeps over this rank's anchor rows, then (after the
+ * caller has all-reduced the row statistics) the finalisation over all rows */
+int mscs_sim_forward_sweeps(const mscs_sim_job* job, void* stream);
+int mscs_sim_finalize(const mscs_sim_job* job, void* stream);
 /* backward: dF[set] (N_set, C) fp32 += d total_loss / d unit rows * (*grad_out), for every
  * set; the caller zero-initialises dF.  grad_out is a device scalar (upstream gradient). */
 int mscs_sim_backward(const mscs_sim_job* job, const float* grad_out, float* const* dF_sets,

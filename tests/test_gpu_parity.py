@@ -327,3 +327,77 @@ def test_properties_full_size(dev):
         loss2 = mod(labels.to(dev), [f.detach() * 4.0 for f in fg])
     assert all(torch.equal(a, s.pix) for a, s in zip(pix0, mod.last_samples))
     assert abs(float(loss2) - float(loss)) < 1e-5 * abs(float(loss))
+
+
+# ---- pooled cross-batch mode: `world` ranks emulated on one GPU (ThreadComm) ------------------
+def _pooled_emulated(cfg, labels, feats, world, seed, dev):
+    import threading
+    import mscs_b200
+    from mscs_b200 import _ops
+    n = labels.shape[0]
+    nl = n // world
+    shared = _ops.ThreadComm._Shared(world)
+    results, errors = [None] * world, []
+
+    def worker(r):
+        try:
+            torch.cuda.set_device(dev)
+            mod = mscs_b200.DenseContrastiveLossV2_ms(dict(cfg), comm=_ops.ThreadComm(shared, r))
+            lab = labels[r * nl:(r + 1) * nl].to(dev)
+            fts = [f[r * nl:(r + 1) * nl].to(dev).requires_grad_(True) for f in feats]
+            loss = mod(lab, fts)
+            grads = _ops.run_backward(mod.last_state, torch.ones((), device=dev), [True] * len(fts),
+                                      [tuple(f.shape) for f in fts], [f.dtype for f in fts])
+            torch.cuda.synchronize()
+            results[r] = (float(loss.detach()), [g.cpu() for g in grads],
+                          [float(x) for x in mod.ms_losses] + [float(x) for x in mod.cs_losses])
+        except Exception as e:      # noqa: BLE001
+            errors.append(e)
+            shared.barrier.abort()
+
+    torch.manual_seed(seed)
+    threads = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return results
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_pooled_mode_matches_single_process(world, dev):
+    """The pooled loss over `world` ranks (rows sharded, keys exchanged) equals the single-process loss
+    of the concatenated batch: same sampled pixels, same loss, same gradient for every rank's images."""
+    import mscs_b200
+    from mscs_b200 import synth
+    cfg = dict(dataset="CITYSCAPES", experiment=1, temperature=0.1, scales=3, weights=[1.0, 0.7, 0.4],
+               cross_scale_contrast=True, w_high_low=0.5, w_high_mid=0.25, min_views_per_class=5,
+               max_views_per_class=50, max_features_total=1500)
+    n = 4
+    labels = synth.synth_labels(n, 128, 256, 19, 7, 16, 0.05, 21)
+    feats = synth.synth_features(n, 64, 128, 256, [4, 8, 16], 22)
+    # single process, whole batch
+    full = mscs_b200.DenseContrastiveLossV2_ms(dict(cfg))
+    fg = [f.to(dev).requires_grad_(True) for f in feats]
+    torch.manual_seed(5)
+    loss = full(labels.to(dev), fg)
+    loss.backward()
+    state_after = torch.get_rng_state()
+    want_terms = [float(x) for x in full.ms_losses] + [float(x) for x in full.cs_losses]
+    assert full.last_samples[0].N > 256          # several row tiles, so the row ranges matter
+    res = _pooled_emulated(cfg, labels, feats, world, 5, dev)
+    assert torch.equal(torch.get_rng_state(), state_after)
+    nl = n // world
+    for r, (l, grads, terms) in enumerate(res):
+        assert abs(l - float(loss)) < 2e-5 * abs(float(loss)), (r, l, float(loss))
+        for a, b in zip(terms, want_terms):
+            assert abs(a - b) < 2e-5 * abs(b)
+        for s, g in enumerate(grads):
+            want = fg[s].grad[r * nl:(r + 1) * nl].cpu()
+            assert torch.equal(g != 0, want != 0), f"rank {r} scale {s}: sampled pixels differ"
+            cs = cosine(g.numpy(), want.numpy())
+            err = float((g - want).abs().max())
+            print(f"world {world} rank {r} scale {s}: grad cosine {cs:.8f} max-abs {err:.3e}")
+            assert cs > 0.99999
