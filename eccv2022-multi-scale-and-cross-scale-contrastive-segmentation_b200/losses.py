@@ -67,7 +67,7 @@ class DenseContrastiveLossV2(nn.Module):
         self._spec.num_classes = self.num_all_classes          # the reference lets callers override it (V2.py:238)
         total, _terms = MsCsContrastiveFn.apply(label, self._spec, True, holder, features)
         smp = holder["samples"][0]
-        self.last_samples = holder["samples"]
+        self.last_samples, self.last_state = holder["samples"], holder["state"]
         self._scale = int(label.shape[-1] // features.shape[-1])                         # V2.py:46,203
         if smp.log_flag:
             self.log_this_step = True                                                    # V2.py:75,83

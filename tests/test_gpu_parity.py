@@ -401,3 +401,70 @@ def test_pooled_mode_matches_single_process(world, dev):
             err = float((g - want).abs().max())
             print(f"world {world} rank {r} scale {s}: grad cosine {cs:.8f} max-abs {err:.3e}")
             assert cs > 0.99999
+
+
+# ---- API behaviours of the reference classes ----------------------------------------------------
+def test_validation_shape_forward_only(dev):
+    """validate() calls the loss under no_grad with n = 1 and full frames."""
+    import mscs_b200
+    from mscs_b200 import synth
+    from oracle import loss_fp64
+    from oracle.config import oracle_cfg
+    from oracle.mt19937 import MT19937
+    cfg = dict(dataset="CITYSCAPES", experiment=1, temperature=0.1, scales=2, weights=[1.0, 0.5],
+               cross_scale_contrast=True, min_views_per_class=5, max_views_per_class=300, max_features_total=2000)
+    labels = synth.synth_labels(1, 128, 256, 19, 6, 16, 0.05, 31)
+    feats = synth.synth_features(1, 96, 128, 256, [4, 8], 32)
+    mod = mscs_b200.DenseContrastiveLossV2_ms(cfg)
+    torch.manual_seed(9)
+    gen = MT19937.from_torch_state(torch.get_rng_state().numpy().tobytes())
+    with torch.no_grad():
+        loss = mod(labels.to(dev), [f.to(dev) for f in feats])
+    assert not loss.requires_grad
+    want = loss_fp64.ms_cs_loss(labels.numpy(), [f.numpy() for f in feats], oracle_cfg(cfg, 20), gen, need_grad=False)
+    assert abs(float(loss) - want["total"]) < 1e-3 * abs(want["total"])
+    for s, smp in enumerate(mod.last_samples):
+        assert np.array_equal(smp.idx_ref.cpu().numpy(), want["samples"][s]["idx"])
+
+
+def test_single_scale_class_cross_scale_tuple(dev):
+    """DenseContrastiveLossV2 with cross_scale_contrast=True returns the reference 4-tuple (V2.py:60-61)."""
+    import mscs_b200
+    from mscs_b200 import synth
+    cfg = dict(dataset="CITYSCAPES", experiment=1, temperature=0.1, cross_scale_contrast=True,
+               min_views_per_class=5, max_views_per_class=30)
+    labels = synth.synth_labels(2, 64, 128, 19, 5, 8, 0.05, 41)
+    feat = synth.synth_features(2, 32, 64, 128, [4], 42)[0].to(dev).requires_grad_(True)
+    mod = mscs_b200.DenseContrastiveLossV2(cfg)
+    torch.manual_seed(3)
+    loss, sampled, slabels, flag = mod(label=labels.to(dev), features=feat)
+    smp = mod.last_samples[0]
+    assert flag is False and sampled.shape == (smp.T, 32, smp.V) and slabels.shape == (smp.T,)
+    idx, pairs = smp.idx_ref.cpu().long(), smp.pair_ref.cpu().long()
+    want = feat.detach().cpu().reshape(2, 32, -1)[pairs[:, 0][:, None], :, idx].permute(0, 2, 1)
+    assert torch.equal(sampled.detach().cpu(), want)
+    assert torch.equal(slabels.cpu(), pairs[:, 1].float())
+    loss.backward()
+    assert feat.grad is not None and int((feat.grad != 0).any(dim=1).sum()) == smp.N
+
+
+def test_second_backward_and_half_inputs(dev):
+    """retain_graph: the second backward must not reuse the consumed pre-zeroed buffers; fp16 inputs
+    (autocast-style) are accepted and the gradient comes back in the input dtype."""
+    import mscs_b200
+    from mscs_b200 import synth
+    cfg = dict(dataset="CITYSCAPES", experiment=1, temperature=0.1, max_views_per_class=20)
+    labels = synth.synth_labels(2, 64, 128, 19, 5, 8, 0.05, 51).to(dev)
+    feat = synth.synth_features(2, 32, 64, 128, [4], 52)[0].to(dev).requires_grad_(True)
+    mod = mscs_b200.DenseContrastiveLossV2(cfg)
+    torch.manual_seed(1)
+    loss = mod(labels, feat)
+    loss.backward(retain_graph=True)
+    g1 = feat.grad.clone()
+    feat.grad = None
+    loss.backward()
+    assert torch.allclose(feat.grad, g1, rtol=1e-4, atol=1e-9)
+    fh = feat.detach().half().requires_grad_(True)
+    torch.manual_seed(1)
+    mod(labels, fh).backward()
+    assert fh.grad.dtype == torch.float16 and torch.isfinite(fh.grad).all()
