@@ -190,7 +190,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
               const int c0 = cb + c4 * 32;
               // 32-column chunk without positives of any row of this warp and inside the key set: no masks
               const bool fast = (c0 + 32 <= wmin || c0 >= wmax) && (c0 + 32 <= t.N2);
-              if (fast) {
+              if (fast && (args.debug_flags & 4)) {      // experiment: no MUFU (wrong results)
+#pragma unroll
+                for (int c = 0; c < 32; c += 4) {
+                  acc0 += __uint_as_float(cur[c]) * scale;
+                  acc1 += __uint_as_float(cur[c + 1]) * scale;
+                  acc2 += __uint_as_float(cur[c + 2]) * scale;
+                  acc3 += __uint_as_float(cur[c + 3]) * scale;
+                }
+              } else if (fast) {
 #pragma unroll
                 for (int c = 0; c < 32; c += 4) {
                   acc0 += ptx::ex2(__uint_as_float(cur[c]) * scale);
