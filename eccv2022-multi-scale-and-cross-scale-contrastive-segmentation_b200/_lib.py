@@ -55,7 +55,9 @@ _SIGNATURES = {
     "mscs_plan_fetch": (C.c_int, [C.c_void_p, C.POINTER(ScalePlan), C.c_int, C.c_void_p]),
     "mscs_mt19937_stream": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]),
     "mscs_sample_select": (C.c_int, [C.POINTER(SampleCfg), C.POINTER(ScalePlan), C.c_void_p, C.c_void_p,
-                                     _PTRS, _PTRS, _PTRS, _PTRS, _PTRS, C.c_void_p]),
+                                     _PTRS, _PTRS, _PTRS, _PTRS, _PTRS, _PTRS, C.c_void_p]),
+    "mscs_gather_normalize_sectors": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mscs_mt19937_advance_host": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_uint64]),
     "mscs_gather_normalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -266,7 +266,7 @@ def sample_anchors(labels, feat_hw, spec, mt_state=None, defer_rng=False):
                        slab, offs[s], A) for s in range(S)]
     arrs = [[out[s].ptr(k) for s in range(S)] for k in range(5)]
     _lib.check(lib.mscs_sample_select(C.byref(cfg), plan, ws.data_ptr(), draws.data_ptr(),
-                                      *[_lib.ptr_array(a) for a in arrs], st), "mscs_sample_select")
+                                      *[_lib.ptr_array(a) for a in arrs], None, st), "mscs_sample_select")
 
     def finish_rng():
         """Publish the generator state the reference would leave behind and start producing the
@@ -412,14 +412,12 @@ class _GradBuffers:
         if side is None:
             side = self._side[dev] = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream()
-        self.bufs, self.slots = [], []
+        self.bufs = []
         for f, need in zip(feats, needs):
             n, Cc, h, w = f.shape
             if not need or (h * w) % 8 != 0:
                 self.bufs.append(None)
-                self.slots.append(None)
                 continue
-            self.slots.append(torch.empty(n * h * w, dtype=torch.int32, device=dev))   # filled by mscs_slot_map
             self.bufs.append(torch.empty(f.shape, dtype=torch.float32, device=dev))
         side.wait_stream(main)
         with torch.cuda.stream(side):
@@ -433,7 +431,7 @@ class _GradBuffers:
     def take(self, s):
         """The pre-zeroed buffer of scale s (once: a second backward falls back to zero-fill)."""
         b, self.bufs[s] = self.bufs[s], None
-        return b, self.slots[s]
+        return b
 
 
 
@@ -641,11 +639,20 @@ def run_forward(sp, labels, feats32, needs, comm=None):
         islab = torch.empty(sp.islab_n, dtype=i32, device=dev) if not pooled else \
             torch.zeros(sp.islab_n, dtype=i32, device=dev)
         fslab = torch.empty(sp.fslab_n, dtype=f32, device=dev)
-        bslab = torch.empty(sp.bslab_n, dtype=torch.bfloat16, device=dev)
+        bslab = (torch.zeros if pooled else torch.empty)(sp.bslab_n, dtype=torch.bfloat16, device=dev)   # pooled: rows of
+        # other ranks must be zero for the all-reduce
         stats = torch.zeros(sp.stats_n, dtype=f32, device=dev)
         misc = torch.empty(sp.misc_n, dtype=f32, device=dev)
         work = torch.empty(sp.work_bytes, dtype=u8, device=dev)
         gradbufs = _GradBuffers(feats32, needs) if any(needs) else None
+        # pixel -> row maps (filled by the selection kernel): drive the address-ordered gather and the
+        # sector scatter of the backward
+        sizes = [shp[0] * shp[2] * shp[3] if (shp[2] * shp[3]) % 8 == 0 else 0 for shp in sp.feat_shapes]
+        slot_slab = torch.full((sum(sizes),), -1, dtype=i32, device=dev) if sum(sizes) else None     # one fill
+        slots, off = [], 0
+        for x in sizes:
+            slots.append(slot_slab[off:off + x] if x else None)
+            off += x
         mt, pos = torch_mt_state()
         draws = _stream_cache(dev).acquire(mt, pos, sp.max_draws)
         plan = (_lib.ScalePlan * S)()
@@ -663,7 +670,8 @@ def run_forward(sp, labels, feats32, needs, comm=None):
             for s in range(S):
                 islab[sp.ioff[s][2]:sp.ioff[s][2] + sp.Ncap[s]].fill_(-1)
         arrs = [_lib.ptr_array([ibase + 4 * sp.ioff[s][k] for s in range(S)]) for k in range(5)]
-        _lib.check(lib.mscs_sample_select(C.byref(sp.cfg), plan, ws.data_ptr(), draws.data_ptr(), *arrs, st),
+        sarr = _lib.ptr_array([x.data_ptr() if x is not None else 0 for x in slots])
+        _lib.check(lib.mscs_sample_select(C.byref(sp.cfg), plan, ws.data_ptr(), draws.data_ptr(), *arrs, sarr, st),
                    "mscs_sample_select")
     samples = [ScaleSample(plan[s].T, plan[s].V, plan[s].N, bool(plan[s].log_flag), plan[s].dl_h, plan[s].dl_w,
                            islab, sp.ioff[s], A) for s in range(S)]
@@ -673,12 +681,15 @@ def run_forward(sp, labels, feats32, needs, comm=None):
     with _timed("gather"):
         for s in range(S):
             n, Cc, h, w = sp.feat_shapes[s]
-            if gradbufs is not None and gradbufs.slots[s] is not None:
-                _lib.check(lib.mscs_slot_map(samples[s].ptr(2), samples[s].N, n * h * w,
-                                             gradbufs.slots[s].data_ptr(), st), "mscs_slot_map")
-            _lib.check(lib.mscs_gather_normalize(feats32[s].data_ptr(), n, Cc, h * w, samples[s].ptr(2), samples[s].N,
-                                                 bbase + 2 * sp.boff[s], fbase + 4 * sp.foff[s][0],
-                                                 fbase + 4 * sp.foff[s][1], st), "mscs_gather_normalize")
+            if slots[s] is not None:
+                _lib.check(lib.mscs_gather_normalize_sectors(feats32[s].data_ptr(), n, Cc, h * w, slots[s].data_ptr(),
+                                                             samples[s].N, bbase + 2 * sp.boff[s],
+                                                             fbase + 4 * sp.foff[s][0], fbase + 4 * sp.foff[s][1], st),
+                           "mscs_gather_normalize_sectors")
+            else:
+                _lib.check(lib.mscs_gather_normalize(feats32[s].data_ptr(), n, Cc, h * w, samples[s].ptr(2),
+                                                     samples[s].N, bbase + 2 * sp.boff[s], fbase + 4 * sp.foff[s][0],
+                                                     fbase + 4 * sp.foff[s][1], st), "mscs_gather_normalize")
     if pooled:           # normalised rows of all ranks: all-gather expressed as a sum of disjoint supports
         comm.all_reduce(bslab)
     job = _lib.SimJob()
@@ -715,7 +726,7 @@ def run_forward(sp, labels, feats32, needs, comm=None):
         mt2, pos2 = torch_mt_advance(mt, pos, total)
         _stream_cache(dev).release_and_prefetch(mt2, pos2, sp.max_draws)
     state = _StepState()
-    state.sp, state.job, state.samples, state.gradbufs = sp, job, samples, gradbufs
+    state.sp, state.job, state.samples, state.gradbufs, state.slots = sp, job, samples, gradbufs, slots
     state.keep = (ws, islab, fslab, bslab, stats, misc, work)
     state.fslab, state.term_loss = fslab, misc[sp.out_off:sp.out_off + nt]
     state.total = misc[sp.out_off + nt]
@@ -752,8 +763,8 @@ def run_backward(state, grad_out, needs, shapes, dtypes):
                 continue
             n, Cc, h, w = shapes[s]
             smp = state.samples[s]
-            pre, slot = gb.take(s) if gb is not None else (None, None)
-            if pre is not None:
+            pre, slot = (gb.take(s) if gb is not None else None), state.slots[s]
+            if pre is not None and slot is not None:
                 out = pre
                 _lib.check(lib.mscs_scatter_sectors(ptrs[s], sp.C_pad, fbase + 4 * sp.foff[s][0],
                                                     fbase + 4 * sp.foff[s][1], slot.data_ptr(), n, Cc, h * w,

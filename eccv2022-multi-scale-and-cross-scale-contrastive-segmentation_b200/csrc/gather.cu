@@ -83,6 +83,50 @@ k_scatter_grad(const float* __restrict__ dF, int ldF, const float* __restrict__ 
   }
 }
 
+// Gather in ADDRESS order: one warp per 8-pixel octet of the slot map (18% of them hold a sampled
+// pixel at cfg-2).  Neighbouring warps then touch neighbouring 32-byte sectors of the same channel
+// planes, so the 256 strided sector reads of an anchor hit open DRAM pages instead of random ones.
+__global__ void __launch_bounds__(256)
+k_gather_sectors(const float* __restrict__ feat, int C, int C_pad, int plane, const int* __restrict__ slot,
+                 int n_octets, __nv_bfloat16* __restrict__ anc_bf16, float* __restrict__ anc_f32,
+                 float* __restrict__ inv_norm) {
+  const int lane = threadIdx.x & 31;
+  const int oct = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (oct >= n_octets) return;
+  const int gp = oct * 8;
+  const int s_mine = (lane < 8) ? slot[gp + lane] : -1;
+  unsigned act = __ballot_sync(0xffffffffu, s_mine >= 0);
+  if (act == 0) return;
+  const int b = gp / plane, p = gp - b * plane;
+  const float* src0 = feat + ((size_t)b * C) * plane + p;
+  while (act) {
+    const int j = __ffs(act) - 1;
+    act &= act - 1;
+    const int row = __shfl_sync(0xffffffffu, s_mine, j);
+    const float* src = src0 + j;
+    float v[kMaxC / 32];
+    float ss = 0.f;
+#pragma unroll
+    for (int q = 0; q < kMaxC / 32; ++q) {
+      const int c = lane + 32 * q;
+      v[q] = (c < C) ? __ldg(src + (size_t)c * plane) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < kMaxC / 32; ++q) ss = fmaf(v[q], v[q], ss);
+    ss = warp_sum(ss);
+    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    if (lane == 0) inv_norm[row] = inv;
+    __nv_bfloat16* orow = anc_bf16 + (size_t)row * C_pad;
+#pragma unroll
+    for (int q = 0; q < kMaxC / 32; ++q) {
+      const int c = lane + 32 * q;
+      const float f = v[q] * inv;
+      if (c < C) anc_f32[(size_t)row * C + c] = f;
+      if (c < C_pad) orow[c] = __float2bfloat16(c < C ? f : 0.f);
+    }
+  }
+}
+
 // slot map: slot[image*plane + pixel] = sorted anchor row sampled there, or -1
 __global__ void k_slot_map(const int* __restrict__ pix, int N, int* __restrict__ slot) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -142,6 +186,23 @@ k_scatter_sectors(const float* __restrict__ dF, int ldF, const float* __restrict
 }  // namespace mscs
 
 using namespace mscs;
+
+extern "C" int mscs_gather_normalize_sectors(const float* feat, int n, int C, int plane, const int32_t* slot, int N,
+                                             void* anc_bf16, float* anc_f32, float* inv_norm, void* stream_) {
+  MSCS_CHECK_ARG(feat && slot && anc_bf16 && anc_f32 && inv_norm, "null pointer argument");
+  MSCS_CHECK_ARG(C >= 1 && C <= kMaxC, "C=%d unsupported (1..%d)", C, kMaxC);
+  MSCS_CHECK_ARG(n >= 1 && plane >= 8 && plane % 8 == 0 && N >= 1, "bad sizes (plane must be a multiple of 8)");
+  cudaStream_t st = (cudaStream_t)stream_;
+  const int C_pad = (C + 63) / 64 * 64, N_pad = (N + 255) / 256 * 256;
+  if (N_pad > N)      // zero padding rows of the operand matrix (TMA tiles read them)
+    MSCS_CUDA(cudaMemsetAsync((__nv_bfloat16*)anc_bf16 + (size_t)N * C_pad, 0,
+                              sizeof(__nv_bfloat16) * (size_t)(N_pad - N) * C_pad, st));
+  const int n_oct = n * (plane / 8);
+  k_gather_sectors<<<ceil_div(n_oct, 8), 256, 0, st>>>(feat, C, C_pad, plane, slot, n_oct, (__nv_bfloat16*)anc_bf16,
+                                                       anc_f32, inv_norm);
+  MSCS_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int mscs_slot_map(const int32_t* pix, int N, int n_pixels, int32_t* slot, void* stream_) {
   MSCS_CHECK_ARG(pix && slot && N >= 1 && n_pixels >= 1, "bad arguments");

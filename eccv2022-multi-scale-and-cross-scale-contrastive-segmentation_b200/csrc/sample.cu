@@ -344,6 +344,7 @@ struct SelectArgs {
   int* pix[MSCS_MAX_SCALES];
   int* cls[MSCS_MAX_SCALES];
   int* seg[MSCS_MAX_SCALES];
+  int* slot[MSCS_MAX_SCALES];     // optional pixel -> sorted row map (pre-filled with -1 by the caller)
 };
 
 __global__ void __launch_bounds__(256)
@@ -418,6 +419,7 @@ k_fy_select(const __grid_constant__ SampleLayout L, const __grid_constant__ Sele
       a.idx_ref[s][(size_t)k * V + i] = p;
       a.pix[s][dst + i] = b * g.hw + p;
       a.cls[s][dst + i] = c;
+      if (a.slot[s]) a.slot[s][b * g.hw + p] = dst + i;
     }
   }
 }
@@ -512,7 +514,7 @@ extern "C" int mscs_mt19937_stream(const uint32_t* mt_state_host, int mt_pos, ui
 extern "C" int mscs_sample_select(const mscs_sample_cfg* cfg, const mscs_scale_plan* plan_host, void* workspace,
                                   const uint32_t* draws_dev, int32_t* const* idx_ref, int32_t* const* pair_ref,
                                   int32_t* const* pix, int32_t* const* cls, int32_t* const* seg,
-                                  void* stream_) {
+                                  int32_t* const* slot, void* stream_) {
   SampleLayout L;
   int rc = make_layout(cfg, &L);
   if (rc) return rc;
@@ -526,6 +528,7 @@ extern "C" int mscs_sample_select(const mscs_sample_cfg* cfg, const mscs_scale_p
                    plan_host[s].V, kMaxV);
     a.draw_base[s] = plan_host[s].draw_base; a.T[s] = plan_host[s].T; a.V[s] = plan_host[s].V;
     a.idx_ref[s] = idx_ref[s]; a.pair_ref[s] = pair_ref[s]; a.pix[s] = pix[s]; a.cls[s] = cls[s]; a.seg[s] = seg[s];
+    a.slot[s] = slot ? slot[s] : nullptr;
     if (plan_host[s].T > maxT) maxT = plan_host[s].T;
     if (plan_host[s].V > maxV) maxV = plan_host[s].V;
   }

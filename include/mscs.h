@@ -113,10 +113,13 @@ int mscs_mt19937_stream(const uint32_t* mt_state_host, int mt_pos, uint64_t n_wo
  *   pix[s]      : image*dl_h*dl_w + y*w+x, rows sorted by class (kernel order)
  *   cls[s]      : class id of each sorted row
  *   seg[s]      : A+1 int32, seg[c] = first sorted row of class c, seg[A] = N
+ *   slot[s]     : optional (array or entries may be NULL): int32 n*dl_h*dl_w pixel -> sorted row map,
+ *                 PRE-FILLED with -1 by the caller; the sampled pixels receive their row
  */
 int mscs_sample_select(const mscs_sample_cfg* cfg, const mscs_scale_plan* plan_host, void* workspace,
                        const uint32_t* draws_dev, int32_t* const* idx_ref, int32_t* const* pair_ref,
-                       int32_t* const* pix, int32_t* const* cls, int32_t* const* seg, void* stream);
+                       int32_t* const* pix, int32_t* const* cls, int32_t* const* seg, int32_t* const* slot,
+                       void* stream);
 /* host helper: advance an MT19937 state by k draws exactly as at::mt19937 does */
 int mscs_mt19937_advance_host(uint32_t* mt_state_host, int* mt_pos, uint64_t k);
 
@@ -131,6 +134,10 @@ int mscs_mt19937_advance_host(uint32_t* mt_state_host, int* mt_pos, uint64_t k);
  * ------------------------------------------------------------------------------------- */
 int mscs_gather_normalize(const float* feat, int n, int C, int plane, const int32_t* pix, int N,
                           void* anc_bf16, float* anc_f32, float* inv_norm, void* stream);
+/* same result, driven by the slot map (pixel -> row) in ADDRESS order, which keeps the strided sector
+ * reads inside open DRAM pages; needs plane % 8 == 0 */
+int mscs_gather_normalize_sectors(const float* feat, int n, int C, int plane, const int32_t* slot, int N,
+                                  void* anc_bf16, float* anc_f32, float* inv_norm, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * K3 / K4 -- fused similarity + loss forward and backward for every term of one call.
