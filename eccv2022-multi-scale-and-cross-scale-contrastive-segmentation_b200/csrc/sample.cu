@@ -157,10 +157,13 @@ __global__ void k_tile_scan(const __grid_constant__ SampleLayout L, char* ws) {
   int b = e / L.A, c = e - b * L.A;
   int* tc = reinterpret_cast<int*>(ws + g.off_tilecnt) + (size_t)b * g.tiles * L.A + c;
   int run = 0;
-  for (int t = 0; t < g.tiles; ++t) {
-    int v = tc[(size_t)t * L.A];
-    tc[(size_t)t * L.A] = run;
-    run += v;
+  for (int t0 = 0; t0 < g.tiles; t0 += 32) {      // 32 independent loads in flight, then the serial sum
+    int v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = (t0 + i < g.tiles) ? tc[(size_t)(t0 + i) * L.A] : 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (t0 + i < g.tiles) { tc[(size_t)(t0 + i) * L.A] = run; run += v[i]; }
   }
 }
 
@@ -394,26 +397,40 @@ k_fy_select(const __grid_constant__ SampleLayout L, const __grid_constant__ Sele
     r_arr[i] = r;
   }
   __syncthreads();
-  // rank -> pixel, one warp per sample
+  // rank -> pixel, one warp per sample.  The per-tile prefix column of (image, class) is staged in
+  // smem (t_arr / w_arr are dead by now); the 1024 labels of the hit tile are fetched with 32
+  // independent loads per lane-group before the ballots, so one memory latency is paid, not 32.
   const int lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
   const int* prefix = reinterpret_cast<const int*>(ws + g.off_tilecnt) + (size_t)b * g.tiles * A + c;
   const short* dlab = reinterpret_cast<const short*>(ws + g.off_dlab) + (size_t)b * g.hw;
+  int* pre_s = sm;                                  // reuse: needs g.tiles <= 2V ints, else read global
+  const bool pre_in_smem = g.tiles <= 2 * V;
+  if (pre_in_smem) for (int t = tid; t < g.tiles; t += blockDim.x) pre_s[t] = prefix[(size_t)t * A];
+  __syncthreads();
   for (int i = wid; i < V; i += nw) {
-    int r = r_arr[i];
+    const int r = r_arr[i];
     int lo = 0, hi = g.tiles - 1;          // last tile whose exclusive prefix <= r
     while (lo < hi) {
-      int mid = (lo + hi + 1) >> 1;
-      if (prefix[(size_t)mid * A] <= r) lo = mid; else hi = mid - 1;
+      const int mid = (lo + hi + 1) >> 1;
+      const int pv = pre_in_smem ? pre_s[mid] : prefix[(size_t)mid * A];
+      if (pv <= r) lo = mid; else hi = mid - 1;
     }
-    int rem = r - prefix[(size_t)lo * A];
-    int p = -1;
+    int rem = r - (pre_in_smem ? pre_s[lo] : prefix[(size_t)lo * A]);
+    short lab[kTile / 32];
+#pragma unroll
     for (int ch = 0; ch < kTile / 32; ++ch) {
-      int q = lo * kTile + ch * 32 + lane;
-      int v = (q < g.hw) ? (int)dlab[q] : -1;
-      unsigned m = __ballot_sync(0xffffffffu, v == c);
-      int pc = __popc(m);
-      if (rem < pc) { p = lo * kTile + ch * 32 + (int)__fns(m, 0, rem + 1); break; }
-      rem -= pc;
+      const int q = lo * kTile + ch * 32 + lane;
+      lab[ch] = (q < g.hw) ? dlab[q] : (short)-1;
+    }
+    int p = -1;
+#pragma unroll
+    for (int ch = 0; ch < kTile / 32; ++ch) {
+      const unsigned m = __ballot_sync(0xffffffffu, (int)lab[ch] == c);
+      const int pc = __popc(m);
+      if (p < 0) {
+        if (rem < pc) p = lo * kTile + ch * 32 + (int)__fns(m, 0, rem + 1);
+        else rem -= pc;
+      }
     }
     if (lane == 0) {
       a.idx_ref[s][(size_t)k * V + i] = p;
