@@ -77,10 +77,6 @@ static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parit
       __trap();
     }
   }
-#ifndef MSCS_WAIT_PROFILE
-  atomicAdd(&g_wait_ns[tag & 31], globaltimer_ns() - t0);
-  atomicAdd(&g_wait_cnt[tag & 31], 1ull);
-#endif
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
 #ifdef MSCS_WAIT_PROFILE     // profiling build (make prof): time every wait, including the first probe
@@ -208,6 +204,65 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// 2^(v*scale) on the FMA / ALU pipes only (no MUFU): round-to-nearest split x = n + f with the
+// 1.5*2^23 trick, degree-4 minimax polynomial of 2^f on [-0.5, 0.5] (max relative error 2.7e-6),
+// n added into the exponent field.  Valid for |v*scale| < 120.  Used to take part of the exp
+// load off the 16/clk/SM MUFU unit in the forward epilogue.
+__device__ __forceinline__ float ex2_poly(float v, float scale) {
+  const float magic = 12582912.f;
+  const float t = fmaf(v, scale, magic);
+  const float n = t - magic;
+  const float f = fmaf(v, scale, -n);
+  float p = fmaf(0.009570100344717503f, f, 0.05591785907745361f);
+  p = fmaf(p, f, 0.240247443318367f);
+  p = fmaf(p, f, 0.6931217908859253f);
+  p = fmaf(p, f, 0.9999992847442627f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+// ---- packed fp32x2 arithmetic (sm_100: one FMA-pipe issue slot for two elements) -------------
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pack2u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// two exponentials 2^(v*scale) per call, polynomial path (see ex2_poly), packed arithmetic:
+// 7 FMA-pipe instructions + 2 integer adds for two elements
+__device__ __forceinline__ uint64_t ex2_poly2(uint64_t v, uint64_t scale2) {
+  const uint64_t magic = pack2(12582912.f, 12582912.f), nmagic = pack2(-12582912.f, -12582912.f);
+  const uint64_t t = fma2(v, scale2, magic);
+  const uint64_t n = add2(t, nmagic);
+  const uint64_t nn = n ^ 0x8000000080000000ull;          // -n (sign flips fold into the operand modifiers)
+  const uint64_t f = fma2(v, scale2, nn);
+  uint64_t p = fma2(pack2(0.009570100344717503f, 0.009570100344717503f), f, pack2(0.05591785907745361f, 0.05591785907745361f));
+  p = fma2(p, f, pack2(0.240247443318367f, 0.240247443318367f));
+  p = fma2(p, f, pack2(0.6931217908859253f, 0.6931217908859253f));
+  p = fma2(p, f, pack2(0.9999992847442627f, 0.9999992847442627f));
+  const uint32_t plo = (uint32_t)p, phi = (uint32_t)(p >> 32), tlo = (uint32_t)t, thi = (uint32_t)(t >> 32);
+  return pack2u(plo + (tlo << 23), phi + (thi << 23));
 }
 __device__ __forceinline__ float lg2(float x) {
   float y;

@@ -18,6 +18,7 @@
 //                                  MN-major B operand) -> TMEM
 // dX stays in TMEM for the whole run and is flushed with fp32 reductions at the end.
 #include "sim_tc.cuh"
+#include <stdlib.h>
 
 namespace mscs {
 
@@ -36,10 +37,11 @@ struct BwdArgs {
   BwdDev p[MSCS_MAX_PASSES];
   WorkTable work;
   const float* grad_out;
+  int flags;      // MSCS_DEBUG_FLAGS experiments: 64 = un-split dX MMAs (N = C_pad, one release per Y stage)
 };
 
 __host__ __device__ constexpr size_t bwd_smem_bytes(int KB) {
-  return 1024 + (size_t)(3 * KB) * kBlkBytes + 2 * 3 * 128 * sizeof(float) + 256;   // 21 barriers + TMEM slot < 256 B
+  return 1024 + (size_t)(3 * KB) * kBlkBytes + 2 * 3 * 128 * sizeof(float) + 256;   // 24 barriers + TMEM slot < 256 B
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -64,7 +66,10 @@ __global__ void __maxnreg__(152) k_sim_bwd(const __grid_constant__ BwdArgs args)
   float* cstat = reinterpret_cast<float*>(smB + (size_t)2 * KB * kBlkBytes);   // [2 buffers][3][128] column coefficients
   uint64_t* bars = reinterpret_cast<uint64_t*>(cstat + 2 * 3 * 128);
   uint64_t* a_full = bars;        uint64_t* a_empty = bars + 1;
-  uint64_t* b_empty = bars + 2;                                     // [2]
+  uint64_t* b_empty = bars + 20;                                    // [2 stages][2 channel halves]: the dX product
+                                                                    // runs channel half by channel half, so the first
+                                                                    // K-blocks of a Y stage are refilled while the
+                                                                    // second half of the product still reads the rest
   uint64_t* s_full = bars + 4;                                      // [2]
   uint64_t* w_full = bars + 6;                                      // [2 halves][2 S buffers]: one phase per
                                                                     // two tiles, so a column-half group that runs a
@@ -72,13 +77,15 @@ __global__ void __maxnreg__(152) k_sim_bwd(const __grid_constant__ BwdArgs args)
   uint64_t* df_full = bars + 10;  uint64_t* df_empty = bars + 11;
   uint64_t* b_full = bars + 12;                                     // [2 stages][4 K-blocks]: the S MMAs start on
                                                                     // the first 16 KB of a tile, not the whole 64 KB
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  constexpr bool kCanSplit = (KB % 2 == 0);
+  const bool split = kCanSplit && !(args.flags & 64);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     ptx::mbar_init(a_full, 1); ptx::mbar_init(a_empty, 1);
     for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&b_empty[i], 1);
+      ptx::mbar_init(&b_empty[2 * i], 1); ptx::mbar_init(&b_empty[2 * i + 1], 1);
       for (int kb = 0; kb < 4; ++kb) ptx::mbar_init(&b_full[i * 4 + kb], 1);
       ptx::mbar_init(&s_full[i], 1);
       ptx::mbar_init(&w_full[i], 4); ptx::mbar_init(&w_full[2 + i], 4);
@@ -91,6 +98,10 @@ __global__ void __maxnreg__(152) k_sim_bwd(const __grid_constant__ BwdArgs args)
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+#ifdef MSCS_WAIT_PROFILE     // effective SM clock of this launch: slot 31 accumulates (ns, cycles) of CTA 0
+  const unsigned long long prof_t0 = ptx::globaltimer_ns();
+  const long long prof_c0 = clock64();
+#endif
   const uint32_t tmem_dF = tmem_base + 256;
 
   // Roles 0 and 1 run on the whole warp with warp-uniform control flow; one lane issues (see sim_fwd.cu)
@@ -110,13 +121,19 @@ __global__ void __maxnreg__(152) k_sim_bwd(const __grid_constant__ BwdArgs args)
       a_phase ^= 1;
       for (int ct = sg.c_begin; ct < sg.c_end; ++ct, ++it) {
         const uint32_t st = it & 1;
-        ptx::mbar_wait(&b_empty[st], ((it >> 1) & 1) ^ 1, 202);
-        if (ptx::elect_one()) {
-          for (int kb = 0; kb < KB; ++kb) {
-            ptx::mbar_expect_tx(&b_full[st * 4 + kb], kBlkBytes);
-            ptx::tma_load_2d(smB + (size_t)(st * KB + kb) * kBlkBytes, &args.maps[p.y_map], &b_full[st * 4 + kb],
-                             kb * kKBlk, ct * kTileN);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          // un-split: both halves are released together by the same commit
+          ptx::mbar_wait(&b_empty[2 * st + q], ((it >> 1) & 1) ^ 1, 202 + q);
+          const int kb0 = q == 0 ? 0 : (KB + 1) / 2, kb1 = q == 0 ? (KB + 1) / 2 : KB;
+          if (ptx::elect_one()) {
+            for (int kb = kb0; kb < kb1; ++kb) {
+              ptx::mbar_expect_tx(&b_full[st * 4 + kb], kBlkBytes);
+              ptx::tma_load_2d(smB + (size_t)(st * KB + kb) * kBlkBytes, &args.maps[p.y_map], &b_full[st * 4 + kb],
+                               kb * kKBlk, ct * kTileN);
+            }
           }
+          __syncwarp();
         }
       }
     }
@@ -124,6 +141,7 @@ __global__ void __maxnreg__(152) k_sim_bwd(const __grid_constant__ BwdArgs args)
     // ================= MMA issuer =================
     constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(128, kTileN, 0, 0);   // S  = X Y^T
     constexpr uint32_t idesc_d = ptx::umma_idesc_bf16(128, CP, 0, 1);       // dX += W Y (B MN-major)
+    constexpr uint32_t idesc_dh = ptx::umma_idesc_bf16(128, kCanSplit ? CP / 2 : CP, 0, 1);   // one channel half
     const uint32_t a_addr = ptx::smem_u32(smA), b_addr = ptx::smem_u32(smB);
     Walker wk(args.work);
     Segment sg;
@@ -160,25 +178,47 @@ __global__ void __maxnreg__(152) k_sim_bwd(const __grid_constant__ BwdArgs args)
         // turns S(cur) into W(cur).  (Splitting S(cur+1) around dX(cur) to release the Y stage earlier
         // measured slower: 0.585 vs 0.513 ms at cfg-2 -- the dX MMAs then wait for W.)
         if (j + 1 < ntiles) issue_s(cur + 1, 0, KB);
+        if (!split) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          ptx::mbar_wait(&w_full[h * 2 + st], (cur >> 1) & 1, 214 + h);
-          ptx::tc_fence_after();
-          if (ptx::elect_one()) {
+          for (int h = 0; h < 2; ++h) {
+            ptx::mbar_wait(&w_full[h * 2 + st], (cur >> 1) & 1, 214 + h);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              // W of column half h lives in columns [64h, 64h+32) of S buffer st, 8 columns per K=16 slice
-              const uint32_t a_tm = tmem_base + st * 128 + h * 64 + k * 8;
-              // Y rows h*64 + k*16 .. +16 are the K slice; LBO = next 64-channel block, SBO = next 8 K rows
-              const uint64_t bd = ptx::umma_desc_sw128(b_addr + st * KB * kBlkBytes + (h * 64 + k * 16) * 128,
-                                                       kBlkBytes, 1024);
-              ptx::umma_ts(tmem_dF, a_tm, bd, idesc_d, (j | h | k) != 0);
+              for (int k = 0; k < 4; ++k) {
+                // W of column half h lives in columns [64h, 64h+32) of S buffer st, 8 columns per K=16 slice
+                const uint32_t a_tm = tmem_base + st * 128 + h * 64 + k * 8;
+                // Y rows h*64 + k*16 .. +16 are the K slice; LBO = next 64-channel block, SBO = next 8 K rows
+                const uint64_t bd = ptx::umma_desc_sw128(b_addr + st * KB * kBlkBytes + (h * 64 + k * 16) * 128,
+                                                         kBlkBytes, 1024);
+                ptx::umma_ts(tmem_dF, a_tm, bd, idesc_d, (j | h | k) != 0);
+              }
             }
+            __syncwarp();
           }
+          if (ptx::elect_one()) { ptx::umma_commit(&b_empty[2 * st]); ptx::umma_commit(&b_empty[2 * st + 1]); }
           __syncwarp();
+        } else {
+          // channel half q of dX needs only the K-blocks of that half: release them as soon as it is done
+          ptx::mbar_wait(&w_full[st], (cur >> 1) & 1, 214);
+          ptx::mbar_wait(&w_full[2 + st], (cur >> 1) & 1, 215);
+          ptx::tc_fence_after();
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int hk = 0; hk < 8; ++hk) {
+                const int h = hk >> 2, k = hk & 3;
+                const uint32_t a_tm = tmem_base + st * 128 + h * 64 + k * 8;
+                const uint64_t bd = ptx::umma_desc_sw128(
+                    b_addr + (st * KB + q * (KB / 2)) * kBlkBytes + (h * 64 + k * 16) * 128, kBlkBytes, 1024);
+                ptx::umma_ts(tmem_dF + q * (CP / 2), a_tm, bd, idesc_dh, (j | hk) != 0);
+              }
+              ptx::umma_commit(&b_empty[2 * st + q]);
+            }
+            __syncwarp();
+          }
         }
-        if (ptx::elect_one()) ptx::umma_commit(&b_empty[st]);
-        __syncwarp();
       }
       if (ptx::elect_one()) { ptx::umma_commit(df_full); ptx::umma_commit(a_empty); }
       __syncwarp();
@@ -310,6 +350,12 @@ __global__ void __maxnreg__(152) k_sim_bwd(const __grid_constant__ BwdArgs args)
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+#ifdef MSCS_WAIT_PROFILE
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    atomicAdd(&ptx::g_wait_ns[31], ptx::globaltimer_ns() - prof_t0);
+    atomicAdd(&ptx::g_wait_cnt[31], (unsigned long long)(clock64() - prof_c0));
+  }
+#endif
 }
 
 }  // namespace mscs
@@ -345,6 +391,7 @@ extern "C" int mscs_sim_backward(const mscs_sim_job* job, const float* grad_out,
             2 * (align_up(sizeof(WorkItem) * fwd_items, 64) + align_up(sizeof(int) * (fwd_items + 1), 64));
   BwdArgs args{};
   args.grad_out = grad_out;
+  if (const char* e = getenv("MSCS_DEBUG_FLAGS")) args.flags = atoi(e);
   const void* bases[MSCS_MAX_SCALES]; int nmaps = 0;
   auto map_of = [&](const void* base, int rows) -> int {
     for (int i = 0; i < nmaps; ++i) if (bases[i] == base) return i;

@@ -13,15 +13,21 @@
 // shared-memory operand traffic per FLOP is 25% lower than with 128x128 MMAs (which measured at
 // ~45% of the tensor peak here, shared-memory bound) and the accumulate dependency is hidden.
 // Accumulators (128 lanes x 256 columns) are double-buffered in TMEM.
-// Warp roles: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..11 epilogue: thread = (anchor row
-// of the streamed tile, 128-key half); partial row sums go out with one atomicAdd per row and tile.
+// Warp roles: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..11 / 12..19 epilogue groups 0 / 1
+// (even / odd tiles): thread = (anchor row of the tile, 128-key half); partial row sums go out with
+// one atomicAdd per row, half and tile.
 #include "sim_tc.cuh"
 #include <stdlib.h>
 
 namespace mscs {
 
 constexpr int kFwdKeys = 256;       // resident key block = N of the MMA
-constexpr int kFwdThreads = 384;
+// Two epilogue groups of 8 warps: group g owns accumulator buffer g, i.e. every second tile, so the TMEM-load
+// latency and barrier hand-over of one tile overlap the exponentials of the other (with one group the
+// MUFU unit idled half of the time although it is the busiest unit of the pass).
+constexpr int kFwdEpiWarps = 16;
+constexpr int kFwdThreads = 128 + 32 * kFwdEpiWarps;
+constexpr int kFwdColsPerThread = kFwdKeys / 2;      // thread = (anchor row, 128-key half) of its group's tiles
 constexpr int kFwdStages = 5;
 
 struct FwdTerm {
@@ -41,6 +47,20 @@ struct FwdArgs {
 
 __host__ __device__ constexpr size_t fwd_smem_bytes(int KB) {
   return 1024 /*alignment slack*/ + (size_t)(2 * KB + kFwdStages) * kBlkBytes + 256 /*barriers*/;
+}
+
+// 32 unmasked logits -> 4 partial sums of exp2(v * scale).  Bit (c & 7) of POLY selects the elements
+// whose exponential is evaluated as a polynomial on the FMA pipe instead of MUFU.EX2 (the MUFU unit,
+// 16 results/clk/SM, is the forward pass's second bottleneck next to the tensor pipe).
+template <int POLY>
+__device__ __forceinline__ void fast_chunk(const uint32_t (&cur)[32], float scale, float& acc0, float& acc1,
+                                           float& acc2, float& acc3) {
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    const float v = __uint_as_float(cur[c]);
+    const float e = ((POLY >> (c & 7)) & 1) ? ptx::ex2_poly(v, scale) : ptx::ex2(v * scale);
+    if ((c & 3) == 0) acc0 += e; else if ((c & 3) == 1) acc1 += e; else if ((c & 3) == 2) acc2 += e; else acc3 += e;
+  }
 }
 
 template <int KB, int MODE>
@@ -63,7 +83,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < kFwdStages; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
     ptx::mbar_init(k_full, 1); ptx::mbar_init(k_empty, 1);
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], kFwdEpiWarps / 2); }
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc(tmem_slot, 512);
@@ -71,6 +91,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+#ifdef MSCS_WAIT_PROFILE     // effective SM clock of this launch: slot 31 accumulates (ns, cycles) of CTA 0
+  const unsigned long long prof_t0 = ptx::globaltimer_ns();
+  const long long prof_c0 = clock64();
+#endif
 
   // Roles 0 and 1 are executed by the WHOLE warp (waits, loop control and descriptor arithmetic stay
   // warp-uniform); only the TMA / MMA instructions themselves are issued by one elected lane.
@@ -119,12 +143,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
           ptx::mbar_wait(&a_full[stage], phase, 113);
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
+            if (!(args.debug_flags & 2)) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ad = ptx::umma_desc_sw128(a_addr + stage * kBlkBytes + k * 32, 16, 1024);
-              const uint64_t bd = ptx::umma_desc_sw128(k_addr + kb * 2 * kBlkBytes + k * 32, 16, 1024);
-              ptx::umma_ss(tmem_base + buf * kFwdKeys, ad, bd, idesc, (kb | k) != 0);
-            }
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t ad = ptx::umma_desc_sw128(a_addr + stage * kBlkBytes + k * 32, 16, 1024);
+                const uint64_t bd = ptx::umma_desc_sw128(k_addr + kb * 2 * kBlkBytes + k * 32, 16, 1024);
+                ptx::umma_ss(tmem_base + buf * kFwdKeys, ad, bd, idesc, (kb | k) != 0);
+              }
+            }      // experiment 2: no MMAs, the stage is released at once (pure TMA streaming rate)
             ptx::umma_commit(&a_empty[stage]);
           }
           __syncwarp();
@@ -138,59 +164,50 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
     }
   } else if (warp >= 4) {
     // ================= epilogue: thread = (anchor row of the tile, 128-key half) =================
-    const int ch = (warp - 4) >> 2, quad = warp & 3;
+    constexpr int CPT = kFwdColsPerThread, NCH = CPT / 32;
+    const int grp = (warp - 4) >> 3, ch = ((warp - 4) >> 2) & 1, quad = warp & 3;
     Walker wk(args.work);
     Segment sg;
     uint32_t it = 0;
     while (wk.next(sg)) {
       const FwdTerm& t = args.t[sg.owner];
-      const int cb = sg.rb * kFwdKeys + ch * 128;          // first key column of this thread's half
+      const int cb = sg.rb * kFwdKeys + ch * CPT;          // first key column of this thread's quarter
       const float scale = t.scale_log2;
-      // positive key range of each row (and of its 32-row group) comes precomputed from k_row_ranges;
-      // the values of the NEXT tile are fetched one tile ahead so no load sits on the critical path
-      int2 n_rr = make_int2(0, 0), n_gr = make_int2(0x7fffffff, 0); float n_neg = 1.f;
-      auto fetch_row = [&](int rt_) {
-        const int r = rt_ * 128 + quad * 32 + lane;
-        n_rr = make_int2(0, 0); n_gr = make_int2(0x7fffffff, 0); n_neg = 1.f;
-        if (rt_ < sg.c_end) {
-          n_gr = t.grp_range[rt_ * 4 + quad];
-          if (r < t.N1) {
-            n_rr = t.row_range[r];
-            if (MODE == 1) n_neg = t.neg[r];
-          }
-        }
-      };
-      fetch_row(sg.c_begin);
+      // positive key range of each row (and of its 32-row group) comes precomputed from k_row_ranges; the
+      // loads are issued before the accumulator wait (the other group keeps the SM busy meanwhile)
       for (int rt = sg.c_begin; rt < sg.c_end; ++rt, ++it) {
         const uint32_t buf = it & 1;
+        if (buf != (uint32_t)grp) continue;
         const int row = rt * 128 + quad * 32 + lane;
         const bool valid = row < t.N1;
+        const int2 n_gr = t.grp_range[rt * 4 + quad];
+        const int2 n_rr = valid ? t.row_range[row] : make_int2(0, 0);
+        const float negi = (MODE == 1 && valid) ? t.neg[row] : 1.f;
         const int p0 = n_rr.x, p1 = n_rr.y, wmin = n_gr.x, wmax = n_gr.y;
-        const float negi = n_neg;
-        fetch_row(rt + 1);
         const unsigned plen = (unsigned)(p1 - p0);
         const int self_col = t.self_mask ? row : -1;
-        const bool touches = !(cb + 128 <= wmin || cb >= wmax);
+        const bool touches = !(cb + CPT <= wmin || cb >= wmax);
         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;   // MODE 1: acc0 = pos (log2 units), acc1 = S
         ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1, 121);
         ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kFwdKeys + ch * 128;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kFwdKeys + ch * CPT;
         if (args.debug_flags & 1) {
           // experiment: no TMEM reads / math
         } else if (MODE == 0) {
-          if (cb < t.N2) {      // a half that lies entirely in the zero padding of the key block has no work
+          if (cb < t.N2) {      // a quarter that lies entirely in the zero padding of the key block has no work
             uint32_t va[32], vb[32];
             ptx::tmem_ld32(taddr, va);
             ptx::tmem_ld_wait(va);
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
+            for (int c4 = 0; c4 < NCH; ++c4) {
               uint32_t (&cur)[32] = (c4 & 1) ? vb : va;
               uint32_t (&nxt)[32] = (c4 & 1) ? va : vb;
-              if (c4 < 3) ptx::tmem_ld32(taddr + (c4 + 1) * 32, nxt);
+              if (c4 < NCH - 1) ptx::tmem_ld32(taddr + (c4 + 1) * 32, nxt);
               const int c0 = cb + c4 * 32;
               // 32-column chunk without positives of any row of this warp and inside the key set: no masks
               const bool fast = (c0 + 32 <= wmin || c0 >= wmax) && (c0 + 32 <= t.N2);
-              if (fast && (args.debug_flags & 4)) {      // experiment: no MUFU (wrong results)
+              if (args.debug_flags & 8) {               // experiment: TMEM loads only, no math (wrong results)
+              } else if (fast && (args.debug_flags & 4)) {      // experiment: no MUFU (wrong results)
 #pragma unroll
                 for (int c = 0; c < 32; c += 4) {
                   acc0 += __uint_as_float(cur[c]) * scale;
@@ -199,13 +216,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
                   acc3 += __uint_as_float(cur[c + 3]) * scale;
                 }
               } else if (fast) {
-#pragma unroll
-                for (int c = 0; c < 32; c += 4) {
-                  acc0 += ptx::ex2(__uint_as_float(cur[c]) * scale);
-                  acc1 += ptx::ex2(__uint_as_float(cur[c + 1]) * scale);
-                  acc2 += ptx::ex2(__uint_as_float(cur[c + 2]) * scale);
-                  acc3 += ptx::ex2(__uint_as_float(cur[c + 3]) * scale);
-                }
+                const int pm = (args.debug_flags >> 4) & 3;      // experiment: share of exps on the FMA pipe
+                if (pm == 0) fast_chunk<0x00>(cur, scale, acc0, acc1, acc2, acc3);
+                else if (pm == 1) fast_chunk<0x88>(cur, scale, acc0, acc1, acc2, acc3);
+                else if (pm == 2) fast_chunk<0x92>(cur, scale, acc0, acc1, acc2, acc3);
+                else fast_chunk<0xAA>(cur, scale, acc0, acc1, acc2, acc3);
               } else if (c0 < t.N2) {
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
@@ -215,12 +230,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
                   acc0 += isneg ? e : 0.f;
                 }
               }
-              if (c4 < 3) ptx::tmem_ld_wait(nxt);
+              if (c4 < NCH - 1) ptx::tmem_ld_wait(nxt);
             }
           }
         } else if (touches) {
 #pragma unroll 1
-          for (int c4 = 0; c4 < 4; ++c4) {
+          for (int c4 = 0; c4 < NCH; ++c4) {
             const int c0 = cb + c4 * 32;
             if (c0 + 32 <= wmin || c0 >= wmax) continue;      // warp-uniform
             uint32_t v[32];
@@ -251,6 +266,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+#ifdef MSCS_WAIT_PROFILE
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    atomicAdd(&ptx::g_wait_ns[31], ptx::globaltimer_ns() - prof_t0);
+    atomicAdd(&ptx::g_wait_cnt[31], (unsigned long long)(clock64() - prof_c0));
+  }
+#endif
 }
 
 // per anchor row: positive key range [k_seg[y], k_seg[y+1]); per 32-row group: the union (groups are

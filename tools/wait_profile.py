@@ -27,6 +27,8 @@ namesb = {201 % 32: "bwd producer a_empty", 202 % 32: "bwd producer b_empty", 21
 for which, nm in (("fwd", names), ("bwd", namesb)):
     getattr(lib, f"mscs_debug_wait_profile_{which}")(ns.ctypes.data, cnt.ctypes.data)
     print(which, "(per step, summed over 148 CTAs; divide by 148 for per-CTA; epilogue tags are per thread)")
-    for t in range(32):
+    if ns[31]:
+        print(f"  CTA 0: {ns[31]/K/1e3:.1f} us/step in this kernel family, effective SM clock {cnt[31]/ns[31]:.3f} GHz")
+    for t in range(31):
         if cnt[t]:
             print(f"  tag%32={t:2d} {nm.get(t,'?'):40s} waits/step {cnt[t]/K:10.0f}  us/step/CTA {ns[t]/K/148/1e3:10.1f}")
