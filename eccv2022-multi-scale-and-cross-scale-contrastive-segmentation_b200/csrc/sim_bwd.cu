@@ -22,7 +22,10 @@
 
 namespace mscs {
 
-constexpr int kBwdThreads = 384;
+constexpr int kBwdEpiWarps = 16;     // 4 per SM sub-partition: thread = (row, 32-column quarter of the tile).  The
+                                     // S -> W conversion sits between the two MMAs of a tile (S buffer cycle =
+                                     // S MMAs + conversion + dX MMAs), so its LATENCY bounds the tile rate
+constexpr int kBwdThreads = 128 + 32 * kBwdEpiWarps;
 
 struct BwdDev {
   const int* row_cls; const int* col_seg;
@@ -41,7 +44,7 @@ struct BwdArgs {
 };
 
 __host__ __device__ constexpr size_t bwd_smem_bytes(int KB) {
-  return 1024 + (size_t)(3 * KB) * kBlkBytes + 2 * 3 * 128 * sizeof(float) + 256;   // 24 barriers + TMEM slot < 256 B
+  return 1024 + (size_t)(3 * KB) * kBlkBytes + (size_t)kBwdEpiWarps * 2 * 3 * 32 * sizeof(float) + 256;   // 24 barriers + TMEM slot < 256 B
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -57,23 +60,23 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 }
 
 template <int KB>
-__global__ void __maxnreg__(152) k_sim_bwd(const __grid_constant__ BwdArgs args) {
+__global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constant__ BwdArgs args) {
   constexpr int CP = KB * 64;                       // padded channel count = N of the second MMA
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smA = smem;                                         // [KB][128][128 B]   X tile
   uint8_t* smB = smA + (size_t)KB * kBlkBytes;                 // [2][KB][128][128 B] Y tiles
-  float* cstat = reinterpret_cast<float*>(smB + (size_t)2 * KB * kBlkBytes);   // [2 buffers][3][128] column coefficients
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cstat + 2 * 3 * 128);
+  float* cstat = reinterpret_cast<float*>(smB + (size_t)2 * KB * kBlkBytes);   // per epilogue warp: [2 buffers][3][32] column coefficients
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cstat + kBwdEpiWarps * 2 * 3 * 32);
   uint64_t* a_full = bars;        uint64_t* a_empty = bars + 1;
   uint64_t* b_empty = bars + 20;                                    // [2 stages][2 channel halves]: the dX product
                                                                     // runs channel half by channel half, so the first
                                                                     // K-blocks of a Y stage are refilled while the
                                                                     // second half of the product still reads the rest
   uint64_t* s_full = bars + 4;                                      // [2]
-  uint64_t* w_full = bars + 6;                                      // [2 halves][2 S buffers]: one phase per
-                                                                    // two tiles, so a column-half group that runs a
-                                                                    // tile ahead of the MMA thread cannot overrun it
+  uint64_t* w_full = bars + 6;                                      // [2 S buffers]: one phase per two tiles, so a
+                                                                    // warp that runs a tile ahead of the MMA thread
+                                                                    // cannot overrun it
   uint64_t* df_full = bars + 10;  uint64_t* df_empty = bars + 11;
   uint64_t* b_full = bars + 12;                                     // [2 stages][4 K-blocks]: the S MMAs start on
                                                                     // the first 16 KB of a tile, not the whole 64 KB
@@ -88,9 +91,9 @@ __global__ void __maxnreg__(152) k_sim_bwd(const __grid_constant__ BwdArgs args)
       ptx::mbar_init(&b_empty[2 * i], 1); ptx::mbar_init(&b_empty[2 * i + 1], 1);
       for (int kb = 0; kb < 4; ++kb) ptx::mbar_init(&b_full[i * 4 + kb], 1);
       ptx::mbar_init(&s_full[i], 1);
-      ptx::mbar_init(&w_full[i], 4); ptx::mbar_init(&w_full[2 + i], 4);
+      ptx::mbar_init(&w_full[i], kBwdEpiWarps);
     }
-    ptx::mbar_init(df_full, 1); ptx::mbar_init(df_empty, 8);
+    ptx::mbar_init(df_full, 1); ptx::mbar_init(df_empty, kBwdEpiWarps);
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc(tmem_slot, 512);
@@ -178,41 +181,33 @@ __global__ void __maxnreg__(152) k_sim_bwd(const __grid_constant__ BwdArgs args)
         // turns S(cur) into W(cur).  (Splitting S(cur+1) around dX(cur) to release the Y stage earlier
         // measured slower: 0.585 vs 0.513 ms at cfg-2 -- the dX MMAs then wait for W.)
         if (j + 1 < ntiles) issue_s(cur + 1, 0, KB);
+        // W of tile column quarter cq lives in columns [32cq, 32cq+16) of S buffer st: the K = 16 slice ks
+        // (tile columns 16ks .. 16ks+15, two bf16 per TMEM column) is at column 32 (ks / 2) + 8 (ks % 2).
+        // Y rows 16ks .. 16ks+15 are the matching K slice of B; LBO = next 64-channel block, SBO = next 8 rows.
+        ptx::mbar_wait(&w_full[st], (cur >> 1) & 1, 214);
+        ptx::tc_fence_after();
         if (!split) {
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            ptx::mbar_wait(&w_full[h * 2 + st], (cur >> 1) & 1, 214 + h);
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                // W of column half h lives in columns [64h, 64h+32) of S buffer st, 8 columns per K=16 slice
-                const uint32_t a_tm = tmem_base + st * 128 + h * 64 + k * 8;
-                // Y rows h*64 + k*16 .. +16 are the K slice; LBO = next 64-channel block, SBO = next 8 K rows
-                const uint64_t bd = ptx::umma_desc_sw128(b_addr + st * KB * kBlkBytes + (h * 64 + k * 16) * 128,
-                                                         kBlkBytes, 1024);
-                ptx::umma_ts(tmem_dF, a_tm, bd, idesc_d, (j | h | k) != 0);
-              }
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint32_t a_tm = tmem_base + st * 128 + (ks >> 1) * 32 + (ks & 1) * 8;
+              const uint64_t bd = ptx::umma_desc_sw128(b_addr + st * KB * kBlkBytes + ks * 16 * 128, kBlkBytes, 1024);
+              ptx::umma_ts(tmem_dF, a_tm, bd, idesc_d, (j | ks) != 0);
             }
-            __syncwarp();
+            ptx::umma_commit(&b_empty[2 * st]); ptx::umma_commit(&b_empty[2 * st + 1]);
           }
-          if (ptx::elect_one()) { ptx::umma_commit(&b_empty[2 * st]); ptx::umma_commit(&b_empty[2 * st + 1]); }
           __syncwarp();
         } else {
           // channel half q of dX needs only the K-blocks of that half: release them as soon as it is done
-          ptx::mbar_wait(&w_full[st], (cur >> 1) & 1, 214);
-          ptx::mbar_wait(&w_full[2 + st], (cur >> 1) & 1, 215);
-          ptx::tc_fence_after();
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             if (ptx::elect_one()) {
 #pragma unroll
-              for (int hk = 0; hk < 8; ++hk) {
-                const int h = hk >> 2, k = hk & 3;
-                const uint32_t a_tm = tmem_base + st * 128 + h * 64 + k * 8;
+              for (int ks = 0; ks < 8; ++ks) {
+                const uint32_t a_tm = tmem_base + st * 128 + (ks >> 1) * 32 + (ks & 1) * 8;
                 const uint64_t bd = ptx::umma_desc_sw128(
-                    b_addr + (st * KB + q * (KB / 2)) * kBlkBytes + (h * 64 + k * 16) * 128, kBlkBytes, 1024);
-                ptx::umma_ts(tmem_dF + q * (CP / 2), a_tm, bd, idesc_dh, (j | hk) != 0);
+                    b_addr + (st * KB + q * (KB / 2)) * kBlkBytes + ks * 16 * 128, kBlkBytes, 1024);
+                ptx::umma_ts(tmem_dF + q * (CP / 2), a_tm, bd, idesc_dh, (j | ks) != 0);
               }
               ptx::umma_commit(&b_empty[2 * st + q]);
             }
@@ -225,10 +220,10 @@ __global__ void __maxnreg__(152) k_sim_bwd(const __grid_constant__ BwdArgs args)
       it += ntiles; ++seg;
     }
   } else if (warp >= 4) {
-    // ================= epilogue: thread = (row, 64-column half) =================
-    const int h = (warp - 4) >> 2, quad = warp & 3;
-    const int wg_tid = threadIdx.x - (4 + 4 * h) * 32;      // 0..127 inside the column-half group
+    // ================= epilogue: thread = (row, 32-column quarter) =================
+    const int cq = (warp - 4) >> 2, quad = warp & 3;
     const int r_loc = quad * 32 + lane;                     // row inside the tile = TMEM lane
+    float* my_cs = cstat + (warp - 4) * (2 * 3 * 32);       // this warp's [2 buffers][cs, cpn, neg][32 columns]
     const float gout = *args.grad_out;
     Walker wk(args.work);
     Segment sg;
@@ -251,13 +246,14 @@ __global__ void __maxnreg__(152) k_sim_bwd(const __grid_constant__ BwdArgs args)
       const float rneg = (valid && p.row_neg) ? p.row_neg[row] : 1.f;
       const int self_col = p.self_mask ? row : -1;
       const float scale = p.scale_log2;
-      // column coefficients of a tile are staged in smem one tile ahead (double buffered): the global
-      // loads of tile t+1 are issued before tile t is processed and parked in registers meanwhile
+      const uint64_t scale2 = ptx::pack2(scale, scale), rcs2 = ptx::pack2(rcs, rcs);
+      // column coefficients: lane l fetches those of column l of this warp's quarter one tile ahead (parked in
+      // registers), then the warp stages them in its own smem slot -- no cross-warp synchronisation
       float pf_s = 0.f, pf_pn = 0.f, pf_neg = 1.f;
       auto prefetch_cols = [&](int ct_) {
         pf_s = 0.f; pf_pn = 0.f; pf_neg = 1.f;
-        if (wg_tid < 64 && ct_ < sg.c_end) {
-          const int c = ct_ * kTileN + h * 64 + wg_tid;
+        if (ct_ < sg.c_end) {
+          const int c = ct_ * kTileN + cq * 32 + lane;
           if (c < p.n_cols) {
             if (p.col_cs) pf_s = p.col_cs[c];
             if (p.col_cpn) pf_pn = p.col_cpn[c];
@@ -266,78 +262,81 @@ __global__ void __maxnreg__(152) k_sim_bwd(const __grid_constant__ BwdArgs args)
         }
       };
       auto publish_cols = [&](uint32_t b_) {
-        if (wg_tid < 64) {
-          float* cs = cstat + b_ * 384;
-          cs[h * 64 + wg_tid] = pf_s; cs[128 + h * 64 + wg_tid] = pf_pn; cs[256 + h * 64 + wg_tid] = pf_neg;
-        }
-        named_bar_sync(1 + h, 128);
+        float* cs = my_cs + b_ * 96;
+        cs[lane] = pf_s; cs[32 + lane] = pf_pn; cs[64 + lane] = pf_neg;
+        __syncwarp();
       };
       prefetch_cols(sg.c_begin);
       publish_cols(it & 1);
       for (int ct = sg.c_begin; ct < sg.c_end; ++ct, ++it) {
         const uint32_t buf = it & 1;
-        const int cb = ct * kTileN + h * 64;               // first global column of this thread's half
-        const float* cs_s = cstat + buf * 384; const float* cs_pn = cs_s + 128; const float* cs_neg = cs_s + 256;
+        const int cb = ct * kTileN + cq * 32;               // first global column of this thread's quarter
+        const float* cs_s = my_cs + buf * 96; const float* cs_pn = cs_s + 32; const float* cs_neg = cs_s + 64;
         prefetch_cols(ct + 1);
         ptx::mbar_wait(&s_full[buf], (it >> 1) & 1, 221);
         ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128 + h * 64;
-        const bool touches = !(cb + 64 <= wmin || cb >= wmax);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * 128 + cq * 32;
+        const bool touches = !(cb + 32 <= wmin || cb >= wmax);
+        uint32_t v[32];
+        ptx::tmem_ld32(taddr, v);
+        ptx::tmem_ld_wait(v);
+        uint32_t packed[16];
+        if (!touches) {
+          // W = exp2(S scale) (cS_row + cS_col), two columns per packed fp32x2 instruction
 #pragma unroll
-        for (int part = 0; part < 2; ++part) {
-          uint32_t v[32];
-          ptx::tmem_ld32(taddr + part * 32, v);
-          ptx::tmem_ld_wait(v);
-          uint32_t packed[16];
-          if (!touches) {
+          for (int c = 0; c < 32; c += 4) {
+            const float4 cc = *reinterpret_cast<const float4*>(cs_s + c);
 #pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-              const int j = h * 64 + part * 32 + c;
-              const float w0 = ptx::ex2(__uint_as_float(v[c]) * scale) * (rcs + cs_s[j]);
-              const float w1 = ptx::ex2(__uint_as_float(v[c + 1]) * scale) * (rcs + cs_s[j + 1]);
-              packed[c >> 1] = pack_bf16(w0, w1);
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < 32; c += 2) {
-              float w[2];
-#pragma unroll
-              for (int q = 0; q < 2; ++q) {
-                const int j = h * 64 + part * 32 + c + q;
-                const int col = cb + part * 32 + c + q;
-                const float e = ptx::ex2(__uint_as_float(v[c + q]) * scale);
-                const bool ispos = (unsigned)(col - p0) < plen;
-                const float wn = e * (rcs + cs_s[j]);
-                const float wp = -(rcpn * ptx::rcp(e + rneg) + cs_pn[j] * ptx::rcp(e + cs_neg[j]));
-                w[q] = ispos ? (col == self_col ? 0.f : wp) : wn;
-              }
-              packed[c >> 1] = pack_bf16(w[0], w[1]);
+            for (int q = 0; q < 2; ++q) {
+              float x0, x1;
+              ptx::unpack2(ptx::mul2(ptx::pack2u(v[c + 2 * q], v[c + 2 * q + 1]), scale2), x0, x1);
+              const uint64_t e2 = ptx::pack2(ptx::ex2(x0), ptx::ex2(x1));
+              const uint64_t c2 = ptx::add2(rcs2, q == 0 ? ptx::pack2(cc.x, cc.y) : ptx::pack2(cc.z, cc.w));
+              float w0, w1;
+              ptx::unpack2(ptx::mul2(e2, c2), w0, w1);
+              packed[(c >> 1) + q] = pack_bf16(w0, w1);
             }
           }
-          // 32 logits -> 16 packed columns, written over S columns this thread has already read
-          ptx::tmem_st16(taddr + part * 16, packed);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            float w[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int j = c + q;
+              const int col = cb + j;
+              const float e = ptx::ex2(__uint_as_float(v[j]) * scale);
+              const bool ispos = (unsigned)(col - p0) < plen;
+              const float wn = e * (rcs + cs_s[j]);
+              const float wp = -(rcpn * ptx::rcp(e + rneg) + cs_pn[j] * ptx::rcp(e + cs_neg[j]));
+              w[q] = ispos ? (col == self_col ? 0.f : wp) : wn;
+            }
+            packed[c >> 1] = pack_bf16(w[0], w[1]);
+          }
         }
+        // 32 logits -> 16 packed columns, written over S columns this thread has already read
+        ptx::tmem_st16(taddr, packed);
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&w_full[h * 2 + buf]);
-        publish_cols(buf ^ 1);       // also: every thread of the group is done reading cstat[buf]
+        if (lane == 0) ptx::mbar_arrive(&w_full[buf]);
+        publish_cols(buf ^ 1);       // (the __syncwarp above: every lane is done reading slot buf^1's predecessor)
       }
-      // ---- flush dX: this group drains channel half h ----
+      // ---- flush dX: this warp drains channel quarter cq of its 32 rows ----
       ptx::mbar_wait(df_full, seg & 1, 222);
       ptx::tc_fence_after();
       const float sc = p.out_scale * gout;
       float* drow = p.dF + (size_t)row * p.ld;
 #pragma unroll 1
-      for (int c0 = h * (CP / 2); c0 < (h + 1) * (CP / 2); c0 += 32) {
-        uint32_t v[32];
-        ptx::tmem_ld32(tmem_dF + ((uint32_t)(quad * 32) << 16) + c0, v);
-        ptx::tmem_ld_wait(v);
+      for (int c0 = cq * (CP / 4); c0 < (cq + 1) * (CP / 4); c0 += 16) {
+        uint32_t u[16];
+        ptx::tmem_ld16(tmem_dF + ((uint32_t)(quad * 32) << 16) + c0, u);
+        ptx::tmem_ld_wait16(u);
         if (valid) {
 #pragma unroll
-          for (int c = 0; c < 32; c += 4)
-            red_add_v4(drow + c0 + c, __uint_as_float(v[c]) * sc, __uint_as_float(v[c + 1]) * sc,
-                       __uint_as_float(v[c + 2]) * sc, __uint_as_float(v[c + 3]) * sc);
+          for (int c = 0; c < 16; c += 4)
+            red_add_v4(drow + c0 + c, __uint_as_float(u[c]) * sc, __uint_as_float(u[c + 1]) * sc,
+                       __uint_as_float(u[c + 2]) * sc, __uint_as_float(u[c + 3]) * sc);
         }
       }
       ptx::tc_fence_before();
