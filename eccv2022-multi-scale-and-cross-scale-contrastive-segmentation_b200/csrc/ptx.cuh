@@ -58,12 +58,27 @@ static __device__ unsigned long long* g_trap_buf = nullptr;   // one copy per tr
 // wait profile: nanoseconds spent in the slow path of mbar_wait per tag (tag % 32), summed over all threads
 static __device__ unsigned long long g_wait_ns[32];
 static __device__ unsigned long long g_wait_cnt[32];
+// event trace (make trace, -DMSCS_TRACE): lane 0 of selected warps of ONE CTA records (event, tile, clock64)
+#ifdef MSCS_TRACE
+static __device__ unsigned long long g_trace[8192];       // [4 slots][256 tiles][8 events] clock64 values
+#define MSCS_TRACE_EV(slot, k, tile)                                                                 \
+  do {                                                                                               \
+    if (blockIdx.x == 5 && (threadIdx.x & 31) == 0 && (tile) < 256u)                                 \
+      mscs::ptx::g_trace[(slot) * 2048 + (tile) * 8 + (k)] = (unsigned long long)clock64();          \
+  } while (0)
+#else
+#define MSCS_TRACE_EV(slot, k, tile) do { } while (0)
+#endif
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
 static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, uint32_t tag) {
+  // plain retries first: reading %globaltimer costs a few hundred cycles, which showed up as wake-up latency on
+  // every wait that was entered before its barrier completed (try_wait itself suspends the thread in hardware)
+  for (int i = 0; i < 64; ++i)
+    if (mbar_try_wait(bar, parity)) return;
   const unsigned long long t0 = globaltimer_ns();
   while (!mbar_try_wait(bar, parity)) {
     if (globaltimer_ns() - t0 > 2000000000ull) {
@@ -87,6 +102,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
 #else
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(bar, parity, tag);
+#endif
+}
+
+// Low-latency wait for the thread that feeds the tensor pipe: polls with the NON-blocking test_wait.  A thread
+// suspended inside try_wait resumed ~250 cycles after the phase completed (measured, tools/trace_bwd.py) -- longer
+// than the work the pipe has buffered, i.e. a bubble on every tile.  Falls back to the guarded wait.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_spin_wait(uint64_t* bar, uint32_t parity, uint32_t tag) {
+#ifdef MSCS_WAIT_PROFILE
+  mbar_wait(bar, parity, tag);
+#else
+  for (int i = 0; i < 4096; ++i)
+    if (mbar_test_wait(bar, parity)) return;
+  mbar_wait(bar, parity, tag);
 #endif
 }
 
@@ -167,6 +206,22 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+        "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+        "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- UMMA -------------------------------------------------------------------------------
@@ -208,6 +263,31 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Same MMAs with the 64-bit shared-memory descriptors passed as (lo, hi) halves.  The tensor pipe executes a
+// 128 x N x 16 MMA in N/2 cycles, so for N <= 128 the ISSUE code must cost less than that per MMA: with the
+// descriptor of a tile precomputed once, stepping to the next K slice / K block is ONE 32-bit add on `lo`
+// (the start-address field, 16-byte units; all operand offsets here stay below its 256 KB range).
+__device__ __forceinline__ void umma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 bd, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ss2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 ad, {%1, %2};\n\t"
+      "mov.b64 bd, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // make an mbarrier track completion of all previously issued MMAs of this thread
@@ -277,6 +357,18 @@ __device__ __forceinline__ uint64_t ex2_poly2(uint64_t v, uint64_t scale2) {
   p = fma2(p, f, pack2(0.240247443318367f, 0.240247443318367f));
   p = fma2(p, f, pack2(0.6931217908859253f, 0.6931217908859253f));
   p = fma2(p, f, pack2(0.9999992847442627f, 0.9999992847442627f));
+  const uint32_t plo = (uint32_t)p, phi = (uint32_t)(p >> 32), tlo = (uint32_t)t, thi = (uint32_t)(t >> 32);
+  return pack2u(plo + (tlo << 23), phi + (thi << 23));
+}
+// degree-3 variant (max relative error 7.5e-5): for results that are rounded to bf16 anyway (backward W)
+__device__ __forceinline__ uint64_t ex2_poly2_d3(uint64_t v, uint64_t scale2) {
+  const uint64_t magic = pack2(12582912.f, 12582912.f), nmagic = pack2(-12582912.f, -12582912.f);
+  const uint64_t t = fma2(v, scale2, magic);
+  const uint64_t n = add2(t, nmagic);
+  const uint64_t f = fma2(v, scale2, n ^ 0x8000000080000000ull);
+  uint64_t p = fma2(pack2(0.055171653628349304f, 0.055171653628349304f), f, pack2(0.2426111251115799f, 0.2426111251115799f));
+  p = fma2(p, f, pack2(0.6932609677314758f, 0.6932609677314758f));
+  p = fma2(p, f, pack2(0.9999280571937561f, 0.9999280571937561f));
   const uint32_t plo = (uint32_t)p, phi = (uint32_t)(p >> 32), tlo = (uint32_t)t, thi = (uint32_t)(t >> 32);
   return pack2u(plo + (tlo << 23), phi + (thi << 23));
 }

@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(1024) k_build_work(const __grid_constant__ Bui
       }
       ct0 = max(ct0, t.ct_lo); ct1 = max(ct0, min(ct1, t.ct_hi));      // pooled mode: this rank's streamed tiles
       a.items[i] = WorkItem{ti, rb, ct0, ct1};
-      len = ct1 - ct0;
+      len = ct1 > ct0 ? ct1 - ct0 + a.pad : 0;
     }
     int s = len;
 #pragma unroll
@@ -457,7 +457,7 @@ extern "C" int mscs_sim_forward_sweeps(const mscs_sim_job* job, void* stream_) {
     b.prefix = (int*)w;     w += align_up(sizeof(int) * (size_t)(nitems + 1), 64);
     rc = launch_build_work(b, st);
     if (rc) return rc;
-    args.work = WorkTable{b.items, b.prefix, nitems};
+    args.work = WorkTable{b.items, b.prefix, nitems, b.pad};
     switch (job->C_pad / 64) {
       case 1: rc = launch_fwd<1>(args, mode, st); break;
       case 2: rc = launch_fwd<2>(args, mode, st); break;

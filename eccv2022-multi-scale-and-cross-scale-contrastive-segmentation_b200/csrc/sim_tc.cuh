@@ -12,7 +12,10 @@ constexpr int kBlkBytes = 128 * 128; // one [128 rows][64 bf16] operand block = 
 
 // one unit of work = one (row block, column tile); an item is a run of column tiles of one row block
 struct WorkItem { int owner, rb, ct0, ct1; };
-struct WorkTable { const WorkItem* items; const int* prefix; int nitems; };
+// `pad`: virtual units charged to every item on top of its tiles when the work is cut into equal shares -- the
+// fixed cost of starting a run (operand load, pipeline fill, accumulator flush), in tiles.  A CTA whose share is
+// made of many short runs then gets fewer tiles instead of finishing late (sim_bwd: 17% tail before).
+struct WorkTable { const WorkItem* items; const int* prefix; int nitems; int pad; };
 
 struct Segment { int owner, rb, c_begin, c_end; };
 
@@ -30,23 +33,30 @@ struct Walker {
     }
     item = lo;
   }
+  // prefix[] counts pad + tiles per item (items without tiles count 0); the first `pad` virtual units of an
+  // item are its start-up charge and map to no tile
   __device__ bool next(Segment& s) {
-    if (u >= u_end) return false;
-    while (w.prefix[item + 1] <= u) ++item;
-    const WorkItem it = w.items[item];
-    const int base = w.prefix[item];
-    const int e = min(u_end, w.prefix[item + 1]);
-    s.owner = it.owner; s.rb = it.rb;
-    s.c_begin = it.ct0 + (u - base);
-    s.c_end = it.ct0 + (e - base);
-    u = e;
-    return true;
+    while (u < u_end) {
+      while (w.prefix[item + 1] <= u) ++item;
+      const WorkItem it = w.items[item];
+      const int base = w.prefix[item];
+      const int e = min(u_end, w.prefix[item + 1]);
+      const int b0 = max(0, u - base - w.pad), b1 = max(0, e - base - w.pad);
+      u = e;
+      if (b1 > b0) {
+        s.owner = it.owner; s.rb = it.rb;
+        s.c_begin = it.ct0 + b0;
+        s.c_end = it.ct0 + b1;
+        return true;
+      }
+    }
+    return false;
   }
 };
 
 // work-table builder (sim_fwd.cu): one item per (owner, row block)
 struct BuildTerm { const int* a_cls; const int* k_seg; int N1, N2, item_base, blk_lo, ct_lo, ct_hi; };
-struct BuildArgs { BuildTerm t[MSCS_MAX_PASSES]; int num_terms, nitems, rows_per_item, mode; WorkItem* items; int* prefix; };
+struct BuildArgs { BuildTerm t[MSCS_MAX_PASSES]; int num_terms, nitems, rows_per_item, mode, pad; WorkItem* items; int* prefix; };
 int launch_build_work(const BuildArgs& b, cudaStream_t st);
 int trap_buffer_device_ptr(unsigned long long** out);
 // each translation unit with tensor kernels installs the buffer into its own g_trap_buf copy

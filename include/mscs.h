@@ -40,6 +40,9 @@ int mscs_debug_trap_info(char* out, int len);
  * 32 entries indexed by wait tag % 32 (nanoseconds summed over threads, and wait counts) */
 int mscs_debug_wait_profile_fwd(unsigned long long* ns_out, unsigned long long* cnt_out);
 int mscs_debug_wait_profile_bwd(unsigned long long* ns_out, unsigned long long* cnt_out);
+/* debug (library built with -DMSCS_TRACE only, otherwise returns 0): copy out and reset the event trace of
+   the backward tensor kernel -- clock64 values of one CTA, indexed [4 slots][256 tiles][8 events]. */
+int mscs_debug_trace_bwd(unsigned long long* out, int max_events);
 /* 1 if a CUDA device with compute capability 10.x is present */
 int mscs_device_ok(void);
 
