@@ -54,6 +54,12 @@ _SIGNATURES = {
     "mscs_sample_hist": (C.c_int, [C.POINTER(SampleCfg), C.c_void_p, C.c_void_p, C.c_void_p]),
     "mscs_sample_plan_from_counts": (C.c_int, [C.POINTER(SampleCfg), _PTRS, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mscs_plan_fetch": (C.c_int, [C.c_void_p, C.POINTER(ScalePlan), C.c_int, C.c_void_p]),
+    "mscs_plan_fetch_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "mscs_plan_fetch_end": (C.c_int, [C.POINTER(ScalePlan), C.c_int]),
+    "mscs_sample_select_async": (C.c_int, [C.POINTER(SampleCfg), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                           _PTRS, _PTRS, _PTRS, _PTRS, _PTRS, _PTRS, C.c_void_p]),
+    "mscs_gather_normalize_sectors_async": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mscs_mt19937_stream": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]),
     "mscs_sample_select": (C.c_int, [C.POINTER(SampleCfg), C.POINTER(ScalePlan), C.c_void_p, C.c_void_p,
                                      _PTRS, _PTRS, _PTRS, _PTRS, _PTRS, _PTRS, C.c_void_p]),

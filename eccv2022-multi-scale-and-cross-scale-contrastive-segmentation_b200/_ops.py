@@ -21,6 +21,8 @@ _MT_N = 624
 
 # optional per-stage device timing (bench.py): {stage: [(start_event, end_event), ...]} or None
 TIMING = None
+# optional host-side accounting (tools/stage_times.py): seconds the host spent blocked in the plan fetch, per call
+HOST_WAIT = None
 
 
 class _timed:
@@ -40,10 +42,10 @@ class _timed:
 
 
 def LAUNCHES_PER_STEP(num_scales, single_scale):
-    """Kernels of libmscs.so launched by one forward+backward (memsets not counted):
-    K1 hist, tile-scan, plan, MT19937 stream, select; K2 one per scale; K3 2 x (work table + sweep)
-    + finalise; K4 work table + backward; scatter one per scale."""
-    return 5 + num_scales + 6 + 2 + 2 * num_scales      # + slot maps; finalise is two kernels
+    """Kernels of libmscs.so launched by one forward+backward (torch fills not counted; checked against the ncu
+    launch list in profiles/): K1 hist, tile-scan, plan, MT19937 stream, select (5); K2 one per scale; K3 row ranges,
+    2 x (work table + sweep), 2 finalise kernels (7); K4 work table + backward (2); scatter one per scale."""
+    return 5 + num_scales + 7 + 2 + num_scales
 
 
 @dataclass
@@ -525,6 +527,8 @@ class _StepPlan:
         if self.ws_bytes == 0:
             raise RuntimeError("mscs_sample_workspace_bytes: " + lib.mscs_last_error().decode())
         self.max_draws = int(lib.mscs_sample_max_draws(C.byref(cfg)))
+        # upper bound of views per pair (V2.py:64-84): V <= max_views_per_class unless that is 1, and V*T <= max_total
+        self.v_cap = min(spec.max_total, 16384) if spec.max_views == 1 else min(spec.max_views, spec.max_total, 16384)
         self.C = Cc = feat_shapes[0][1]
         for shp in feat_shapes:
             if shp[1] != Cc:
@@ -656,64 +660,95 @@ def run_forward(sp, labels, feats32, needs, comm=None):
         mt, pos = torch_mt_state()
         draws = _stream_cache(dev).acquire(mt, pos, sp.max_draws)
         plan = (_lib.ScalePlan * S)()
-        _lib.check(lib.mscs_plan_fetch(plan_dev.data_ptr(), plan, S, st), "mscs_plan_fetch")     # the host sync
-        # ---- after the sync: three kinds of calls ----
-        for s in range(S):
-            if plan[s].error == 1:   # reference: torch.min() of an empty tensor raises (V2.py:110)
-                raise RuntimeError(f"scale {s}: no (image, class) pair has >= min_views_per_class="
-                                   f"{spec.min_views} pixels (the reference raises here too, V2.py:110)")
-            if plan[s].error == 2:   # reference: 0-d squeeze then .shape[0] raises (V2.py:119-121)
-                raise IndexError(f"scale {s}: a kept class has a single pixel (the reference raises here too)")
-        total = sum(int(plan[s].draws) for s in range(S))
         ibase = islab.data_ptr()
-        if pooled:       # rows of other ranks keep pix = -1 (not gathered / scattered here)
-            for s in range(S):
-                islab[sp.ioff[s][2]:sp.ioff[s][2] + sp.Ncap[s]].fill_(-1)
         arrs = [_lib.ptr_array([ibase + 4 * sp.ioff[s][k] for s in range(S)]) for k in range(5)]
         sarr = _lib.ptr_array([x.data_ptr() if x is not None else 0 for x in slots])
-        _lib.check(lib.mscs_sample_select(C.byref(sp.cfg), plan, ws.data_ptr(), draws.data_ptr(), *arrs, sarr, st),
-                   "mscs_sample_select")
+        fbase, bbase = fslab.data_ptr(), bslab.data_ptr()
+        plan_sz = C.sizeof(_lib.ScalePlan)
+        # the similarity job: every pointer is known from the slab layouts (sized by upper bounds), so it is
+        # filled in BEFORE the host waits for the plan; only the row counts are patched in afterwards
+        job = _lib.SimJob()
+        job.num_terms, job.C_pad, job.num_classes = len(sp.terms), sp.C_pad, A
+        sbase, mbase = stats.data_ptr(), misc.data_ptr()
+        for i, (a, k, self_mask, weight, tau, need_dk) in enumerate(sp.terms):
+            t = job.terms[i]
+            t.a_bf16, t.k_bf16 = bbase + 2 * sp.boff[a], bbase + 2 * sp.boff[k]
+            t.a_cls, t.k_seg = ibase + 4 * sp.ioff[a][3], ibase + 4 * sp.ioff[k][4]
+            t.k_cls, t.a_seg = ibase + 4 * sp.ioff[k][3], ibase + 4 * sp.ioff[a][4]
+            t.self_mask, t.need_dk = int(self_mask), int(need_dk)
+            t.temperature, t.weight, t.a_set, t.k_set = tau, weight, a, k
+            n1 = (sp.Ncap[a] + 15) // 16 * 16
+            t.neg_sum = sbase + 4 * sp.soff[i]
+            t.pos_sum = sbase + 4 * (sp.soff[i] + n1)
+            t.s_sum = sbase + 4 * (sp.soff[i] + 2 * n1)
+            t.coef_s = mbase + 4 * sp.coff[i]
+            t.coef_pn = mbase + 4 * (sp.coff[i] + n1)
+        nt = len(sp.terms)
+        job.term_loss, job.total_loss = mbase + 4 * sp.out_off, mbase + 4 * (sp.out_off + nt)
+        job.work = work.data_ptr()
+        device_driven = not pooled and all(x is not None for x in slots) and sp.v_cap * 12 <= 200 * 1024
+        if device_driven:
+            # Selection and gather are driven by the DEVICE plan records and enqueued before the host looks at the
+            # plan: the one host synchronisation of the forward pass then overlaps ~150 us of GPU work instead of
+            # draining the stream (it used to leave the GPU idle for the sync + the host work after it).
+            _lib.check(lib.mscs_plan_fetch_begin(plan_dev.data_ptr(), S, st), "mscs_plan_fetch_begin")
+            _lib.check(lib.mscs_sample_select_async(C.byref(sp.cfg), plan_dev.data_ptr(), sp.v_cap, ws.data_ptr(),
+                                                    draws.data_ptr(), *arrs, sarr, st), "mscs_sample_select_async")
+    if device_driven:
+        with _timed("gather"):
+            for s in range(S):
+                n, Cc, h, w = sp.feat_shapes[s]
+                _lib.check(lib.mscs_gather_normalize_sectors_async(
+                    feats32[s].data_ptr(), n, Cc, h * w, slots[s].data_ptr(), plan_dev.data_ptr() + s * plan_sz + 8,
+                    bbase + 2 * sp.boff[s], fbase + 4 * sp.foff[s][0], fbase + 4 * sp.foff[s][1], st),
+                    "mscs_gather_normalize_sectors_async")
+        if HOST_WAIT is not None:
+            import time
+            _t0 = time.perf_counter()
+        _lib.check(lib.mscs_plan_fetch_end(plan, S), "mscs_plan_fetch_end")       # the host sync (plan records only)
+        if HOST_WAIT is not None:
+            HOST_WAIT.append(time.perf_counter() - _t0)
+    else:
+        _lib.check(lib.mscs_plan_fetch(plan_dev.data_ptr(), plan, S, st), "mscs_plan_fetch")     # the host sync
+    for s in range(S):
+        if plan[s].error == 1:   # reference: torch.min() of an empty tensor raises (V2.py:110)
+            raise RuntimeError(f"scale {s}: no (image, class) pair has >= min_views_per_class="
+                               f"{spec.min_views} pixels (the reference raises here too, V2.py:110)")
+        if plan[s].error == 2:   # reference: 0-d squeeze then .shape[0] raises (V2.py:119-121)
+            raise IndexError(f"scale {s}: a kept class has a single pixel (the reference raises here too)")
+    total = sum(int(plan[s].draws) for s in range(S))
+    if not device_driven:
+        with _timed("sample"):
+            if pooled:       # rows of other ranks keep pix = -1 (not gathered / scattered here)
+                for s in range(S):
+                    islab[sp.ioff[s][2]:sp.ioff[s][2] + sp.Ncap[s]].fill_(-1)
+            _lib.check(lib.mscs_sample_select(C.byref(sp.cfg), plan, ws.data_ptr(), draws.data_ptr(), *arrs, sarr, st),
+                       "mscs_sample_select")
     samples = [ScaleSample(plan[s].T, plan[s].V, plan[s].N, bool(plan[s].log_flag), plan[s].dl_h, plan[s].dl_w,
                            islab, sp.ioff[s], A) for s in range(S)]
     if pooled:           # class of every row on every rank (disjoint supports: the sum is the union)
         comm.all_reduce(islab[sp.cls_begin:])
-    fbase, bbase = fslab.data_ptr(), bslab.data_ptr()
-    with _timed("gather"):
-        for s in range(S):
-            n, Cc, h, w = sp.feat_shapes[s]
-            if slots[s] is not None:
-                _lib.check(lib.mscs_gather_normalize_sectors(feats32[s].data_ptr(), n, Cc, h * w, slots[s].data_ptr(),
-                                                             samples[s].N, bbase + 2 * sp.boff[s],
-                                                             fbase + 4 * sp.foff[s][0], fbase + 4 * sp.foff[s][1], st),
-                           "mscs_gather_normalize_sectors")
-            else:
-                _lib.check(lib.mscs_gather_normalize(feats32[s].data_ptr(), n, Cc, h * w, samples[s].ptr(2),
-                                                     samples[s].N, bbase + 2 * sp.boff[s], fbase + 4 * sp.foff[s][0],
-                                                     fbase + 4 * sp.foff[s][1], st), "mscs_gather_normalize")
+    if not device_driven:
+        with _timed("gather"):
+            for s in range(S):
+                n, Cc, h, w = sp.feat_shapes[s]
+                if slots[s] is not None:
+                    _lib.check(lib.mscs_gather_normalize_sectors(feats32[s].data_ptr(), n, Cc, h * w, slots[s].data_ptr(),
+                                                                 samples[s].N, bbase + 2 * sp.boff[s],
+                                                                 fbase + 4 * sp.foff[s][0], fbase + 4 * sp.foff[s][1], st),
+                               "mscs_gather_normalize_sectors")
+                else:
+                    _lib.check(lib.mscs_gather_normalize(feats32[s].data_ptr(), n, Cc, h * w, samples[s].ptr(2),
+                                                         samples[s].N, bbase + 2 * sp.boff[s], fbase + 4 * sp.foff[s][0],
+                                                         fbase + 4 * sp.foff[s][1], st), "mscs_gather_normalize")
     if pooled:           # normalised rows of all ranks: all-gather expressed as a sum of disjoint supports
         comm.all_reduce(bslab)
-    job = _lib.SimJob()
-    job.num_terms, job.C_pad, job.num_classes = len(sp.terms), sp.C_pad, A
-    sbase, mbase = stats.data_ptr(), misc.data_ptr()
-    for i, (a, k, self_mask, weight, tau, need_dk) in enumerate(sp.terms):
+    for i, (a, k, *_rest) in enumerate(sp.terms):      # the only plan-dependent fields of the job
         t = job.terms[i]
-        t.a_bf16, t.k_bf16 = bbase + 2 * sp.boff[a], bbase + 2 * sp.boff[k]
-        t.a_cls, t.k_seg = samples[a].ptr(3), samples[k].ptr(4)
-        t.k_cls, t.a_seg = samples[k].ptr(3), samples[a].ptr(4)
-        t.N1, t.N2, t.self_mask, t.need_dk = samples[a].N, samples[k].N, int(self_mask), int(need_dk)
-        t.temperature, t.weight, t.a_set, t.k_set = tau, weight, a, k
+        t.N1, t.N2 = samples[a].N, samples[k].N
         if pooled:       # anchor (and key) rows are sharded over the ranks in 128-row granules
             t.row_begin, t.row_end = shard_rows(samples[a].N, comm.world, comm.rank)
             t.krow_begin, t.krow_end = shard_rows(samples[k].N, comm.world, comm.rank)
-        n1 = (sp.Ncap[a] + 15) // 16 * 16
-        t.neg_sum = sbase + 4 * sp.soff[i]
-        t.pos_sum = sbase + 4 * (sp.soff[i] + n1)
-        t.s_sum = sbase + 4 * (sp.soff[i] + 2 * n1)
-        t.coef_s = mbase + 4 * sp.coff[i]
-        t.coef_pn = mbase + 4 * (sp.coff[i] + n1)
-    nt = len(sp.terms)
-    job.term_loss, job.total_loss = mbase + 4 * sp.out_off, mbase + 4 * (sp.out_off + nt)
-    job.work = work.data_ptr()
     with _timed("sim_fwd"):
         if not pooled:
             _lib.check(lib.mscs_sim_forward(C.byref(job), st), "mscs_sim_forward")

@@ -89,8 +89,16 @@ k_scatter_grad(const float* __restrict__ dF, int ldF, const float* __restrict__ 
 __global__ void __launch_bounds__(256)
 k_gather_sectors(const float* __restrict__ feat, int C, int C_pad, int plane, const int* __restrict__ slot,
                  int n_octets, __nv_bfloat16* __restrict__ anc_bf16, float* __restrict__ anc_f32,
-                 float* __restrict__ inv_norm) {
+                 float* __restrict__ inv_norm, const int* __restrict__ n_rows_dev) {
   const int lane = threadIdx.x & 31;
+  if (n_rows_dev != nullptr && blockIdx.x == gridDim.x - 1) {
+    // device-driven call: the row count is only known on the device; this (extra) block zeroes the padding
+    // rows [N, N_pad) of the operand matrix that the TMA tiles read
+    const int N = *n_rows_dev, N_pad = (N + 255) / 256 * 256;
+    uint32_t* z = reinterpret_cast<uint32_t*>(anc_bf16 + (size_t)N * C_pad);
+    for (int i = threadIdx.x; i < (N_pad - N) * (C_pad / 2); i += blockDim.x) z[i] = 0u;
+    return;
+  }
   const int oct = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (oct >= n_octets) return;
   const int gp = oct * 8;
@@ -199,7 +207,24 @@ extern "C" int mscs_gather_normalize_sectors(const float* feat, int n, int C, in
                               sizeof(__nv_bfloat16) * (size_t)(N_pad - N) * C_pad, st));
   const int n_oct = n * (plane / 8);
   k_gather_sectors<<<ceil_div(n_oct, 8), 256, 0, st>>>(feat, C, C_pad, plane, slot, n_oct, (__nv_bfloat16*)anc_bf16,
-                                                       anc_f32, inv_norm);
+                                                       anc_f32, inv_norm, nullptr);
+  MSCS_LAUNCH_CHECK();
+  return 0;
+}
+
+// Same, with the number of sampled rows read from device memory (`n_rows_dev`, e.g. &plan_dev[s].N): no host
+// knowledge of the sampling result is needed to enqueue it.
+extern "C" int mscs_gather_normalize_sectors_async(const float* feat, int n, int C, int plane, const int32_t* slot,
+                                                   const int32_t* n_rows_dev, void* anc_bf16, float* anc_f32,
+                                                   float* inv_norm, void* stream_) {
+  MSCS_CHECK_ARG(feat && slot && n_rows_dev && anc_bf16 && anc_f32 && inv_norm, "null pointer argument");
+  MSCS_CHECK_ARG(C >= 1 && C <= kMaxC, "C=%d unsupported (1..%d)", C, kMaxC);
+  MSCS_CHECK_ARG(n >= 1 && plane >= 8 && plane % 8 == 0, "bad sizes (plane must be a multiple of 8)");
+  cudaStream_t st = (cudaStream_t)stream_;
+  const int C_pad = (C + 63) / 64 * 64;
+  const int n_oct = n * (plane / 8);
+  k_gather_sectors<<<ceil_div(n_oct, 8) + 1, 256, 0, st>>>(feat, C, C_pad, plane, slot, n_oct, (__nv_bfloat16*)anc_bf16,
+                                                           anc_f32, inv_norm, n_rows_dev);
   MSCS_LAUNCH_CHECK();
   return 0;
 }

@@ -348,22 +348,32 @@ struct SelectArgs {
   int* cls[MSCS_MAX_SCALES];
   int* seg[MSCS_MAX_SCALES];
   int* slot[MSCS_MAX_SCALES];     // optional pixel -> sorted row map (pre-filled with -1 by the caller)
+  const mscs_scale_plan* plan_dev; // non-null: T, V and the draw offsets are read from the device plan records
+                                   // (the launch then does not wait for the host to have fetched the plan)
 };
 
 __global__ void __launch_bounds__(256)
 k_fy_select(const __grid_constant__ SampleLayout L, const __grid_constant__ SelectArgs a, char* ws,
             const uint32_t* __restrict__ draws) {
   const int s = blockIdx.y, k = blockIdx.x;
-  if (k >= a.T[s]) return;
+  int T_s = a.T[s], V_s = a.V[s];
+  long long base_s = a.draw_base[s];
+  if (a.plan_dev != nullptr) {
+    if (a.plan_dev[s].error != 0) return;
+    T_s = a.plan_dev[s].T; V_s = a.plan_dev[s].V;
+    base_s = 0;
+    for (int q = 0; q < s; ++q) base_s += a.plan_dev[q].draws;
+  }
+  if (k >= T_s) return;
   const ScaleGeo& g = L.g[s];
-  const int V = a.V[s], A = L.A;
+  const int V = V_s, A = L.A;
   PairArrays pa = pair_arrays(ws, g);
   if (k == 0)                                   // class segments: identical on every rank
     for (int i = threadIdx.x; i <= A; i += blockDim.x) a.seg[s][i] = reinterpret_cast<const int*>(ws + g.off_seg)[i];
   const int bg = pa.b[k], c = pa.c[k], cnt = pa.cnt[k], dst = pa.dst[k];
   const int b = bg - L.b0;                      // local image index; other ranks' pairs are skipped
   if (b < 0 || b >= L.n) return;
-  const uint32_t* u = draws + a.draw_base[s] + pa.off[k];
+  const uint32_t* u = draws + base_s + pa.off[k];
   extern __shared__ int sm[];
   int* t_arr = sm;            // t_i = i + z_i : position swapped with i at step i
   int* w_arr = sm + V;        // w_arr[p] = latest step j < p that wrote position p (t_j == p), or -1
@@ -538,6 +548,7 @@ extern "C" int mscs_sample_select(const mscs_sample_cfg* cfg, const mscs_scale_p
   MSCS_CHECK_ARG(plan_host && workspace && draws_dev, "null pointer argument");
   cudaStream_t st = (cudaStream_t)stream_;
   SelectArgs a;
+  a.plan_dev = nullptr;
   int maxT = 0, maxV = 0;
   for (int s = 0; s < L.S; ++s) {
     MSCS_CHECK_ARG(plan_host[s].error == 0, "scale %d: sampling plan reports error %d", s, plan_host[s].error);
@@ -555,6 +566,64 @@ extern "C" int mscs_sample_select(const mscs_sample_cfg* cfg, const mscs_scale_p
   dim3 grid(maxT, L.S);
   k_fy_select<<<grid, 256, smem, st>>>(L, a, (char*)workspace, draws_dev);
   MSCS_LAUNCH_CHECK();
+  return 0;
+}
+
+// Selection driven by the DEVICE plan records: can be enqueued before the host has seen the plan, so the one
+// host synchronisation of the forward pass overlaps this kernel and the gather instead of idling the GPU.
+// Grid and shared memory are sized by the configuration's upper bounds (pairs: n_global (A-1); views: v_cap).
+extern "C" int mscs_sample_select_async(const mscs_sample_cfg* cfg, const mscs_scale_plan* plan_dev, int v_cap,
+                                        void* workspace, const uint32_t* draws_dev, int32_t* const* idx_ref,
+                                        int32_t* const* pair_ref, int32_t* const* pix, int32_t* const* cls,
+                                        int32_t* const* seg, int32_t* const* slot, void* stream_) {
+  SampleLayout L;
+  int rc = make_layout(cfg, &L);
+  if (rc) return rc;
+  MSCS_CHECK_ARG(plan_dev && workspace && draws_dev, "null pointer argument");
+  MSCS_CHECK_ARG(v_cap >= 1 && v_cap <= kMaxV, "view bound %d outside 1..%d", v_cap, kMaxV);
+  cudaStream_t st = (cudaStream_t)stream_;
+  SelectArgs a;
+  a.plan_dev = plan_dev;
+  for (int s = 0; s < L.S; ++s) {
+    a.draw_base[s] = 0; a.T[s] = 0; a.V[s] = 0;
+    a.idx_ref[s] = idx_ref[s]; a.pair_ref[s] = pair_ref[s]; a.pix[s] = pix[s]; a.cls[s] = cls[s]; a.seg[s] = seg[s];
+    a.slot[s] = slot ? slot[s] : nullptr;
+  }
+  const int n_glob = cfg->n_global > 0 ? cfg->n_global : cfg->n;
+  const int t_cap = n_glob * (cfg->num_classes - 1);
+  size_t smem = sizeof(int) * 3 * (size_t)v_cap;
+  if (smem > 48 * 1024)
+    MSCS_CUDA(cudaFuncSetAttribute(k_fy_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(t_cap, L.S);
+  k_fy_select<<<grid, 256, smem, st>>>(L, a, (char*)workspace, draws_dev);
+  MSCS_LAUNCH_CHECK();
+  return 0;
+}
+
+// Split plan fetch: begin = async D2H into a pinned staging buffer + event; end = wait for that event only
+// (work enqueued after begin keeps running) and hand the records out.
+static thread_local mscs_scale_plan* t_plan_pinned = nullptr;
+static thread_local cudaEvent_t t_plan_event = nullptr;
+extern "C" int mscs_plan_fetch_begin(const mscs_scale_plan* plan_dev, int num_scales, void* stream_) {
+  MSCS_CHECK_ARG(plan_dev && num_scales >= 1 && num_scales <= MSCS_MAX_SCALES, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (!t_plan_pinned) {
+    MSCS_CUDA(cudaHostAlloc((void**)&t_plan_pinned, sizeof(mscs_scale_plan) * MSCS_MAX_SCALES, cudaHostAllocDefault));
+    MSCS_CUDA(cudaEventCreateWithFlags(&t_plan_event, cudaEventDisableTiming));
+  }
+  MSCS_CUDA(cudaMemcpyAsync(t_plan_pinned, plan_dev, sizeof(mscs_scale_plan) * num_scales, cudaMemcpyDeviceToHost, st));
+  MSCS_CUDA(cudaEventRecord(t_plan_event, st));
+  return 0;
+}
+extern "C" int mscs_plan_fetch_end(mscs_scale_plan* plan_host, int num_scales) {
+  MSCS_CHECK_ARG(plan_host && num_scales >= 1 && num_scales <= MSCS_MAX_SCALES, "bad arguments");
+  MSCS_CHECK_ARG(t_plan_pinned != nullptr, "mscs_plan_fetch_end without mscs_plan_fetch_begin on this thread");
+  MSCS_CUDA(cudaEventSynchronize(t_plan_event));
+  long long base = 0;
+  for (int s = 0; s < num_scales; ++s) {
+    plan_host[s] = t_plan_pinned[s];
+    plan_host[s].draw_base = base; base += plan_host[s].draws;
+  }
   return 0;
 }
 

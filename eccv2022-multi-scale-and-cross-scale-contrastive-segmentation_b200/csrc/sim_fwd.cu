@@ -216,11 +216,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
                   acc3 += __uint_as_float(cur[c + 3]) * scale;
                 }
               } else if (fast) {
-                const int pm = (args.debug_flags >> 4) & 3;      // experiment: share of exps on the FMA pipe
-                if (pm == 0) fast_chunk<0x00>(cur, scale, acc0, acc1, acc2, acc3);
-                else if (pm == 1) fast_chunk<0x88>(cur, scale, acc0, acc1, acc2, acc3);
-                else if (pm == 2) fast_chunk<0x92>(cur, scale, acc0, acc1, acc2, acc3);
-                else fast_chunk<0xAA>(cur, scale, acc0, acc1, acc2, acc3);
+                // a quarter of the exponentials on the FMA pipe (degree-4 polynomial, 2.7e-6 relative): measured
+                // best of {0, 1/4, 3/8, 1/2}; MSCS_DEBUG_FLAGS=16 selects the MUFU-only variant for comparison
+                if (args.debug_flags & 16) fast_chunk<0x00>(cur, scale, acc0, acc1, acc2, acc3);
+                else fast_chunk<0x88>(cur, scale, acc0, acc1, acc2, acc3);
               } else if (c0 < t.N2) {
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
@@ -451,6 +450,8 @@ extern "C" int mscs_sim_forward_sweeps(const mscs_sim_job* job, void* stream_) {
   k_row_ranges<<<dim3(ceil_div(maxN1 + 127, 256), job->num_terms), 256, 0, st>>>(ra);
   MSCS_LAUNCH_CHECK();
   b.num_terms = job->num_terms; b.nitems = nitems; b.rows_per_item = kFwdKeys;
+  b.pad = 0;      // start-up charge of a key block (128 KB load + pipeline fill), in anchor tiles
+  if (const char* e = getenv("MSCS_FWD_PAD")) b.pad = atoi(e);
   for (int mode = 0; mode < 2; ++mode) {
     b.mode = mode;
     b.items = (WorkItem*)w; w += align_up(sizeof(WorkItem) * (size_t)nitems, 64);

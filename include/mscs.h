@@ -101,6 +101,11 @@ int mscs_sample_plan_from_counts(const mscs_sample_cfg* cfg, const int32_t* cons
  * the reference has ~1000). */
 int mscs_plan_fetch(const mscs_scale_plan* plan_dev, mscs_scale_plan* plan_host, int num_scales,
                     void* stream);
+/* The same fetch split in two, so that work enqueued in between overlaps the host wait: begin = async copy into a
+ * pinned staging buffer + event record on `stream`; end = wait for that event only, then hand the records out.
+ * (One outstanding fetch per host thread.) */
+int mscs_plan_fetch_begin(const mscs_scale_plan* plan_dev, int num_scales, void* stream);
+int mscs_plan_fetch_end(mscs_scale_plan* plan_host, int num_scales);
 /* MT19937 stream (async): `n_words` consecutive UNTEMPERED state words (the consumer applies the
  * tempering) of the generator whose state is
  * (mt_state_host[624], mt_pos in 0..624) -- the torch CPU default generator, which the reference
@@ -123,6 +128,12 @@ int mscs_sample_select(const mscs_sample_cfg* cfg, const mscs_scale_plan* plan_h
                        const uint32_t* draws_dev, int32_t* const* idx_ref, int32_t* const* pair_ref,
                        int32_t* const* pix, int32_t* const* cls, int32_t* const* seg, int32_t* const* slot,
                        void* stream);
+/* Selection driven by the DEVICE plan records (T, V, draw offsets read in the kernel): can be enqueued before the
+ * host has fetched the plan.  `v_cap`: upper bound of views per pair for this configuration (sizes shared memory). */
+int mscs_sample_select_async(const mscs_sample_cfg* cfg, const mscs_scale_plan* plan_dev, int v_cap, void* workspace,
+                             const uint32_t* draws_dev, int32_t* const* idx_ref, int32_t* const* pair_ref,
+                             int32_t* const* pix, int32_t* const* cls, int32_t* const* seg, int32_t* const* slot,
+                             void* stream);
 /* host helper: advance an MT19937 state by k draws exactly as at::mt19937 does */
 int mscs_mt19937_advance_host(uint32_t* mt_state_host, int* mt_pos, uint64_t k);
 
@@ -141,6 +152,10 @@ int mscs_gather_normalize(const float* feat, int n, int C, int plane, const int3
  * reads inside open DRAM pages; needs plane % 8 == 0 */
 int mscs_gather_normalize_sectors(const float* feat, int n, int C, int plane, const int32_t* slot, int N,
                                   void* anc_bf16, float* anc_f32, float* inv_norm, void* stream);
+/* Same with the row count read from device memory (e.g. &plan_dev[s].N); also zeroes the padding rows. */
+int mscs_gather_normalize_sectors_async(const float* feat, int n, int C, int plane, const int32_t* slot,
+                                        const int32_t* n_rows_dev, void* anc_bf16, float* anc_f32, float* inv_norm,
+                                        void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * K3 / K4 -- fused similarity + loss forward and backward for every term of one call.

@@ -8,7 +8,7 @@ echo "bench exit $?"; tail -c 3500 gpurun_out/bench.json; tail -5 gpurun_out/ben
 timeout -s KILL 400 ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 60 --csv \
   --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 echo "ncu launches exit $?"
-timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:k_sim_ -s 12 -c 3 \
+timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:"k_sim_|k_gather|k_scatter|k_fy_select|k_label_hist" -s 40 -c 14 \
   -o gpurun_out/prof_sim python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 echo "ncu full exit $?"
 ls -la gpurun_out
