@@ -455,6 +455,16 @@ class TorchDistComm:
         self.dist.all_gather_into_tensor(out, t.reshape(-1), group=self.group)
         return out
 
+    def all_reduce_async(self, t):
+        """Returns a handle whose wait() orders the current stream after the collective."""
+        return self.dist.all_reduce(t, group=self.group, async_op=True)
+
+    def all_gather_blocks_async(self, buf, per):
+        """In place: block r (buf[r*per:(r+1)*per]) is valid on rank r; afterwards all `world` blocks are valid
+        everywhere.  Half the volume of the all-reduce that would do the same job on zero-initialised buffers."""
+        return self.dist.all_gather_into_tensor(buf[:self.world * per], buf[self.rank * per:(self.rank + 1) * per],
+                                                group=self.group, async_op=True)
+
 
 class ThreadComm:
     """In-process emulation of `world` ranks on ONE device (one Python thread per rank, lock-step
@@ -489,6 +499,20 @@ class ThreadComm:
 
     def all_gather(self, t):
         return self._exchange(t, lambda ts: torch.cat([x.reshape(-1) for x in ts])).clone()
+
+    class _Done:
+        def wait(self):
+            pass
+
+    def all_reduce_async(self, t):
+        self.all_reduce(t)
+        return ThreadComm._Done()
+
+    def all_gather_blocks_async(self, buf, per):
+        mine = buf[self.rank * per:(self.rank + 1) * per]
+        res = self._exchange(mine, lambda ts: torch.cat([x.reshape(-1).clone() for x in ts]))
+        buf[:self.world * per].copy_(res)
+        return ThreadComm._Done()
 
 
 def shard_rows(N, world, rank):
@@ -595,7 +619,7 @@ class _StepPlan:
         self.dF_off, off = [], 0
         for s in range(S):
             self.dF_off.append(off)
-            off += self.Ncap[s] * self.C_pad
+            off += (self.Ncap[s] + 128 * world) * self.C_pad      # slack: `world` 128-aligned row blocks (pooled mode)
         self.dF_n = off
 
 
@@ -742,7 +766,7 @@ def run_forward(sp, labels, feats32, needs, comm=None):
                                                          samples[s].N, bbase + 2 * sp.boff[s], fbase + 4 * sp.foff[s][0],
                                                          fbase + 4 * sp.foff[s][1], st), "mscs_gather_normalize")
     if pooled:           # normalised rows of all ranks: all-gather expressed as a sum of disjoint supports
-        comm.all_reduce(bslab)
+        comm.all_reduce(bslab)      # (one collective: per-scale pieces measured no faster at 2 GPUs)
     for i, (a, k, *_rest) in enumerate(sp.terms):      # the only plan-dependent fields of the job
         t = job.terms[i]
         t.N1, t.N2 = samples[a].N, samples[k].N
@@ -784,8 +808,17 @@ def run_backward(state, grad_out, needs, shapes, dtypes):
     with _timed("sim_bwd"):
         _lib.check(lib.mscs_sim_backward(C.byref(state.job), g.data_ptr(), _lib.ptr_array(ptrs), lds, st),
                    "mscs_sim_backward")
-    if state.comm is not None:      # every rank computed the rows of its range; owners need their rows
-        state.comm.all_reduce(dF)
+    handles = [None] * S
+    if state.comm is not None:
+        # every rank computed the COMPLETE gradient rows of its 128-aligned row block of every set; the owners of
+        # the pixels need them: all-gather of the blocks (in place), one per set so that the scatter of set s
+        # overlaps the exchange of set s+1
+        comm = state.comm
+        for s in range(S):
+            N = state.samples[s].N
+            per = ((N + 127) // 128 + comm.world - 1) // comm.world * 128
+            rows = dF[sp.dF_off[s]:sp.dF_off[s] + comm.world * per * sp.C_pad]
+            handles[s] = comm.all_gather_blocks_async(rows, per * sp.C_pad)
     grads = []
     fbase = state.fslab.data_ptr()
     with _timed("scatter"):
@@ -798,6 +831,8 @@ def run_backward(state, grad_out, needs, shapes, dtypes):
                 continue
             n, Cc, h, w = shapes[s]
             smp = state.samples[s]
+            if handles[s] is not None:
+                handles[s].wait()
             pre, slot = (gb.take(s) if gb is not None else None), state.slots[s]
             if pre is not None and slot is not None:
                 out = pre
