@@ -340,7 +340,7 @@ def build_job(spec, samples, sets, single_scale):
     n_rows = [sets[a].N for a, *_ in terms]
     stats = torch.zeros(3 * sum(n_rows), dtype=torch.float32, device=dev)
     coefs = torch.empty(2 * sum(n_rows), dtype=torch.float32, device=dev)
-    out = torch.empty(len(terms) + 1, dtype=torch.float32, device=dev)
+    out = torch.empty(len(terms) + 2, dtype=torch.float32, device=dev)      # term losses, total, inf/NaN flag
     job = _lib.SimJob()
     job.num_terms, job.C_pad, job.num_classes = len(terms), sets[0].C_pad, spec.num_classes
     so = co = 0
@@ -421,7 +421,12 @@ class _GradBuffers:
                 self.bufs.append(None)
                 continue
             self.bufs.append(torch.empty(f.shape, dtype=torch.float32, device=dev))
-        side.wait_stream(main)
+        self.side, self.ready = side, None
+
+    def start_fill(self):
+        """Zero-fill on the side stream, ordered after what the main stream has enqueued so far."""
+        side = self.side
+        side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for b in self.bufs:
                 if b is not None:
@@ -607,7 +612,7 @@ class _StepPlan:
             self.coff.append(off)
             off += 2 * al(self.Ncap[a])
         self.out_off = off
-        self.misc_n = off + al(len(terms) + 1)
+        self.misc_n = off + al(len(terms) + 2)      # term losses, total, inf/NaN flag
         job = _lib.SimJob()
         job.num_terms, job.C_pad, job.num_classes = len(terms), self.C_pad, A
         for i, (a, k, self_mask, weight, tau, need_dk) in enumerate(terms):
@@ -673,6 +678,8 @@ def run_forward(sp, labels, feats32, needs, comm=None):
         misc = torch.empty(sp.misc_n, dtype=f32, device=dev)
         work = torch.empty(sp.work_bytes, dtype=u8, device=dev)
         gradbufs = _GradBuffers(feats32, needs) if any(needs) else None
+        if gradbufs is not None:      # (started here: overlapping the tensor kernels instead measured slower -- the
+            gradbufs.start_fill()     # fill's CTAs share the SMs with the persistent kernel's epilogue warps)
         # pixel -> row maps (filled by the selection kernel): drive the address-ordered gather and the
         # sector scatter of the backward
         sizes = [shp[0] * shp[2] * shp[3] if (shp[2] * shp[3]) % 8 == 0 else 0 for shp in sp.feat_shapes]
@@ -766,7 +773,7 @@ def run_forward(sp, labels, feats32, needs, comm=None):
                                                          samples[s].N, bbase + 2 * sp.boff[s], fbase + 4 * sp.foff[s][0],
                                                          fbase + 4 * sp.foff[s][1], st), "mscs_gather_normalize")
     if pooled:           # normalised rows of all ranks: all-gather expressed as a sum of disjoint supports
-        comm.all_reduce(bslab)      # (one collective: per-scale pieces measured no faster at 2 GPUs)
+        comm.all_reduce(bslab)
     for i, (a, k, *_rest) in enumerate(sp.terms):      # the only plan-dependent fields of the job
         t = job.terms[i]
         t.N1, t.N2 = samples[a].N, samples[k].N
@@ -789,6 +796,7 @@ def run_forward(sp, labels, feats32, needs, comm=None):
     state.keep = (ws, islab, fslab, bslab, stats, misc, work)
     state.fslab, state.term_loss = fslab, misc[sp.out_off:sp.out_off + nt]
     state.total = misc[sp.out_off + nt]
+    state.scalars = misc[sp.out_off:sp.out_off + nt + 2]      # [term losses..., total, inf/NaN flag]: one copy for the logger
     state.num_ms, state.cs_logged, state.comm = S, sp.cs_logged, comm if pooled else None
     return state
 

@@ -52,12 +52,17 @@ __global__ void __launch_bounds__(256) k_finalize_rows(const __grid_constant__ F
 __global__ void k_finalize_total(const __grid_constant__ FinArgs a, const double* acc) {
   if (threadIdx.x != 0) return;
   double total = 0.0;
+  bool bad = false;
   for (int ti = 0; ti < a.num_terms; ++ti) {
     const float l = (float)(acc[ti] / (double)a.t[ti].N1);
     a.term_loss[ti] = l;
+    bad = bad || !isfinite(l);
     total += (double)a.t[ti].weight * (double)l;
   }
-  *a.total_loss = (float)total;
+  a.total_loss[0] = (float)total;
+  // device-side replacement of the logger's has_inf_or_nan(loss) host check (utils.py / LoggingManager.py:190):
+  // one flag next to the scalars, fetched together with them in a single copy
+  a.total_loss[1] = (bad || !isfinite((float)total)) ? 1.f : 0.f;
 }
 
 // job->work: the first 4096 bytes are reserved for these accumulators (zeroed by the forward launcher)

@@ -71,6 +71,7 @@ class DenseContrastiveLossV2(nn.Module):
         self._scale = int(label.shape[-1] // features.shape[-1])                         # V2.py:46,203
         if smp.log_flag:
             self.log_this_step = True                                                    # V2.py:75,83
+        self.nan_flag = holder["state"].scalars[-1]      # 0-d device tensor: 1.0 if the loss is inf/NaN (no sync)
         if self.cross_scale_contrast:
             n, c = features.shape[:2]
             flat = features.reshape(n, c, -1)
@@ -78,6 +79,10 @@ class DenseContrastiveLossV2(nn.Module):
             sampled = flat[img[:, None], :, smp.idx_ref.long()].permute(0, 2, 1)          # (T, C, V)
             return total, sampled, smp.pair_ref[:, 1].float(), False
         return total
+
+    def fetch_logged(self):
+        """Scalars of the last call for the logger with a single device->host copy (see the _ms class)."""
+        return _fetch_logged(self, self.last_state, 1, [])
 
 
 class DenseContrastiveLossV2_ms(nn.Module):
@@ -121,9 +126,25 @@ class DenseContrastiveLossV2_ms(nn.Module):
         self.last_samples, self.last_state = holder["samples"], state
         self.ms_losses = [terms[s] for s in range(state.num_ms)]
         self.cs_losses = [terms[i] for i in state.cs_logged]
+        self.nan_flag = state.scalars[-1]                # 0-d device tensor: 1.0 if the loss is inf/NaN (no sync)
         if any(s.log_flag for s in holder["samples"]):
             self.log_this_step = True
         return total
+
+    def fetch_logged(self):
+        """Scalars of the last call for the logger -- total, ms_losses, cs_losses (unweighted, as the reference logs
+        them) and the inf/NaN flag -- with a single device->host copy."""
+        st = self.last_state
+        return _fetch_logged(self, st, st.num_ms, st.cs_logged)
+
+
+def _fetch_logged(module, state, num_ms, cs_logged):
+    """Everything the reference's logger reads per step, in ONE device->host copy (the reference does one
+    ``.item()`` per scalar plus ``has_inf_or_nan`` = 4+ syncs per step, LoggingManager.py:179-196)."""
+    v = state.scalars.detach().cpu().tolist()
+    nt = len(v) - 2
+    return {"total": v[nt], "ms_losses": v[:num_ms], "cs_losses": [v[i] for i in cs_logged],
+            "has_inf_or_nan": v[nt + 1] != 0.0, "log_this_step": bool(module.log_this_step)}
 
 
 def install_into_reference():

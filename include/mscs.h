@@ -192,7 +192,8 @@ typedef struct {
   int32_t num_classes;
   mscs_term terms[MSCS_MAX_TERMS];
   float* term_loss;   /* out: num_terms floats, unweighted per-term losses (ms_losses/cs_losses) */
-  float* total_loss;  /* out: 1 float = sum_t weight_t * term_loss_t                  */
+  float* total_loss;  /* out: 2 floats: [0] = sum_t weight_t * term_loss_t; [1] = 1.0 if any term or the
+                         total is inf/NaN else 0.0 (device-side has_inf_or_nan, LoggingManager.py:190) */
   void* work;         /* scratch, mscs_sim_workspace_bytes() */
 } mscs_sim_job;
 

@@ -468,3 +468,32 @@ def test_second_backward_and_half_inputs(dev):
     torch.manual_seed(1)
     mod(labels, fh).backward()
     assert fh.grad.dtype == torch.float16 and torch.isfinite(fh.grad).all()
+
+
+@pytest.mark.gpu
+def test_fetch_logged_single_copy_and_nan_flag(dev):
+    """the scalars the reference logger reads (LoggingManager.py:179-196) come back in one
+    copy and agree with the per-tensor values; the device-side inf/NaN flag replaces has_inf_or_nan()."""
+    import mscs_b200
+    from mscs_b200 import synth
+    cfg = dict(dataset="CITYSCAPES", experiment=1, temperature=0.1, scales=3, weights=[1.0, 0.7, 0.4],
+               cross_scale_contrast=True, min_views_per_class=5, max_views_per_class=40, max_features_total=600)
+    labels = synth.synth_labels(2, 128, 256, 19, 6, 16, 0.05, 1)
+    feats = synth.synth_features(2, 128, 128, 256, [4, 8, 16], 2)
+    mod = mscs_b200.DenseContrastiveLossV2_ms(cfg)
+    torch.manual_seed(0)
+    loss = mod(labels.to(dev), [f.to(dev) for f in feats])
+    got = mod.fetch_logged()
+    assert got["total"] == float(loss)
+    assert got["ms_losses"] == [float(x) for x in mod.ms_losses]
+    assert got["cs_losses"] == [float(x) for x in mod.cs_losses]
+    assert got["has_inf_or_nan"] is False and float(mod.nan_flag) == 0.0
+    # the reference total: sum_s w_s ms_s + w_high_low cs(0,S-1) + w_high_mid cs(0,S-2)   (_ms.py:54,72,79)
+    want = sum(w * l for w, l in zip(cfg["weights"], got["ms_losses"])) + sum(got["cs_losses"])
+    assert abs(want - got["total"]) < 1e-5 * abs(want)
+    bad = [f.clone() for f in feats]
+    bad[1][0] = float("nan")          # every pixel of image 0 at scale 1: some of them are sampled
+    torch.manual_seed(0)
+    loss = mod(labels.to(dev), [f.to(dev) for f in bad])
+    got = mod.fetch_logged()
+    assert got["has_inf_or_nan"] is True and float(mod.nan_flag) == 1.0
