@@ -772,7 +772,10 @@ def run_forward(sp, labels, feats32, needs, comm=None):
                     _lib.check(lib.mscs_gather_normalize(feats32[s].data_ptr(), n, Cc, h * w, samples[s].ptr(2),
                                                          samples[s].N, bbase + 2 * sp.boff[s], fbase + 4 * sp.foff[s][0],
                                                          fbase + 4 * sp.foff[s][1], st), "mscs_gather_normalize")
-    if pooled:           # normalised rows of all ranks: all-gather expressed as a sum of disjoint supports
+    if pooled:
+        # normalised rows of all ranks: all-gather expressed as a sum of disjoint supports (the slab is
+        # zero-initialised).  One collective: per-scale asynchronous pieces overlapping the gather measured much
+        # slower at 2 GPUs (17.1 vs 13.2 ms per step).
         comm.all_reduce(bslab)
     for i, (a, k, *_rest) in enumerate(sp.terms):      # the only plan-dependent fields of the job
         t = job.terms[i]
@@ -813,20 +816,26 @@ def run_backward(state, grad_out, needs, shapes, dtypes):
     for s in range(S):
         ptrs[s], lds[s] = base + 4 * sp.dF_off[s], sp.C_pad
     g = grad_out.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
-    with _timed("sim_bwd"):
-        _lib.check(lib.mscs_sim_backward(C.byref(state.job), g.data_ptr(), _lib.ptr_array(ptrs), lds, st),
-                   "mscs_sim_backward")
     handles = [None] * S
-    if state.comm is not None:
-        # every rank computed the COMPLETE gradient rows of its 128-aligned row block of every set; the owners of
-        # the pixels need them: all-gather of the blocks (in place), one per set so that the scatter of set s
-        # overlaps the exchange of set s+1
-        comm = state.comm
-        for s in range(S):
-            N = state.samples[s].N
-            per = ((N + 127) // 128 + comm.world - 1) // comm.world * 128
-            rows = dF[sp.dF_off[s]:sp.dF_off[s] + comm.world * per * sp.C_pad]
-            handles[s] = comm.all_gather_blocks_async(rows, per * sp.C_pad)
+    with _timed("sim_bwd"):
+        if state.comm is None:
+            _lib.check(lib.mscs_sim_backward(C.byref(state.job), g.data_ptr(), _lib.ptr_array(ptrs), lds, st),
+                       "mscs_sim_backward")
+        else:
+            # Pooled mode.  Every rank computes the COMPLETE gradient rows of its 128-aligned row block of every set;
+            # the owners of the pixels need them: all-gather of the blocks (in place).  The backward is launched set
+            # by set (largest first) and each set's exchange starts as soon as its launch is enqueued, so it overlaps
+            # the tensor work of the following sets; the scatter of a set waits for its own exchange only.
+            comm = state.comm
+            order = sorted(range(S), key=lambda s_: -state.samples[s_].N)
+            pa = _lib.ptr_array(ptrs)
+            for s in order:
+                _lib.check(lib.mscs_sim_backward_sets(C.byref(state.job), g.data_ptr(), pa, lds, 1 << s, st),
+                           "mscs_sim_backward_sets")
+                N = state.samples[s].N
+                per = ((N + 127) // 128 + comm.world - 1) // comm.world * 128
+                rows = dF[sp.dF_off[s]:sp.dF_off[s] + comm.world * per * sp.C_pad]
+                handles[s] = comm.all_gather_blocks_async(rows, per * sp.C_pad)
     grads = []
     fbase = state.fslab.data_ptr()
     with _timed("scatter"):

@@ -418,12 +418,26 @@ static int launch_bwd(const BwdArgs& args, cudaStream_t st) {
 
 extern "C" int mscs_sim_backward(const mscs_sim_job* job, const float* grad_out, float* const* dF_sets,
                                  const int32_t* dF_ld, void* stream_) {
+  return mscs_sim_backward_sets(job, grad_out, dF_sets, dF_ld, 0xffffffffu, stream_);
+}
+
+// Only the passes whose ROW set is in `set_mask` (bit s = anchor set s): the pooled mode launches the backward
+// set by set so that the exchange of one set's gradient rows overlaps the tensor work of the next.
+extern "C" int mscs_sim_backward_sets(const mscs_sim_job* job, const float* grad_out, float* const* dF_sets,
+                                      const int32_t* dF_ld, uint32_t set_mask, void* stream_) {
   int rc = validate_job(job);
   if (rc) return rc;
   MSCS_CHECK_ARG(job->work && grad_out && dF_sets && dF_ld, "null pointer argument");
   cudaStream_t st = (cudaStream_t)stream_;
   BwdPass passes[MSCS_MAX_PASSES];
-  const int np = build_passes(job, passes);
+  int np = build_passes(job, passes);
+  {
+    int kept = 0;
+    for (int i = 0; i < np; ++i)
+      if ((set_mask >> passes[i].row_set) & 1u) passes[kept++] = passes[i];
+    np = kept;
+    if (np == 0) return 0;
+  }
   // the backward work tables live after the two forward tables in job->work
   size_t fwd_items = 0, ranges = 0;
   for (int t = 0; t < job->num_terms; ++t) {

@@ -208,6 +208,10 @@ int mscs_sim_finalize(const mscs_sim_job* job, void* stream);
  * set; the caller zero-initialises dF.  grad_out is a device scalar (upstream gradient). */
 int mscs_sim_backward(const mscs_sim_job* job, const float* grad_out, float* const* dF_sets,
                       const int32_t* dF_ld, void* stream);
+/* the same restricted to the passes whose row set s has bit s of `set_mask` set (pooled mode: one launch per
+ * set, so that the exchange of a set's gradient rows overlaps the tensor work of the next set) */
+int mscs_sim_backward_sets(const mscs_sim_job* job, const float* grad_out, float* const* dF_sets,
+                           const int32_t* dF_ld, uint32_t set_mask, void* stream);
 /* plain CUDA-core fp32 versions of the two calls above: validation kernels for the tests,
  * never used by the product path */
 int mscs_debug_sim_forward_simt(const mscs_sim_job* job, const float* const* f32_sets, void* stream);
