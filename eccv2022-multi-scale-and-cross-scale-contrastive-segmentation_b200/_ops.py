@@ -43,9 +43,9 @@ class _timed:
 
 def LAUNCHES_PER_STEP(num_scales, single_scale):
     """Kernels of libmscs.so launched by one forward+backward (torch fills not counted; checked against the ncu
-    launch list in profiles/): K1 hist, tile-scan, plan, MT19937 stream, select (5); K2 one per scale; K3 row ranges,
-    2 x (work table + sweep), 2 finalise kernels (7); K4 work table + backward (2); scatter one per scale."""
-    return 5 + num_scales + 7 + 2 + num_scales
+    launch list in profiles/): K1 hist, tile-scan, plan, MT19937 stream, select (5); K2 (1); K3 row ranges,
+    2 x (work table + sweep), 2 finalise kernels (7); K4 work table + backward (2); scatter (1)."""
+    return 5 + 1 + 7 + 2 + 1      # gather and scatter: one launch each for all scales
 
 
 @dataclass
@@ -727,12 +727,15 @@ def run_forward(sp, labels, feats32, needs, comm=None):
                                                     draws.data_ptr(), *arrs, sarr, st), "mscs_sample_select_async")
     if device_driven:
         with _timed("gather"):
+            items = (_lib.GatherItem * S)()
             for s in range(S):
                 n, Cc, h, w = sp.feat_shapes[s]
-                _lib.check(lib.mscs_gather_normalize_sectors_async(
-                    feats32[s].data_ptr(), n, Cc, h * w, slots[s].data_ptr(), plan_dev.data_ptr() + s * plan_sz + 8,
-                    bbase + 2 * sp.boff[s], fbase + 4 * sp.foff[s][0], fbase + 4 * sp.foff[s][1], st),
-                    "mscs_gather_normalize_sectors_async")
+                it = items[s]
+                it.feat, it.n, it.C, it.plane = feats32[s].data_ptr(), n, Cc, h * w
+                it.slot, it.n_rows_dev = slots[s].data_ptr(), plan_dev.data_ptr() + s * plan_sz + 8
+                it.anc_bf16, it.anc_f32 = bbase + 2 * sp.boff[s], fbase + 4 * sp.foff[s][0]
+                it.inv_norm = fbase + 4 * sp.foff[s][1]
+            _lib.check(lib.mscs_gather_normalize_sectors_batch(items, S, st), "mscs_gather_normalize_sectors_batch")
         if HOST_WAIT is not None:
             import time
             _t0 = time.perf_counter()
@@ -842,6 +845,7 @@ def run_backward(state, grad_out, needs, shapes, dtypes):
         gb = state.gradbufs
         if gb is not None:
             torch.cuda.current_stream().wait_event(gb.ready)
+        batch = []
         for s in range(S):
             if not needs[s]:
                 grads.append(None)
@@ -853,15 +857,26 @@ def run_backward(state, grad_out, needs, shapes, dtypes):
             pre, slot = (gb.take(s) if gb is not None else None), state.slots[s]
             if pre is not None and slot is not None:
                 out = pre
-                _lib.check(lib.mscs_scatter_sectors(ptrs[s], sp.C_pad, fbase + 4 * sp.foff[s][0],
-                                                    fbase + 4 * sp.foff[s][1], slot.data_ptr(), n, Cc, h * w,
-                                                    out.data_ptr(), st), "mscs_scatter_sectors")
+                if state.comm is None:      # single process: every scale in one launch (below)
+                    batch.append((ptrs[s], fbase + 4 * sp.foff[s][0], fbase + 4 * sp.foff[s][1], slot.data_ptr(),
+                                  n, Cc, h * w, out.data_ptr()))
+                else:
+                    _lib.check(lib.mscs_scatter_sectors(ptrs[s], sp.C_pad, fbase + 4 * sp.foff[s][0],
+                                                        fbase + 4 * sp.foff[s][1], slot.data_ptr(), n, Cc, h * w,
+                                                        out.data_ptr(), st), "mscs_scatter_sectors")
             else:
                 out = torch.empty(shapes[s], dtype=torch.float32, device=dev)
                 _lib.check(lib.mscs_scatter_grad(ptrs[s], sp.C_pad, fbase + 4 * sp.foff[s][0],
                                                  fbase + 4 * sp.foff[s][1], smp.ptr(2), smp.N, n, Cc, h * w,
                                                  out.data_ptr(), 1, st), "mscs_scatter_grad")
-            grads.append(out if dtypes[s] == torch.float32 else out.to(dtypes[s]))
+            grads.append(out)
+        if batch:
+            items = (_lib.ScatterItem * len(batch))()
+            for it, (dfp, f32p, invp, slotp, n, Cc, plane, outp) in zip(items, batch):
+                it.dF, it.ldF, it.anc_f32, it.inv_norm, it.slot = dfp, sp.C_pad, f32p, invp, slotp
+                it.n, it.C, it.plane, it.dfeat = n, Cc, plane, outp
+            _lib.check(lib.mscs_scatter_sectors_batch(items, len(batch), st), "mscs_scatter_sectors_batch")
+        grads = [g_ if (g_ is None or dtypes[s] == torch.float32) else g_.to(dtypes[s]) for s, g_ in enumerate(grads)]
     return grads
 
 

@@ -86,12 +86,12 @@ k_scatter_grad(const float* __restrict__ dF, int ldF, const float* __restrict__ 
 // Gather in ADDRESS order: one warp per 8-pixel octet of the slot map (18% of them hold a sampled
 // pixel at cfg-2).  Neighbouring warps then touch neighbouring 32-byte sectors of the same channel
 // planes, so the 256 strided sector reads of an anchor hit open DRAM pages instead of random ones.
-__global__ void __launch_bounds__(256)
-k_gather_sectors(const float* __restrict__ feat, int C, int C_pad, int plane, const int* __restrict__ slot,
-                 int n_octets, __nv_bfloat16* __restrict__ anc_bf16, float* __restrict__ anc_f32,
-                 float* __restrict__ inv_norm, const int* __restrict__ n_rows_dev) {
+__device__ __forceinline__ void
+gather_sectors_body(int block, int nblocks, const float* __restrict__ feat, int C, int C_pad, int plane,
+                    const int* __restrict__ slot, int n_octets, __nv_bfloat16* __restrict__ anc_bf16,
+                    float* __restrict__ anc_f32, float* __restrict__ inv_norm, const int* __restrict__ n_rows_dev) {
   const int lane = threadIdx.x & 31;
-  if (n_rows_dev != nullptr && blockIdx.x == gridDim.x - 1) {
+  if (n_rows_dev != nullptr && block == nblocks - 1) {
     // device-driven call: the row count is only known on the device; this (extra) block zeroes the padding
     // rows [N, N_pad) of the operand matrix that the TMA tiles read
     const int N = *n_rows_dev, N_pad = (N + 255) / 256 * 256;
@@ -99,7 +99,7 @@ k_gather_sectors(const float* __restrict__ feat, int C, int C_pad, int plane, co
     for (int i = threadIdx.x; i < (N_pad - N) * (C_pad / 2); i += blockDim.x) z[i] = 0u;
     return;
   }
-  const int oct = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int oct = block * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (oct >= n_octets) return;
   const int gp = oct * 8;
   const int s_mine = (lane < 8) ? slot[gp + lane] : -1;
@@ -135,6 +135,30 @@ k_gather_sectors(const float* __restrict__ feat, int C, int C_pad, int plane, co
   }
 }
 
+__global__ void __launch_bounds__(256)
+k_gather_sectors(const float* __restrict__ feat, int C, int C_pad, int plane, const int* __restrict__ slot,
+                 int n_octets, __nv_bfloat16* __restrict__ anc_bf16, float* __restrict__ anc_f32,
+                 float* __restrict__ inv_norm, const int* __restrict__ n_rows_dev) {
+  gather_sectors_body(blockIdx.x, gridDim.x, feat, C, C_pad, plane, slot, n_octets, anc_bf16, anc_f32, inv_norm,
+                      n_rows_dev);
+}
+
+// all scales of a call in ONE launch (the per-scale launches of the small scales do not fill the GPU and each
+// costs a launch gap): block -> scale through the block prefix
+struct GatherBatch {
+  const float* feat[MSCS_MAX_SCALES]; const int* slot[MSCS_MAX_SCALES]; const int* n_rows_dev[MSCS_MAX_SCALES];
+  __nv_bfloat16* bf16[MSCS_MAX_SCALES]; float* f32[MSCS_MAX_SCALES]; float* inv[MSCS_MAX_SCALES];
+  int C[MSCS_MAX_SCALES], plane[MSCS_MAX_SCALES], n_oct[MSCS_MAX_SCALES], block0[MSCS_MAX_SCALES + 1];
+  int count;
+};
+__global__ void __launch_bounds__(256) k_gather_sectors_batch(const __grid_constant__ GatherBatch g) {
+  int s = 0;
+  while (s + 1 < g.count && (int)blockIdx.x >= g.block0[s + 1]) ++s;
+  gather_sectors_body(blockIdx.x - g.block0[s], g.block0[s + 1] - g.block0[s], g.feat[s], g.C[s],
+                      (g.C[s] + 63) / 64 * 64, g.plane[s], g.slot[s], g.n_oct[s], g.bf16[s], g.f32[s], g.inv[s],
+                      g.n_rows_dev[s]);
+}
+
 // slot map: slot[image*plane + pixel] = sorted anchor row sampled there, or -1
 __global__ void k_slot_map(const int* __restrict__ pix, int N, int* __restrict__ slot) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -144,12 +168,12 @@ __global__ void k_slot_map(const int* __restrict__ pix, int N, int* __restrict__
 // Sector writer: the dense gradient is already zero; one warp per 8-pixel octet (= one 32-byte
 // sector per channel plane) rewrites every sector that holds at least one sampled pixel with
 // full-sector stores (values + explicit zeros), so no partial-sector read-modify-write reaches HBM.
-__global__ void __launch_bounds__(256)
-k_scatter_sectors(const float* __restrict__ dF, int ldF, const float* __restrict__ anc_f32,
+__device__ __forceinline__ void
+scatter_sectors_body(const float* __restrict__ dF, int ldF, const float* __restrict__ anc_f32,
                   const float* __restrict__ inv_norm, const int* __restrict__ slot, int n_octets, int C,
-                  int plane, float* __restrict__ dfeat) {
+                  int plane, float* __restrict__ dfeat, int block_base) {
   const int lane = threadIdx.x & 31;
-  const int oct = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int oct = ((int)blockIdx.x - block_base) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (oct >= n_octets) return;
   const int gp = oct * 8;
   const int s_mine = (lane < 8) ? slot[gp + lane] : -1;
@@ -189,6 +213,13 @@ k_scatter_sectors(const float* __restrict__ dF, int ldF, const float* __restrict
       dst[1] = make_float4(dx[4][q], dx[5][q], dx[6][q], dx[7][q]);
     }
   }
+}
+
+__global__ void __launch_bounds__(256)
+k_scatter_sectors(const float* __restrict__ dF, int ldF, const float* __restrict__ anc_f32,
+                  const float* __restrict__ inv_norm, const int* __restrict__ slot, int n_octets, int C,
+                  int plane, float* __restrict__ dfeat, int block_base) {
+  scatter_sectors_body(dF, ldF, anc_f32, inv_norm, slot, n_octets, C, plane, dfeat, block_base);
 }
 
 }  // namespace mscs
@@ -245,7 +276,65 @@ extern "C" int mscs_scatter_sectors(const float* dF, int ldF, const float* anc_f
   MSCS_CHECK_ARG(plane % 8 == 0, "plane %d is not a multiple of 8 pixels: use mscs_scatter_grad", plane);
   const int n_oct = n * (plane / 8);
   k_scatter_sectors<<<ceil_div(n_oct, 8), 256, 0, (cudaStream_t)stream_>>>(dF, ldF, anc_f32, inv_norm, slot, n_oct,
-                                                                           C, plane, dfeat);
+                                                                           C, plane, dfeat, 0);
+  MSCS_LAUNCH_CHECK();
+  return 0;
+}
+
+// One launch for every scale of a call (see mscs.h)
+extern "C" int mscs_gather_normalize_sectors_batch(const mscs_gather_item* items, int count, void* stream_) {
+  MSCS_CHECK_ARG(items && count >= 1 && count <= MSCS_MAX_SCALES, "bad item count %d", count);
+  GatherBatch g{};
+  g.count = count;
+  int blocks = 0;
+  for (int s = 0; s < count; ++s) {
+    const mscs_gather_item& it = items[s];
+    MSCS_CHECK_ARG(it.feat && it.slot && it.n_rows_dev && it.anc_bf16 && it.anc_f32 && it.inv_norm,
+                   "item %d: null pointer argument", s);
+    MSCS_CHECK_ARG(it.C >= 1 && it.C <= kMaxC, "item %d: C=%d unsupported (1..%d)", s, it.C, kMaxC);
+    MSCS_CHECK_ARG(it.n >= 1 && it.plane >= 8 && it.plane % 8 == 0, "item %d: plane must be a multiple of 8", s);
+    g.feat[s] = it.feat; g.slot[s] = it.slot; g.n_rows_dev[s] = it.n_rows_dev;
+    g.bf16[s] = (__nv_bfloat16*)it.anc_bf16; g.f32[s] = it.anc_f32; g.inv[s] = it.inv_norm;
+    g.C[s] = it.C; g.plane[s] = it.plane; g.n_oct[s] = it.n * (it.plane / 8);
+    g.block0[s] = blocks;
+    blocks += ceil_div(g.n_oct[s], 8) + 1;      // + the block that zeroes the padding rows
+  }
+  g.block0[count] = blocks;
+  k_gather_sectors_batch<<<blocks, 256, 0, (cudaStream_t)stream_>>>(g);
+  MSCS_LAUNCH_CHECK();
+  return 0;
+}
+
+struct ScatterBatch {
+  const float* dF[MSCS_MAX_SCALES]; const float* f32[MSCS_MAX_SCALES]; const float* inv[MSCS_MAX_SCALES];
+  const int* slot[MSCS_MAX_SCALES]; float* dfeat[MSCS_MAX_SCALES];
+  int ldF[MSCS_MAX_SCALES], C[MSCS_MAX_SCALES], plane[MSCS_MAX_SCALES], n_oct[MSCS_MAX_SCALES], block0[MSCS_MAX_SCALES + 1];
+  int count;
+};
+__global__ void __launch_bounds__(256) k_scatter_sectors_batch(const __grid_constant__ ScatterBatch g) {
+  int s = 0;
+  while (s + 1 < g.count && (int)blockIdx.x >= g.block0[s + 1]) ++s;
+  scatter_sectors_body(g.dF[s], g.ldF[s], g.f32[s], g.inv[s], g.slot[s], g.n_oct[s], g.C[s], g.plane[s], g.dfeat[s],
+                       g.block0[s]);
+}
+
+extern "C" int mscs_scatter_sectors_batch(const mscs_scatter_item* items, int count, void* stream_) {
+  MSCS_CHECK_ARG(items && count >= 1 && count <= MSCS_MAX_SCALES, "bad item count %d", count);
+  ScatterBatch g{};
+  g.count = count;
+  int blocks = 0;
+  for (int s = 0; s < count; ++s) {
+    const mscs_scatter_item& it = items[s];
+    MSCS_CHECK_ARG(it.dF && it.anc_f32 && it.inv_norm && it.slot && it.dfeat, "item %d: null pointer argument", s);
+    MSCS_CHECK_ARG(it.C >= 1 && it.C <= kMaxC && it.ldF >= it.C, "item %d: C=%d / ldF=%d unsupported", s, it.C, it.ldF);
+    MSCS_CHECK_ARG(it.plane % 8 == 0, "item %d: plane %d is not a multiple of 8 pixels", s, it.plane);
+    g.dF[s] = it.dF; g.f32[s] = it.anc_f32; g.inv[s] = it.inv_norm; g.slot[s] = it.slot; g.dfeat[s] = it.dfeat;
+    g.ldF[s] = it.ldF; g.C[s] = it.C; g.plane[s] = it.plane; g.n_oct[s] = it.n * (it.plane / 8);
+    g.block0[s] = blocks;
+    blocks += ceil_div(g.n_oct[s], 8);
+  }
+  g.block0[count] = blocks;
+  k_scatter_sectors_batch<<<blocks, 256, 0, (cudaStream_t)stream_>>>(g);
   MSCS_LAUNCH_CHECK();
   return 0;
 }

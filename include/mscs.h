@@ -156,6 +156,12 @@ int mscs_gather_normalize_sectors(const float* feat, int n, int C, int plane, co
 int mscs_gather_normalize_sectors_async(const float* feat, int n, int C, int plane, const int32_t* slot,
                                         const int32_t* n_rows_dev, void* anc_bf16, float* anc_f32, float* inv_norm,
                                         void* stream);
+/* every scale of a call in ONE launch (device-driven form, see above) */
+typedef struct {
+  const float* feat; int32_t n, C, plane; const int32_t* slot; const int32_t* n_rows_dev;
+  void* anc_bf16; float* anc_f32; float* inv_norm;
+} mscs_gather_item;
+int mscs_gather_normalize_sectors_batch(const mscs_gather_item* items, int count, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * K3 / K4 -- fused similarity + loss forward and backward for every term of one call.
@@ -236,6 +242,12 @@ int mscs_scatter_grad(const float* dF, int ldF, const float* anc_f32, const floa
 int mscs_slot_map(const int32_t* pix, int N, int n_pixels, int32_t* slot, void* stream);
 int mscs_scatter_sectors(const float* dF, int ldF, const float* anc_f32, const float* inv_norm,
                          const int32_t* slot, int n, int C, int plane, float* dfeat, void* stream);
+/* every scale of a call in ONE launch */
+typedef struct {
+  const float* dF; int32_t ldF; const float* anc_f32; const float* inv_norm; const int32_t* slot;
+  int32_t n, C, plane; float* dfeat;
+} mscs_scatter_item;
+int mscs_scatter_sectors_batch(const mscs_scatter_item* items, int count, void* stream);
 
 #ifdef __cplusplus
 }
