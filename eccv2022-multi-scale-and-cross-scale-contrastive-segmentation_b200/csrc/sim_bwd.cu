@@ -295,7 +295,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
           const int cb = ct * kTileN + h * kBwdSub + cq * 16;      // first global column of this thread's quarter
           const float* cs_s = cs_unit + h * 16; const float* cs_pn = cs_s + 32; const float* cs_neg = cs_s + 64;
           const bool touches = !(cb + 16 <= wmin || cb >= wmax);
-          ptx::mbar_wait(&s_full[sb], (t2 >> 1) & 1, 221);     // (16 warps polling with test_wait measured slower)
+          // (Polling instead -- all 16 warps with test_wait, or one warp per SM sub-partition with the other three
+          // parked in a named barrier -- measured no faster than the suspending try_wait.)
+          ptx::mbar_wait(&s_full[sb], (t2 >> 1) & 1, 221);
           ptx::tc_fence_after();
           const uint32_t taddr = tmem_base + lane_base + kTmS + sb * kBwdSub + cq * 16;
           uint32_t v[16];

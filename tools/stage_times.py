@@ -29,6 +29,6 @@ torch.cuda.synchronize()
 t_all = time.perf_counter() - t0
 print(f"wall/step {t_all/50*1e3:.3f} ms; host blocked in the plan fetch {sum(_ops.HOST_WAIT)/50*1e3:.3f} ms/step -> host busy {(t_enq-sum(_ops.HOST_WAIT))/50*1e3:.3f} ms/step")
 _ops.TIMING = {}
-for _ in range(3): step()
+for _ in range(30): step()
 torch.cuda.synchronize()
 print(os.environ.get("MSCS_DEBUG_FLAGS", "0"), {k: round(sum(a.elapsed_time(b) for a, b in v) / len(v), 4) for k, v in _ops.TIMING.items()})
