@@ -23,6 +23,18 @@ _MT_N = 624
 TIMING = None
 # optional host-side accounting (tools/stage_times.py): seconds the host spent blocked in the plan fetch, per call
 HOST_WAIT = None
+# optional host-side segment accounting (tools/stage_times.py): {segment: seconds}
+HOST_SEG = None
+
+
+def _seg(name, t0):
+    """Adds the host time since t0 to segment `name`; returns the new time stamp (no-op when disabled)."""
+    if HOST_SEG is None:
+        return t0
+    import time
+    t1 = time.perf_counter()
+    HOST_SEG[name] = HOST_SEG.get(name, 0.0) + (t1 - t0)
+    return t1
 
 
 class _timed:
@@ -91,7 +103,7 @@ class ScaleSample:
         return self._slab.data_ptr() + 4 * self._off[k]
 
 
-_stream_override = [None]
+_stream_override = [None, None]
 
 
 def _stream():
@@ -101,12 +113,21 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _cur_stream():
+    """torch Stream object of the current stream (cached for the duration of a forward/backward call:
+    torch.cuda.current_stream() costs ~5 us of Python per call)."""
+    if _stream_override[1] is not None:
+        return _stream_override[1]
+    return torch.cuda.current_stream()
+
+
 class _pin_stream:
     def __enter__(self):
-        _stream_override[0] = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        cur = torch.cuda.current_stream()
+        _stream_override[0], _stream_override[1] = C.c_void_p(cur.cuda_stream), cur
 
     def __exit__(self, *exc):
-        _stream_override[0] = None
+        _stream_override[0] = _stream_override[1] = None
 
 
 def _require_device(t):
@@ -125,6 +146,16 @@ def torch_mt_state():
     return mt, pos
 
 
+def _publish_mt_state(mt, pos):
+    """Writes (state uint32[624], pos in 1..624) into the torch CPU default generator."""
+    raw = torch.get_rng_state().numpy().copy()
+    hdr = struct.pack("<ii", 625 - pos, 1)
+    raw[8:16] = np.frombuffer(hdr, dtype=np.uint8)
+    raw[16:24] = np.frombuffer(struct.pack("<Q", pos), dtype=np.uint8)
+    raw[24:24 + 8 * _MT_N] = mt.astype(np.uint64).view(np.uint8)
+    torch.set_rng_state(torch.from_numpy(raw))
+
+
 def torch_mt_advance(mt, pos, draws):
     """Advance the torch CPU default generator by ``draws`` 32-bit outputs -- what the reference's
     per-pair ``torch.randperm`` calls would have consumed (V2.py:121).  Returns the new (mt, pos)."""
@@ -135,12 +166,7 @@ def torch_mt_advance(mt, pos, draws):
     cpos = C.c_int(pos)
     _lib.check(lib.mscs_mt19937_advance_host(mt.ctypes.data_as(C.c_void_p), C.byref(cpos), C.c_uint64(draws)),
                "mscs_mt19937_advance_host")
-    raw = torch.get_rng_state().numpy().copy()
-    hdr = struct.pack("<ii", 625 - cpos.value, 1)
-    raw[8:16] = np.frombuffer(hdr, dtype=np.uint8)
-    raw[16:24] = np.frombuffer(struct.pack("<Q", cpos.value), dtype=np.uint8)
-    raw[24:24 + 8 * _MT_N] = mt.astype(np.uint64).view(np.uint8)
-    torch.set_rng_state(torch.from_numpy(raw))
+    _publish_mt_state(mt, cpos.value)
     return mt, cpos.value
 
 
@@ -162,13 +188,14 @@ class _StreamCache:
         self.ready = None        # event: buffer `cur` complete
         self.last_use = [None, None]   # event: last main-stream reader of each buffer
         self.lock = threading.Lock()
+        self.copy = torch.cuda.Stream(device=dev)      # read-back of the generator state (see state_after)
 
     def _generate(self, which, mt, pos, words):
         lib = _lib.load()
         if self.bufs[which] is None or self.bufs[which].numel() < words + 1024:
             self.bufs[which] = torch.empty(words + 1024, dtype=torch.int32, device=self.dev)
             self.bufs[which].record_stream(self.side)
-            self.side.wait_stream(torch.cuda.current_stream())      # fresh allocation: order after its previous users
+            self.side.wait_stream(_cur_stream())      # fresh allocation: order after its previous users
         # the stream depends only on the host-side generator state: it is NOT ordered after the main
         # stream, only after the last reader of this buffer (the selection kernel two calls ago)
         if self.last_use[which] is not None:
@@ -185,15 +212,36 @@ class _StreamCache:
         with self.lock:
             if self.key != (mt.tobytes(), pos) or self.words < words:
                 self._generate(self.cur ^ 1, mt, pos, words)
-            torch.cuda.current_stream().wait_event(self.ready)
+            _cur_stream().wait_event(self.ready)
             return self.bufs[self.cur]
+
+    def state_after(self, mt, pos, total):
+        """Generator state (mt', pos') after `total` draws from (mt, pos).  The stream buffer holds the RAW state
+        words, so the new state array is simply the 624-word block the next draw falls into: it is read back
+        (2.5 KB on a private stream) instead of recomputing ~800 block regenerations on the host (~100 us at cfg-2).
+        Same convention as mscs_mt19937_advance_host: pos in 1..624, an exhausted block is not regenerated."""
+        if total <= 0:
+            return mt, pos
+        blk = (pos + total - 1) // _MT_N
+        newpos = pos + total - blk * _MT_N
+        if blk == 0:
+            return mt, newpos
+        off = blk * _MT_N - pos
+        with self.lock:
+            buf = self.bufs[self.cur]
+            if self.key != (mt.tobytes(), pos) or off + _MT_N > self.words:
+                return None
+            self.copy.wait_event(self.ready)
+            with torch.cuda.stream(self.copy):
+                host = buf[off:off + _MT_N].cpu()
+        return host.numpy().view(np.uint32).copy(), newpos
 
     def release_and_prefetch(self, mt_next, pos_next, words):
         if os.environ.get("MSCS_NO_PREFETCH"):      # experiment switch: regenerate inline at the next call
             return
         with self.lock:
             ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream())
+            ev.record(_cur_stream())
             self.last_use[self.cur] = ev
             self._generate(self.cur ^ 1, mt_next, pos_next, words)
 
@@ -405,7 +453,8 @@ def scatter_grad(dF, aset, sample, feat_shape, dtype, prezeroed=None, slot=None)
 
 class _GradBuffers:
     """Dense feature gradients zero-filled ahead of time on a side stream (the zero fill is the
-    largest HBM term of the whole path, SURVEY.md §8d, and does not depend on any result)."""
+    largest HBM term of the whole path, SURVEY.md §8d, and does not depend on any result).  One slab for all
+    scales and one fill: the per-scale tensors handed to autograd are views of it."""
     _side = {}
 
     def __init__(self, feats, needs):
@@ -413,25 +462,23 @@ class _GradBuffers:
         side = self._side.get(dev)
         if side is None:
             side = self._side[dev] = torch.cuda.Stream(device=dev)
-        main = torch.cuda.current_stream()
-        self.bufs = []
-        for f, need in zip(feats, needs):
-            n, Cc, h, w = f.shape
-            if not need or (h * w) % 8 != 0:
-                self.bufs.append(None)
-                continue
-            self.bufs.append(torch.empty(f.shape, dtype=torch.float32, device=dev))
+        sizes = [f.numel() if (need and (f.shape[2] * f.shape[3]) % 8 == 0) else 0 for f, need in zip(feats, needs)]
+        self.slab = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        self.bufs, off = [], 0
+        for f, n_ in zip(feats, sizes):
+            self.bufs.append(self.slab[off:off + n_].view(f.shape) if n_ else None)
+            off += n_
         self.side, self.ready = side, None
 
     def start_fill(self):
         """Zero-fill on the side stream, ordered after what the main stream has enqueued so far."""
         side = self.side
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for b in self.bufs:
-                if b is not None:
-                    b.zero_()
-                    b.record_stream(side)
+        side.wait_stream(_cur_stream())
+        if self.slab.numel():
+            ptrs = _lib.ptr_array([self.slab.data_ptr()])
+            _lib.check(_lib.load().mscs_fill_bytes(ptrs, (C.c_int32 * 1)(0), (C.c_size_t * 1)(4 * self.slab.numel()), 1,
+                                                   C.c_void_p(side.cuda_stream)), "mscs_fill_bytes")
+            self.slab.record_stream(side)
         self.ready = torch.cuda.Event()
         self.ready.record(side)
 
@@ -439,7 +486,6 @@ class _GradBuffers:
         """The pre-zeroed buffer of scale s (once: a second backward falls back to zero-fill)."""
         b, self.bufs[s] = self.bufs[s], None
         return b
-
 
 
 # ---- pooled cross-batch mode: collectives -----------------------------------------------------
@@ -621,6 +667,16 @@ class _StepPlan:
             t.self_mask, t.need_dk, t.temperature, t.weight, t.a_set, t.k_set = int(self_mask), int(need_dk), tau, \
                 weight, a, k
         self.work_bytes = lib.mscs_sim_workspace_bytes(C.byref(job))
+        # single-process calls: ONE allocation per forward; byte offsets (256-aligned) of its parts
+        self.slot_sizes = [shp[0] * shp[2] * shp[3] if (shp[2] * shp[3]) % 8 == 0 else 0 for shp in feat_shapes]
+        parts = [("ws", self.ws_bytes), ("plan", S * C.sizeof(_lib.ScalePlan)), ("work", self.work_bytes),
+                 ("stats", 4 * self.stats_n), ("misc", 4 * self.misc_n), ("fslab", 4 * self.fslab_n),
+                 ("islab", 4 * self.islab_n), ("slot", 4 * sum(self.slot_sizes)), ("bslab", 2 * self.bslab_n)]
+        self.slab_off, off = {}, 0
+        for name, nbytes in parts:
+            self.slab_off[name] = off
+            off += (nbytes + 255) // 256 * 256
+        self.slab_bytes = off
         self.dF_off, off = [], 0
         for s in range(S):
             self.dF_off.append(off)
@@ -646,15 +702,35 @@ class _StepState:
     pass
 
 
+class _Ptr:
+    """Address inside a slab (quacks like a tensor for data_ptr()): a torch view costs a few microseconds of
+    Python each and most buffers of a step are only ever passed to the library as raw pointers."""
+    __slots__ = ("p",)
+
+    def __init__(self, p):
+        self.p = p
+
+    def data_ptr(self):
+        return self.p
+
+
 def run_forward(sp, labels, feats32, needs, comm=None):
     lib = _lib.load()
     dev, S, A, spec = sp.dev, sp.S, sp.A, sp.spec
     st = _stream()
     i32, f32, u8 = torch.int32, torch.float32, torch.uint8
     # ---- everything that does not need the plan: before the sync ----
-    ws = torch.empty(sp.ws_bytes, dtype=u8, device=dev)
-    plan_dev = torch.empty(S * C.sizeof(_lib.ScalePlan), dtype=u8, device=dev)
+    import time
+    _t = time.perf_counter() if HOST_SEG is not None else 0.0
     pooled = comm is not None and comm.world > 1
+    if pooled:
+        ws = torch.empty(sp.ws_bytes, dtype=u8, device=dev)
+        plan_dev = torch.empty(S * C.sizeof(_lib.ScalePlan), dtype=u8, device=dev)
+    else:
+        # one allocation per call; raw addresses for everything the library alone touches
+        slab = torch.empty(sp.slab_bytes, dtype=u8, device=dev)
+        sb, so = slab.data_ptr(), sp.slab_off
+        ws, plan_dev = _Ptr(sb + so["ws"]), _Ptr(sb + so["plan"])
     with _timed("sample"):
         if not pooled:
             _lib.check(lib.mscs_sample_plan(C.byref(sp.cfg), labels.data_ptr(), ws.data_ptr(), plan_dev.data_ptr(),
@@ -669,27 +745,43 @@ def run_forward(sp, labels, feats32, needs, comm=None):
             cptr = _lib.ptr_array([counts_g[s].data_ptr() for s in range(S)])
             _lib.check(lib.mscs_sample_plan_from_counts(C.byref(sp.cfg), cptr, ws.data_ptr(), plan_dev.data_ptr(),
                                                         st), "mscs_sample_plan_from_counts")
-        islab = torch.empty(sp.islab_n, dtype=i32, device=dev) if not pooled else \
-            torch.zeros(sp.islab_n, dtype=i32, device=dev)
-        fslab = torch.empty(sp.fslab_n, dtype=f32, device=dev)
-        bslab = (torch.zeros if pooled else torch.empty)(sp.bslab_n, dtype=torch.bfloat16, device=dev)   # pooled: rows of
-        # other ranks must be zero for the all-reduce
-        stats = torch.zeros(sp.stats_n, dtype=f32, device=dev)
-        misc = torch.empty(sp.misc_n, dtype=f32, device=dev)
-        work = torch.empty(sp.work_bytes, dtype=u8, device=dev)
+        sizes = sp.slot_sizes
+        if pooled:
+            islab = torch.zeros(sp.islab_n, dtype=i32, device=dev)
+            fslab = torch.empty(sp.fslab_n, dtype=f32, device=dev)
+            bslab = torch.zeros(sp.bslab_n, dtype=torch.bfloat16, device=dev)   # rows of other ranks must be zero for
+            # the all-reduce
+            stats = torch.zeros(sp.stats_n, dtype=f32, device=dev)
+            misc = torch.empty(sp.misc_n, dtype=f32, device=dev)
+            work = torch.empty(sp.work_bytes, dtype=u8, device=dev)
+            # pixel -> row maps (filled by the selection kernel): drive the address-ordered gather and the
+            # sector scatter of the backward
+            slot_slab = torch.full((sum(sizes),), -1, dtype=i32, device=dev) if sum(sizes) else None     # one fill
+            slots, off = [], 0
+            for x in sizes:
+                slots.append(slot_slab[off:off + x] if x else None)
+                off += x
+            keep = (ws, islab, fslab, bslab, stats, misc, work, slot_slab)
+        else:
+            keep = slab      # (two byte fills in one call below)
+            islab = slab[so["islab"]:so["islab"] + 4 * sp.islab_n].view(i32)
+            stats = slab[so["stats"]:so["stats"] + 4 * sp.stats_n].view(f32)
+            misc = slab[so["misc"]:so["misc"] + 4 * sp.misc_n].view(f32)
+            fslab, bslab, work = _Ptr(sb + so["fslab"]), _Ptr(sb + so["bslab"]), _Ptr(sb + so["work"])
+            slots, off = [], sb + so["slot"]
+            for x in sizes:
+                slots.append(_Ptr(off) if x else None)
+                off += 4 * x
+            _lib.check(lib.mscs_fill_bytes(_lib.ptr_array([sb + so["stats"], sb + so["slot"]]), (C.c_int32 * 2)(0, 0xFF),
+                                           (C.c_size_t * 2)(4 * sp.stats_n, 4 * sum(sizes)), 2, st), "mscs_fill_bytes")
+        _t = _seg("fwd: alloc + plan kernels", _t)
         gradbufs = _GradBuffers(feats32, needs) if any(needs) else None
         if gradbufs is not None:      # (started here: overlapping the tensor kernels instead measured slower -- the
             gradbufs.start_fill()     # fill's CTAs share the SMs with the persistent kernel's epilogue warps)
-        # pixel -> row maps (filled by the selection kernel): drive the address-ordered gather and the
-        # sector scatter of the backward
-        sizes = [shp[0] * shp[2] * shp[3] if (shp[2] * shp[3]) % 8 == 0 else 0 for shp in sp.feat_shapes]
-        slot_slab = torch.full((sum(sizes),), -1, dtype=i32, device=dev) if sum(sizes) else None     # one fill
-        slots, off = [], 0
-        for x in sizes:
-            slots.append(slot_slab[off:off + x] if x else None)
-            off += x
+        _t = _seg("fwd: grad buffers", _t)
         mt, pos = torch_mt_state()
-        draws = _stream_cache(dev).acquire(mt, pos, sp.max_draws)
+        draws = _stream_cache(dev).acquire(mt, pos, sp.max_draws + _MT_N)
+        _t = _seg("fwd: rng state + stream acquire", _t)
         plan = (_lib.ScalePlan * S)()
         ibase = islab.data_ptr()
         arrs = [_lib.ptr_array([ibase + 4 * sp.ioff[s][k] for s in range(S)]) for k in range(5)]
@@ -736,12 +828,13 @@ def run_forward(sp, labels, feats32, needs, comm=None):
                 it.anc_bf16, it.anc_f32 = bbase + 2 * sp.boff[s], fbase + 4 * sp.foff[s][0]
                 it.inv_norm = fbase + 4 * sp.foff[s][1]
             _lib.check(lib.mscs_gather_normalize_sectors_batch(items, S, st), "mscs_gather_normalize_sectors_batch")
+        _t = _seg("fwd: job + select + gather", _t)
         if HOST_WAIT is not None:
-            import time
             _t0 = time.perf_counter()
         _lib.check(lib.mscs_plan_fetch_end(plan, S), "mscs_plan_fetch_end")       # the host sync (plan records only)
         if HOST_WAIT is not None:
             HOST_WAIT.append(time.perf_counter() - _t0)
+        _t = time.perf_counter() if HOST_SEG is not None else 0.0
     else:
         _lib.check(lib.mscs_plan_fetch(plan_dev.data_ptr(), plan, S, st), "mscs_plan_fetch")     # the host sync
     for s in range(S):
@@ -793,13 +886,22 @@ def run_forward(sp, labels, feats32, needs, comm=None):
             _lib.check(lib.mscs_sim_forward_sweeps(C.byref(job), st), "mscs_sim_forward_sweeps")
             comm.all_reduce(stats)       # row statistics of all ranks' rows
             _lib.check(lib.mscs_sim_finalize(C.byref(job), st), "mscs_sim_finalize")
+    _t = _seg("fwd: after wait -> sim_forward enqueued", _t)
     # host-side generator bookkeeping, off the GPU's critical path
     if comm is None or comm.owns_rng:
-        mt2, pos2 = torch_mt_advance(mt, pos, total)
-        _stream_cache(dev).release_and_prefetch(mt2, pos2, sp.max_draws)
+        nxt = _stream_cache(dev).state_after(mt, pos, total)
+        if nxt is None:
+            mt2, pos2 = torch_mt_advance(mt, pos, total)
+        else:
+            mt2, pos2 = nxt
+            if total > 0:
+                _publish_mt_state(mt2, pos2)
+        _stream_cache(dev).release_and_prefetch(mt2, pos2, sp.max_draws + _MT_N)
+    _t = _seg("fwd: rng advance + prefetch", _t)
     state = _StepState()
     state.sp, state.job, state.samples, state.gradbufs, state.slots = sp, job, samples, gradbufs, slots
-    state.keep = (ws, islab, fslab, bslab, stats, misc, work)
+    state.keep = keep
+    state.stats = stats
     state.fslab, state.term_loss = fslab, misc[sp.out_off:sp.out_off + nt]
     state.total = misc[sp.out_off + nt]
     state.scalars = misc[sp.out_off:sp.out_off + nt + 2]      # [term losses..., total, inf/NaN flag]: one copy for the logger
@@ -844,7 +946,7 @@ def run_backward(state, grad_out, needs, shapes, dtypes):
     with _timed("scatter"):
         gb = state.gradbufs
         if gb is not None:
-            torch.cuda.current_stream().wait_event(gb.ready)
+            _cur_stream().wait_event(gb.ready)
         batch = []
         for s in range(S):
             if not needs[s]:
@@ -881,6 +983,9 @@ def run_backward(state, grad_out, needs, shapes, dtypes):
 
 
 # ---- the autograd.Function ----------------------------------------------------------------
+_device_checked = [False]
+
+
 class MsCsContrastiveFn(torch.autograd.Function):
     """(labels, spec, single_scale, holder, *features) -> (total_loss 0-d, term_losses (n_terms,)).
 
@@ -890,8 +995,10 @@ class MsCsContrastiveFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, labels, spec, single_scale, holder, *feats):
         comm = holder.get("comm")
-        if not _lib.load().mscs_device_ok():
-            raise RuntimeError("mscs_b200 needs a compute-capability 10.x (B200) device; no fallback exists")
+        if not _device_checked[0]:
+            if not _lib.load().mscs_device_ok():
+                raise RuntimeError("mscs_b200 needs a compute-capability 10.x (B200) device; no fallback exists")
+            _device_checked[0] = True
         feats32 = []
         for f in feats:
             _require_device(f)

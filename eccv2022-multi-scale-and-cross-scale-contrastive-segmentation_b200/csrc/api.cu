@@ -54,3 +54,11 @@ extern "C" int mscs_device_ok(void) {
   cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
   return major == 10;
 }
+
+// Up to four byte-fills in one call (workspace initialisation of a step: statistics = 0, slot map = -1, ...).
+extern "C" int mscs_fill_bytes(void* const* ptrs, const int32_t* values, const size_t* bytes, int count, void* stream_) {
+  MSCS_CHECK_ARG(ptrs && values && bytes && count >= 0 && count <= 8, "bad arguments");
+  for (int i = 0; i < count; ++i)
+    if (bytes[i]) MSCS_CUDA(cudaMemsetAsync(ptrs[i], values[i], bytes[i], (cudaStream_t)stream_));
+  return 0;
+}

@@ -45,6 +45,8 @@ int mscs_debug_wait_profile_bwd(unsigned long long* ns_out, unsigned long long* 
 int mscs_debug_trace_bwd(unsigned long long* out, int max_events);
 /* 1 if a CUDA device with compute capability 10.x is present */
 int mscs_device_ok(void);
+/* up to 8 asynchronous byte fills in one call (per-step workspace initialisation: statistics = 0, slot maps = 0xFF) */
+int mscs_fill_bytes(void* const* ptrs, const int32_t* values, const size_t* bytes, int count, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * K1 -- sampling.  Replaces get_dist_and_classes (DenseContrastiveLossV2.py:194-206),

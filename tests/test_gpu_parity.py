@@ -539,7 +539,7 @@ def test_tensor_core_path_vs_fp32_validation_kernels_full_size(name, dev):
     terms_tc = state.term_loss.clone()
     total_tc = float(state.total)
     # fp32 validation kernels on the same job (fresh statistics)
-    state.keep[4].zero_()
+    state.stats.zero_()
     fp = [0] * _lib.MAX_SCALES
     for s in range(S):
         fp[s] = state.fslab.data_ptr() + 4 * sp.foff[s][0]
@@ -560,3 +560,38 @@ def test_tensor_core_path_vs_fp32_validation_kernels_full_size(name, dev):
         cs = float((a @ b) / (a.norm() * b.norm()))
         print(f"{name} set {s}: N {N} dF cosine {cs:.8f} max-abs {float((a - b).abs().max()):.3e}")
         assert cs >= 0.999
+
+
+@pytest.mark.gpu
+def test_generator_state_after_call_matches_host_advance(dev):
+    """Q7: the call must leave the torch CPU generator where the reference's randperm calls would (n-1 draws per
+    kept pair).  The product path reads the new state back from the device stream buffer; it has to equal the host
+    recurrence (mscs_mt19937_advance_host, itself pinned against the reference by the golden fixtures), on a fresh
+    stream (first call) and on the prefetched one (second call)."""
+    import mscs_b200
+    from mscs_b200 import _ops, synth
+    cfg = synth.CONFIGS["cfg2"]
+    labels, feats = synth.make_inputs("cfg2")
+    mod = mscs_b200.DenseContrastiveLossV2_ms(dict(cfg["loss"]))
+    lab, fts = labels.to(dev), [f.to(dev) for f in feats]
+    torch.manual_seed(123)
+    for _ in range(2):
+        mt0, pos0 = _ops.torch_mt_state()
+        with torch.no_grad():
+            mod(lab, fts)
+        got_mt, got_pos = _ops.torch_mt_state()
+        from mscs_b200 import _lib
+        lib = _lib.load()
+        # draws = sum over kept pairs of (count - 1): count = pixels of the class in the image at that scale
+        draws = 0
+        for s, smp in enumerate(mod.last_samples):
+            h, w = feats[s].shape[2:]
+            lab_s = torch.nn.functional.interpolate(labels[:, None].float(), (h, w), mode="nearest")[:, 0].long()
+            for b, c in smp.pair_ref.cpu().tolist():
+                draws += int((lab_s[b] == c).sum()) - 1
+        want = mt0.copy()
+        cpos = C.c_int(pos0)
+        _lib.check(lib.mscs_mt19937_advance_host(want.ctypes.data_as(C.c_void_p), C.byref(cpos), C.c_uint64(draws)),
+                   "advance")
+        assert got_pos == cpos.value
+        assert np.array_equal(got_mt, want)

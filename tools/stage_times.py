@@ -22,9 +22,19 @@ torch.cuda.synchronize()
 import time
 _ops.TIMING = None
 _ops.HOST_WAIT = []
+_ops.HOST_SEG = {}
+_orig_fwd, _orig_bwd = _ops.run_forward, _ops.run_backward
+def _tf(*a, **k):
+    t = time.perf_counter(); r = _orig_fwd(*a, **k); _ops.HOST_SEG["run_forward total"] = _ops.HOST_SEG.get("run_forward total", 0.0) + time.perf_counter() - t; return r
+def _tb(*a, **k):
+    t = time.perf_counter(); r = _orig_bwd(*a, **k); _ops.HOST_SEG["run_backward total"] = _ops.HOST_SEG.get("run_backward total", 0.0) + time.perf_counter() - t; return r
+_ops.run_forward, _ops.run_backward = _tf, _tb
 t0 = time.perf_counter()
 for _ in range(50): step()
 t_enq = time.perf_counter() - t0
+_ops.run_forward, _ops.run_backward = _orig_fwd, _orig_bwd
+print({k: round(v / 50 * 1e6) for k, v in _ops.HOST_SEG.items()}, "us/step")
+_ops.HOST_SEG = None
 torch.cuda.synchronize()
 t_all = time.perf_counter() - t0
 print(f"wall/step {t_all/50*1e3:.3f} ms; host blocked in the plan fetch {sum(_ops.HOST_WAIT)/50*1e3:.3f} ms/step -> host busy {(t_enq-sum(_ops.HOST_WAIT))/50*1e3:.3f} ms/step")
