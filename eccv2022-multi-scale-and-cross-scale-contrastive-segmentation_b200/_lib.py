@@ -39,7 +39,7 @@ class Term(C.Structure):
                 ("temperature", C.c_float), ("weight", C.c_float), ("a_set", C.c_int32), ("k_set", C.c_int32),
                 ("row_begin", C.c_int32), ("row_end", C.c_int32), ("krow_begin", C.c_int32), ("krow_end", C.c_int32),
                 ("neg_sum", C.c_void_p), ("pos_sum", C.c_void_p), ("s_sum", C.c_void_p),
-                ("coef_s", C.c_void_p), ("coef_pn", C.c_void_p)]
+                ("coef_s", C.c_void_p), ("coef_pn", C.c_void_p), ("n1_dev", C.c_void_p), ("n2_dev", C.c_void_p)]
 
 
 class SimJob(C.Structure):
@@ -53,11 +53,13 @@ _SIGNATURES = {
     "mscs_version": (C.c_char_p, []),
     "mscs_last_error": (C.c_char_p, []),
     "mscs_device_ok": (C.c_int, []),
+    "mscs_read_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "mscs_fill_bytes": (C.c_int, [_PTRS, C.POINTER(C.c_int32), C.POINTER(C.c_size_t), C.c_int, C.c_void_p]),
     "mscs_debug_trap_info": (C.c_int, [C.c_char_p, C.c_int]),
     "mscs_debug_wait_profile_fwd": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mscs_debug_wait_profile_bwd": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mscs_debug_trace_bwd": (C.c_int, [C.c_void_p, C.c_int]),
+    "mscs_debug_fwd_timeline": (C.c_int, [C.c_void_p, C.c_int]),
     "mscs_sample_workspace_bytes": (C.c_size_t, [C.POINTER(SampleCfg)]),
     "mscs_sample_max_draws": (C.c_size_t, [C.POINTER(SampleCfg)]),
     "mscs_sample_plan": (C.c_int, [C.POINTER(SampleCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -140,15 +140,21 @@ def torch_mt_state():
     """(state uint32[624], pos) of the torch CPU default generator (at::mt19937 layout:
     [seed u64][left i32][seeded i32][next u64][624 x u64] ...)."""
     raw = torch.get_rng_state().numpy()
-    _seed, left, _seeded, nxt = struct.unpack_from("<QiiQ", raw.tobytes()[:24], 0)
+    _last_raw[0] = raw
+    _seed, left, _seeded, nxt = struct.unpack_from("<QiiQ", raw[:24].tobytes(), 0)
     mt = np.ascontiguousarray(raw[24:24 + 8 * _MT_N].view(np.uint64).astype(np.uint32))
     pos = _MT_N if left == 1 else int(nxt)
     return mt, pos
 
 
+_last_raw = [None]      # serialised generator state read by the last torch_mt_state() (seed / header bytes are reused)
+
+
 def _publish_mt_state(mt, pos):
     """Writes (state uint32[624], pos in 1..624) into the torch CPU default generator."""
-    raw = torch.get_rng_state().numpy().copy()
+    raw = _last_raw[0]
+    raw = torch.get_rng_state().numpy().copy() if raw is None else raw.copy()
+    _last_raw[0] = None
     hdr = struct.pack("<ii", 625 - pos, 1)
     raw[8:16] = np.frombuffer(hdr, dtype=np.uint8)
     raw[16:24] = np.frombuffer(struct.pack("<Q", pos), dtype=np.uint8)
@@ -231,10 +237,11 @@ class _StreamCache:
             buf = self.bufs[self.cur]
             if self.key != (mt.tobytes(), pos) or off + _MT_N > self.words:
                 return None
-            self.copy.wait_event(self.ready)
-            with torch.cuda.stream(self.copy):
-                host = buf[off:off + _MT_N].cpu()
-        return host.numpy().view(np.uint32).copy(), newpos
+            host = np.empty(_MT_N, dtype=np.uint32)
+            _lib.check(_lib.load().mscs_read_to_host(host.ctypes.data, buf.data_ptr() + 4 * off, 4 * _MT_N,
+                                                     C.c_void_p(self.ready.cuda_event), C.c_void_p(self.copy.cuda_stream)),
+                       "mscs_read_to_host")
+        return host, newpos
 
     def release_and_prefetch(self, mt_next, pos_next, words):
         if os.environ.get("MSCS_NO_PREFETCH"):      # experiment switch: regenerate inline at the next call
@@ -776,8 +783,12 @@ def run_forward(sp, labels, feats32, needs, comm=None):
                                            (C.c_size_t * 2)(4 * sp.stats_n, 4 * sum(sizes)), 2, st), "mscs_fill_bytes")
         _t = _seg("fwd: alloc + plan kernels", _t)
         gradbufs = _GradBuffers(feats32, needs) if any(needs) else None
-        if gradbufs is not None:      # (started here: overlapping the tensor kernels instead measured slower -- the
-            gradbufs.start_fill()     # fill's CTAs share the SMs with the persistent kernel's epilogue warps)
+        if gradbufs is not None:
+            # Started here, next to the small sampling kernels.  The fill (535 MB at cfg-2) costs ~70 us of step time
+            # WHEREVER it runs: measured next to the sampling kernels (+65 us there), under the forward (+80), under
+            # the backward (+77), and as a device-to-device copy from a persistent zero buffer (worse everywhere) --
+            # memset and D2D copies run on the SMs and take them away from whatever they overlap.
+            gradbufs.start_fill()
         _t = _seg("fwd: grad buffers", _t)
         mt, pos = torch_mt_state()
         draws = _stream_cache(dev).acquire(mt, pos, sp.max_draws + _MT_N)
@@ -811,9 +822,9 @@ def run_forward(sp, labels, feats32, needs, comm=None):
         job.work = work.data_ptr()
         device_driven = not pooled and all(x is not None for x in slots) and sp.v_cap * 12 <= 200 * 1024
         if device_driven:
-            # Selection and gather are driven by the DEVICE plan records and enqueued before the host looks at the
-            # plan: the one host synchronisation of the forward pass then overlaps ~150 us of GPU work instead of
-            # draining the stream (it used to leave the GPU idle for the sync + the host work after it).
+            # Selection, gather AND the similarity forward are driven by the DEVICE plan records and enqueued before
+            # the host looks at the plan: the one host wait of the forward pass (needed to raise the reference's
+            # errors and to size the backward) then overlaps ~0.5 ms of queued GPU work instead of draining the stream.
             _lib.check(lib.mscs_plan_fetch_begin(plan_dev.data_ptr(), S, st), "mscs_plan_fetch_begin")
             _lib.check(lib.mscs_sample_select_async(C.byref(sp.cfg), plan_dev.data_ptr(), sp.v_cap, ws.data_ptr(),
                                                     draws.data_ptr(), *arrs, sarr, st), "mscs_sample_select_async")
@@ -828,7 +839,15 @@ def run_forward(sp, labels, feats32, needs, comm=None):
                 it.anc_bf16, it.anc_f32 = bbase + 2 * sp.boff[s], fbase + 4 * sp.foff[s][0]
                 it.inv_norm = fbase + 4 * sp.foff[s][1]
             _lib.check(lib.mscs_gather_normalize_sectors_batch(items, S, st), "mscs_gather_normalize_sectors_batch")
-        _t = _seg("fwd: job + select + gather", _t)
+        # the similarity forward too: row counts are read on the device, the job carries their upper bounds
+        pbase = plan_dev.data_ptr()
+        for i, (a, k, *_rest) in enumerate(sp.terms):
+            t = job.terms[i]
+            t.N1, t.N2 = sp.Ncap[a], sp.Ncap[k]
+            t.n1_dev, t.n2_dev = pbase + a * plan_sz + 8, pbase + k * plan_sz + 8
+        with _timed("sim_fwd"):
+            _lib.check(lib.mscs_sim_forward(C.byref(job), st), "mscs_sim_forward")
+        _t = _seg("fwd: job + select + gather + sim_forward", _t)
         if HOST_WAIT is not None:
             _t0 = time.perf_counter()
         _lib.check(lib.mscs_plan_fetch_end(plan, S), "mscs_plan_fetch_end")       # the host sync (plan records only)
@@ -876,16 +895,18 @@ def run_forward(sp, labels, feats32, needs, comm=None):
     for i, (a, k, *_rest) in enumerate(sp.terms):      # the only plan-dependent fields of the job
         t = job.terms[i]
         t.N1, t.N2 = samples[a].N, samples[k].N
+        t.n1_dev = t.n2_dev = None          # (the backward is launched with the actual counts)
         if pooled:       # anchor (and key) rows are sharded over the ranks in 128-row granules
             t.row_begin, t.row_end = shard_rows(samples[a].N, comm.world, comm.rank)
             t.krow_begin, t.krow_end = shard_rows(samples[k].N, comm.world, comm.rank)
-    with _timed("sim_fwd"):
-        if not pooled:
-            _lib.check(lib.mscs_sim_forward(C.byref(job), st), "mscs_sim_forward")
-        else:
-            _lib.check(lib.mscs_sim_forward_sweeps(C.byref(job), st), "mscs_sim_forward_sweeps")
-            comm.all_reduce(stats)       # row statistics of all ranks' rows
-            _lib.check(lib.mscs_sim_finalize(C.byref(job), st), "mscs_sim_finalize")
+    if not device_driven:        # (device-driven: already enqueued, before the host waited for the plan)
+        with _timed("sim_fwd"):
+            if not pooled:
+                _lib.check(lib.mscs_sim_forward(C.byref(job), st), "mscs_sim_forward")
+            else:
+                _lib.check(lib.mscs_sim_forward_sweeps(C.byref(job), st), "mscs_sim_forward_sweeps")
+                comm.all_reduce(stats)       # row statistics of all ranks' rows
+                _lib.check(lib.mscs_sim_finalize(C.byref(job), st), "mscs_sim_finalize")
     _t = _seg("fwd: after wait -> sim_forward enqueued", _t)
     # host-side generator bookkeeping, off the GPU's critical path
     if comm is None or comm.owns_rng:

@@ -55,6 +55,17 @@ extern "C" int mscs_device_ok(void) {
   return major == 10;
 }
 
+// Small device -> host read on `stream` (a private copy stream), ordered after `wait_event` (may be NULL), then
+// synchronised: used to read 2.5 KB of generator state back without touching the compute stream.
+extern "C" int mscs_read_to_host(void* dst_host, const void* src_dev, size_t bytes, void* wait_event, void* stream_) {
+  MSCS_CHECK_ARG(dst_host && src_dev && bytes > 0, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (wait_event) MSCS_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)wait_event, 0));
+  MSCS_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, st));
+  MSCS_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
 // Up to four byte-fills in one call (workspace initialisation of a step: statistics = 0, slot map = -1, ...).
 extern "C" int mscs_fill_bytes(void* const* ptrs, const int32_t* values, const size_t* bytes, int count, void* stream_) {
   MSCS_CHECK_ARG(ptrs && values && bytes && count >= 0 && count <= 8, "bad arguments");

@@ -430,6 +430,9 @@ extern "C" int mscs_sim_backward_sets(const mscs_sim_job* job, const float* grad
   int rc = validate_job(job);
   if (rc) return rc;
   MSCS_CHECK_ARG(job->work && grad_out && dF_sets && dF_ld, "null pointer argument");
+  for (int t = 0; t < job->num_terms; ++t)
+    MSCS_CHECK_ARG(!job->terms[t].n1_dev && !job->terms[t].n2_dev,
+                   "term %d: the backward needs the actual row counts in N1 / N2 (n1_dev / n2_dev must be NULL)", t);
   cudaStream_t st = (cudaStream_t)stream_;
   BwdPass passes[MSCS_MAX_PASSES];
   int np = build_passes(job, passes);
@@ -472,7 +475,7 @@ extern "C" int mscs_sim_backward_sets(const mscs_sim_job* job, const float* grad
     args.p[i] = BwdDev{p.row_cls, p.col_seg, p.row_cs, p.row_cpn, p.row_neg, p.col_cs, p.col_cpn, p.col_neg,
                        (const __nv_bfloat16*)p.x_bf16, dF_sets[p.row_set], dF_ld[p.row_set], p.n_rows, p.n_cols,
                        p.self_mask, ym, p.scale_log2, p.out_scale};
-    b.t[i] = BuildTerm{p.row_cls, p.col_seg, p.n_rows, p.n_cols, nitems, p.rb_lo, 0, 1 << 30};
+    b.t[i] = BuildTerm{p.row_cls, p.col_seg, p.n_rows, p.n_cols, nitems, p.rb_lo, 0, 1 << 30, nullptr, nullptr};
     nitems += p.rb_hi - p.rb_lo;
   }
   b.num_terms = np; b.nitems = nitems; b.rows_per_item = 128; b.mode = 0;

@@ -37,6 +37,7 @@ struct FwdTerm {
   float* neg; float* pos; float* ssum;
   int N1, N2, self_mask, a_map, k_map;
   float scale_log2;
+  const int* n1_dev; const int* n2_dev;      // optional device-resident row counts (N1 / N2 are then upper bounds)
 };
 struct FwdArgs {
   alignas(64) CUtensorMap maps[MSCS_MAX_SCALES];
@@ -171,6 +172,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
     uint32_t it = 0;
     while (wk.next(sg)) {
       const FwdTerm& t = args.t[sg.owner];
+      const int tN1 = t.n1_dev ? *t.n1_dev : t.N1, tN2 = t.n2_dev ? *t.n2_dev : t.N2;
       const int cb = sg.rb * kFwdKeys + ch * CPT;          // first key column of this thread's quarter
       const float scale = t.scale_log2;
       // positive key range of each row (and of its 32-row group) comes precomputed from k_row_ranges; the
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
         const uint32_t buf = it & 1;
         if (buf != (uint32_t)grp) continue;
         const int row = rt * 128 + quad * 32 + lane;
-        const bool valid = row < t.N1;
+        const bool valid = row < tN1;
         const int2 n_gr = t.grp_range[rt * 4 + quad];
         const int2 n_rr = valid ? t.row_range[row] : make_int2(0, 0);
         const float negi = (MODE == 1 && valid) ? t.neg[row] : 1.f;
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
         if (args.debug_flags & 1) {
           // experiment: no TMEM reads / math
         } else if (MODE == 0) {
-          if (cb < t.N2) {      // a quarter that lies entirely in the zero padding of the key block has no work
+          if (cb < tN2) {      // a quarter that lies entirely in the zero padding of the key block has no work
             uint32_t va[32], vb[32];
             ptx::tmem_ld32(taddr, va);
             ptx::tmem_ld_wait(va);
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
               if (c4 < NCH - 1) ptx::tmem_ld32(taddr + (c4 + 1) * 32, nxt);
               const int c0 = cb + c4 * 32;
               // 32-column chunk without positives of any row of this warp and inside the key set: no masks
-              const bool fast = (c0 + 32 <= wmin || c0 >= wmax) && (c0 + 32 <= t.N2);
+              const bool fast = (c0 + 32 <= wmin || c0 >= wmax) && (c0 + 32 <= tN2);
               if (args.debug_flags & 8) {               // experiment: TMEM loads only, no math (wrong results)
               } else if (fast && (args.debug_flags & 4)) {      // experiment: no MUFU (wrong results)
 #pragma unroll
@@ -220,12 +222,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
                 // best of {0, 1/4, 3/8, 1/2}; MSCS_DEBUG_FLAGS=16 selects the MUFU-only variant for comparison
                 if (args.debug_flags & 16) fast_chunk<0x00>(cur, scale, acc0, acc1, acc2, acc3);
                 else fast_chunk<0x88>(cur, scale, acc0, acc1, acc2, acc3);
-              } else if (c0 < t.N2) {
+              } else if (c0 < tN2) {
 #pragma unroll
                 for (int c = 0; c < 32; ++c) {
                   const int col = c0 + c;
                   const float e = ptx::ex2(__uint_as_float(cur[c]) * scale);
-                  const bool isneg = ((unsigned)(col - p0) >= plen) && (col < t.N2);
+                  const bool isneg = ((unsigned)(col - p0) >= plen) && (col < tN2);
                   acc0 += isneg ? e : 0.f;
                 }
               }
@@ -275,14 +277,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
 
 // per anchor row: positive key range [k_seg[y], k_seg[y+1]); per 32-row group: the union (groups are
 // padded to whole 128-row tiles so the epilogue can index them by tile)
-struct RangeTerm { const int* a_cls; const int* k_seg; int2* row_range; int2* grp_range; int N1; };
+struct RangeTerm { const int* a_cls; const int* k_seg; int2* row_range; int2* grp_range; int N1; const int* n1_dev; };
 struct RangeArgs { RangeTerm t[MSCS_MAX_TERMS]; };
 __global__ void __launch_bounds__(256) k_row_ranges(const __grid_constant__ RangeArgs a) {
   const RangeTerm& t = a.t[blockIdx.y];
   const int r = blockIdx.x * 256 + threadIdx.x;
-  if (blockIdx.x * 256 >= (t.N1 + 127) / 128 * 128) return;
+  const int tN1 = t.n1_dev ? *t.n1_dev : t.N1;
+  if (blockIdx.x * 256 >= (tN1 + 127) / 128 * 128) return;
   int p0 = 0x7fffffff, p1 = 0;
-  if (r < t.N1) {
+  if (r < tN1) {
     const int y = t.a_cls[r];
     p0 = t.k_seg[y]; p1 = t.k_seg[y + 1];
     t.row_range[r] = make_int2(p0, p1);
@@ -292,7 +295,7 @@ __global__ void __launch_bounds__(256) k_row_ranges(const __grid_constant__ Rang
     p0 = min(p0, __shfl_xor_sync(0xffffffffu, p0, o));
     p1 = max(p1, __shfl_xor_sync(0xffffffffu, p1, o));
   }
-  if ((threadIdx.x & 31) == 0 && r < (t.N1 + 127) / 128 * 128) t.grp_range[r >> 5] = make_int2(p0, p1);
+  if ((threadIdx.x & 31) == 0 && r < (tN1 + 127) / 128 * 128) t.grp_range[r >> 5] = make_int2(p0, p1);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -312,9 +315,12 @@ __global__ void __launch_bounds__(1024) k_build_work(const __grid_constant__ Bui
       for (int q = 1; q < a.num_terms; ++q) if (i >= a.t[q].item_base) ti = q;
       const BuildTerm& t = a.t[ti];
       const int rb = t.blk_lo + i - t.item_base;
-      int ct0 = 0, ct1 = (t.N2 + kTileN - 1) / kTileN;
-      if (a.mode == 1) {
-        const int r0 = rb * a.rows_per_item, r1 = min(t.N1, r0 + a.rows_per_item) - 1;
+      const int tN1 = t.n1_dev ? *t.n1_dev : t.N1, tN2 = t.n2_dev ? *t.n2_dev : t.N2;
+      int ct0 = 0, ct1 = (tN2 + kTileN - 1) / kTileN;
+      if (rb * a.rows_per_item >= tN1) {      // block beyond the actual row count (items are sized by the upper bound)
+        ct0 = ct1 = 0;
+      } else if (a.mode == 1) {
+        const int r0 = rb * a.rows_per_item, r1 = min(tN1, r0 + a.rows_per_item) - 1;
         const int p0 = t.k_seg[t.a_cls[r0]], p1 = t.k_seg[t.a_cls[r1] + 1];
         if (p1 > p0) { ct0 = p0 / kTileN; ct1 = (p1 + kTileN - 1) / kTileN; } else { ct0 = ct1 = 0; }
       }
@@ -410,6 +416,22 @@ extern "C" size_t mscs_sim_workspace_bytes(const mscs_sim_job* job) {
   return 2 * 4096 + ranges + items * (sizeof(WorkItem) + sizeof(int)) + 16 * 64;
 }
 
+// debug timeline (MSCS_FWD_TIMELINE=1): events after each launch of the last forward call
+static cudaEvent_t g_tl[8];
+static int g_tl_n = 0;
+static bool g_tl_on = false;
+static void tl_mark(cudaStream_t st) {
+  if (!g_tl_on || g_tl_n >= 8) return;
+  if (!g_tl[g_tl_n]) cudaEventCreate(&g_tl[g_tl_n]);
+  cudaEventRecord(g_tl[g_tl_n++], st);
+}
+extern "C" int mscs_debug_fwd_timeline(float* ms_out, int max_n) {
+  cudaDeviceSynchronize();
+  int n = 0;
+  for (int i = 1; i < g_tl_n && n < max_n; ++i, ++n) cudaEventElapsedTime(&ms_out[n], g_tl[i - 1], g_tl[i]);
+  return n;
+}
+
 extern "C" int mscs_sim_forward_sweeps(const mscs_sim_job* job, void* stream_) {
   int rc = validate_job(job);
   if (rc) return rc;
@@ -417,6 +439,9 @@ extern "C" int mscs_sim_forward_sweeps(const mscs_sim_job* job, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   FwdArgs args{};
   if (const char* e = getenv("MSCS_DEBUG_FLAGS")) args.debug_flags = atoi(e);
+  g_tl_on = getenv("MSCS_FWD_TIMELINE") != nullptr;
+  g_tl_n = 0;
+  tl_mark(st);
   // one tensor map per distinct operand matrix
   const void* bases[MSCS_MAX_SCALES]; int nmaps = 0;
   auto map_of = [&](const void* base, int rows) -> int {
@@ -437,18 +462,20 @@ extern "C" int mscs_sim_forward_sweeps(const mscs_sim_job* job, void* stream_) {
     MSCS_CHECK_ARG(am >= 0 && km >= 0, "too many distinct operand matrices");
     int2* rr = (int2*)w; w += align_up(sizeof(int2) * (size_t)m.N1, 64);
     int2* gr = (int2*)w; w += align_up(sizeof(int2) * (size_t)ceil_div(m.N1, 128) * 4, 64);
-    ra.t[t] = RangeTerm{m.a_cls, m.k_seg, rr, gr, m.N1};
+    ra.t[t] = RangeTerm{m.a_cls, m.k_seg, rr, gr, m.N1, m.n1_dev};
     if (m.N1 > maxN1) maxN1 = m.N1;
     args.t[t] = FwdTerm{m.a_cls, m.k_seg, rr, gr, m.neg_sum, m.pos_sum, m.s_sum, m.N1, m.N2, m.self_mask, am, km,
-                        kLog2e / m.temperature};
+                        kLog2e / m.temperature, m.n1_dev, m.n2_dev};
     // blocks are on the KEY side (256 keys), the streamed 128-row tiles on the ANCHOR side
     const bool all_rows = m.row_begin == 0 && m.row_end == 0;     // 0,0 = every row; begin == end = none
     const int r_lo = all_rows ? 0 : m.row_begin, r_hi = all_rows ? m.N1 : m.row_end;
-    b.t[t] = BuildTerm{m.k_cls, m.a_seg, m.N2, m.N1, nitems, 0, r_lo / 128, r_hi > r_lo ? ceil_div(r_hi, 128) : r_lo / 128};
+    b.t[t] = BuildTerm{m.k_cls, m.a_seg, m.N2, m.N1, nitems, 0, r_lo / 128, r_hi > r_lo ? ceil_div(r_hi, 128) : r_lo / 128,
+                       m.n2_dev, m.n1_dev};      // (blocks are on the key side: rows = keys)
     nitems += ceil_div(m.N2, kFwdKeys);
   }
   k_row_ranges<<<dim3(ceil_div(maxN1 + 127, 256), job->num_terms), 256, 0, st>>>(ra);
   MSCS_LAUNCH_CHECK();
+  tl_mark(st);
   b.num_terms = job->num_terms; b.nitems = nitems; b.rows_per_item = kFwdKeys;
   b.pad = 0;      // start-up charge of a key block (128 KB load + pipeline fill), in anchor tiles
   if (const char* e = getenv("MSCS_FWD_PAD")) b.pad = atoi(e);
@@ -458,6 +485,7 @@ extern "C" int mscs_sim_forward_sweeps(const mscs_sim_job* job, void* stream_) {
     b.prefix = (int*)w;     w += align_up(sizeof(int) * (size_t)(nitems + 1), 64);
     rc = launch_build_work(b, st);
     if (rc) return rc;
+    tl_mark(st);
     args.work = WorkTable{b.items, b.prefix, nitems, b.pad};
     switch (job->C_pad / 64) {
       case 1: rc = launch_fwd<1>(args, mode, st); break;
@@ -466,6 +494,7 @@ extern "C" int mscs_sim_forward_sweeps(const mscs_sim_job* job, void* stream_) {
       default: rc = launch_fwd<4>(args, mode, st); break;
     }
     if (rc) return rc;
+    tl_mark(st);
   }
   return 0;
 }
@@ -480,7 +509,9 @@ extern "C" int mscs_sim_finalize(const mscs_sim_job* job, void* stream_) {
 extern "C" int mscs_sim_forward(const mscs_sim_job* job, void* stream_) {
   int rc = mscs_sim_forward_sweeps(job, stream_);
   if (rc) return rc;
-  return launch_finalize(job, (cudaStream_t)stream_);
+  rc = launch_finalize(job, (cudaStream_t)stream_);
+  tl_mark((cudaStream_t)stream_);
+  return rc;
 }
 
 // debug: read and reset the barrier wait profile of this translation unit (ns and count per tag % 32)

@@ -55,7 +55,9 @@ struct Walker {
 };
 
 // work-table builder (sim_fwd.cu): one item per (owner, row block)
-struct BuildTerm { const int* a_cls; const int* k_seg; int N1, N2, item_base, blk_lo, ct_lo, ct_hi; };
+// n1_dev / n2_dev: optional device-resident row counts (then N1 / N2 are upper bounds, see mscs_term)
+struct BuildTerm { const int* a_cls; const int* k_seg; int N1, N2, item_base, blk_lo, ct_lo, ct_hi;
+                   const int* n1_dev; const int* n2_dev; };
 struct BuildArgs { BuildTerm t[MSCS_MAX_PASSES]; int num_terms, nitems, rows_per_item, mode, pad; WorkItem* items; int* prefix; };
 int launch_build_work(const BuildArgs& b, cudaStream_t st);
 int trap_buffer_device_ptr(unsigned long long** out);

@@ -12,6 +12,7 @@ struct FinTerm {
   const float* neg; const float* pos; const float* ssum;
   float* coef_s; float* coef_pn;
   int N1, self_mask; float weight;
+  const int* n1_dev;      // optional device-resident row count
 };
 struct FinArgs { FinTerm t[MSCS_MAX_TERMS]; int num_terms; float* term_loss; float* total_loss; };
 
@@ -23,17 +24,18 @@ __global__ void __launch_bounds__(256) k_finalize_rows(const __grid_constant__ F
   __shared__ double red[8];
   double part = 0.0;
   const int base = blockIdx.x * 1024;
-  if (base >= t.N1) return;
+  const int tN1 = t.n1_dev ? *t.n1_dev : t.N1;
+  if (base >= tN1) return;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int i = base + k * 256 + threadIdx.x;
-    if (i < t.N1) {
+    if (i < tN1) {
       const int y = t.a_cls[i];
       const int P = t.k_seg[y + 1] - t.k_seg[y] - (t.self_mask ? 1 : 0);
       // single-scale: 0/0 -> NaN exactly like the reference; cross-scale: divisor max(P,1)
       const float div = t.self_mask ? (float)P : (float)max(P, 1);
       part += (double)(-t.pos[i] / div);
-      const float invd = 1.f / (div * (float)t.N1);
+      const float invd = 1.f / (div * (float)tN1);
       t.coef_s[i] = t.ssum[i] * invd;
       t.coef_pn[i] = t.neg[i] * invd;
     }
@@ -54,7 +56,7 @@ __global__ void k_finalize_total(const __grid_constant__ FinArgs a, const double
   double total = 0.0;
   bool bad = false;
   for (int ti = 0; ti < a.num_terms; ++ti) {
-    const float l = (float)(acc[ti] / (double)a.t[ti].N1);
+    const float l = (float)(acc[ti] / (double)(a.t[ti].n1_dev ? *a.t[ti].n1_dev : a.t[ti].N1));
     a.term_loss[ti] = l;
     bad = bad || !isfinite(l);
     total += (double)a.t[ti].weight * (double)l;
@@ -73,7 +75,7 @@ int launch_finalize(const mscs_sim_job* job, cudaStream_t st) {
   for (int t = 0; t < job->num_terms; ++t) {
     const mscs_term& m = job->terms[t];
     a.t[t] = FinTerm{m.a_cls, m.k_seg, m.neg_sum, m.pos_sum, m.s_sum, m.coef_s, m.coef_pn, m.N1, m.self_mask,
-                     m.weight};
+                     m.weight, m.n1_dev};
     if (m.N1 > maxN) maxN = m.N1;
   }
   double* acc = (double*)job->work;

@@ -43,9 +43,14 @@ int mscs_debug_wait_profile_bwd(unsigned long long* ns_out, unsigned long long* 
 /* debug (library built with -DMSCS_TRACE only, otherwise returns 0): copy out and reset the event trace of
    the backward tensor kernel -- clock64 values of one CTA, indexed [4 slots][256 tiles][8 events]. */
 int mscs_debug_trace_bwd(unsigned long long* out, int max_events);
+/* debug (MSCS_FWD_TIMELINE set in the environment): milliseconds between the launches of the last forward call
+   (row ranges, work table 0, sweep 0, work table 1, sweep 1); returns the number of intervals */
+int mscs_debug_fwd_timeline(float* ms_out, int max_n);
 /* 1 if a CUDA device with compute capability 10.x is present */
 int mscs_device_ok(void);
 /* up to 8 asynchronous byte fills in one call (per-step workspace initialisation: statistics = 0, slot maps = 0xFF) */
+/* small device->host read on `stream`, ordered after `wait_event` (cudaEvent_t or NULL), synchronised before return */
+int mscs_read_to_host(void* dst_host, const void* src_dev, size_t bytes, void* wait_event, void* stream);
 int mscs_fill_bytes(void* const* ptrs, const int32_t* values, const size_t* bytes, int count, void* stream);
 
 /* ---------------------------------------------------------------------------------------
@@ -192,6 +197,10 @@ typedef struct {
   float* s_sum;     /* sum_j pos 1/(e^l_ij + neg_i)     (backward) */
   float* coef_s;    /* out: S_i/(div_i N1)  */
   float* coef_pn;   /* out: neg_i/(div_i N1) */
+  /* Optional (forward calls only): the row counts live in DEVICE memory (e.g. &plan_dev[s].N).  N1 / N2 above are
+   * then UPPER BOUNDS (they size grids, work tables and tensor maps) and the kernels read the actual counts, so the
+   * forward can be enqueued before the host has seen the sampling plan.  NULL = N1 / N2 are the actual counts. */
+  const int32_t* n1_dev; const int32_t* n2_dev;
 } mscs_term;
 
 typedef struct {

@@ -29,7 +29,7 @@ def test_struct_layouts_match_header():
     # sizes the C side uses (checked against the header by reading the field lists)
     assert ctypes.sizeof(_lib.ScalePlan) == 48
     assert ctypes.sizeof(_lib.SampleCfg) == 4 * 4 + 2 * 8 * 4 + 6 * 4
-    assert ctypes.sizeof(_lib.Term) == 6 * 8 + 4 * 4 + 2 * 4 + 2 * 4 + 4 * 4 + 5 * 8
+    assert ctypes.sizeof(_lib.Term) == 6 * 8 + 4 * 4 + 2 * 4 + 2 * 4 + 4 * 4 + 5 * 8 + 2 * 8      # + n1_dev, n2_dev
 
 
 def test_mt_advance_host_matches_torch():

@@ -42,3 +42,14 @@ _ops.TIMING = {}
 for _ in range(30): step()
 torch.cuda.synchronize()
 print(os.environ.get("MSCS_DEBUG_FLAGS", "0"), {k: round(sum(a.elapsed_time(b) for a, b in v) / len(v), 4) for k, v in _ops.TIMING.items()})
+
+if os.environ.get("MSCS_FWD_TIMELINE"):
+    import ctypes, numpy as np
+    from mscs_b200 import _lib
+    buf = np.zeros(8, np.float32)
+    acc = np.zeros(8)
+    for _ in range(10):
+        step()
+        n = _lib.load().mscs_debug_fwd_timeline(buf.ctypes.data, 8)
+        acc[:n] += buf[:n]
+    print("forward timeline (us): row_ranges, work0, sweep0, work1, sweep1, finalise =", [round(float(x) * 100, 1) for x in acc[:n]])
