@@ -782,7 +782,10 @@ def run_forward(sp, labels, feats32, needs, comm=None):
             _lib.check(lib.mscs_fill_bytes(_lib.ptr_array([sb + so["stats"], sb + so["slot"]]), (C.c_int32 * 2)(0, 0xFF),
                                            (C.c_size_t * 2)(4 * sp.stats_n, 4 * sum(sizes)), 2, st), "mscs_fill_bytes")
         _t = _seg("fwd: alloc + plan kernels", _t)
-        gradbufs = _GradBuffers(feats32, needs) if any(needs) else None
+        # dense gradients: pre-zeroed on a side stream, sampled sectors rewritten by the backward (MSCS_DENSE=1: the
+        # backward writes them in one streaming pass instead -- measured equal, see gather.cu)
+        gradbufs = _GradBuffers(feats32, needs) if (any(needs) and (pooled or os.environ.get("MSCS_DENSE") != "1")) \
+            else None
         if gradbufs is not None:
             # Started here, next to the small sampling kernels.  The fill (535 MB at cfg-2) costs ~70 us of step time
             # WHEREVER it runs: measured next to the sampling kernels (+65 us there), under the forward (+80), under
@@ -964,6 +967,32 @@ def run_backward(state, grad_out, needs, shapes, dtypes):
                 handles[s] = comm.all_gather_blocks_async(rows, per * sp.C_pad)
     grads = []
     fbase = state.fslab.data_ptr()
+    dense = state.comm is None and state.gradbufs is None and \
+        all((not needs[s]) or (state.slots[s] is not None) for s in range(S))
+    if dense:
+        with _timed("scatter"):
+            idx = [s for s in range(S) if needs[s]]
+            sizes = [shapes[s][0] * shapes[s][1] * shapes[s][2] * shapes[s][3] for s in idx]
+            mask_words = sum((shapes[s][0] * shapes[s][2] * shapes[s][3] + 31) // 32 for s in idx)
+            slab = torch.empty(sum(sizes) + mask_words, dtype=torch.float32, device=dev)    # gradients | pixel mask
+            items = (_lib.ScatterItem * len(idx))()
+            rows = (C.c_int32 * len(idx))()
+            outs, off = {}, 0
+            for j, s in enumerate(idx):
+                n, Cc, h, w = shapes[s]
+                outs[s] = slab[off:off + sizes[j]].view(shapes[s])
+                it = items[j]
+                it.dF, it.ldF, it.anc_f32, it.inv_norm = ptrs[s], sp.C_pad, fbase + 4 * sp.foff[s][0], fbase + 4 * sp.foff[s][1]
+                it.slot, it.n, it.C, it.plane = state.slots[s].data_ptr(), n, Cc, h * w
+                it.dfeat = slab.data_ptr() + 4 * off
+                rows[j] = state.samples[s].N
+                off += sizes[j]
+            if idx:
+                _lib.check(lib.mscs_scatter_dense_batch(items, rows, len(idx), slab.data_ptr() + 4 * sum(sizes), st),
+                           "mscs_scatter_dense_batch")
+            grads = [None if not needs[s] else (outs[s] if dtypes[s] == torch.float32 else outs[s].to(dtypes[s]))
+                     for s in range(S)]
+        return grads
     with _timed("scatter"):
         gb = state.gradbufs
         if gb is not None:

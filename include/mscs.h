@@ -259,6 +259,12 @@ typedef struct {
   int32_t n, C, plane; float* dfeat;
 } mscs_scatter_item;
 int mscs_scatter_sectors_batch(const mscs_scatter_item* items, int count, void* stream);
+/* Dense gradients of every scale written in ONE streaming pass, zeros included (no pre-zeroed buffer needed):
+ * dF rows are first turned into dx rows IN PLACE (rows[s] rows of item s), then every float4 of every dfeat is
+ * written once.  plane must be a multiple of 4.  mask_scratch: sum over items of ceil(n*plane/32) uint32 words
+ * (one bit per pixel: sampled or not, built inside the call). */
+int mscs_scatter_dense_batch(const mscs_scatter_item* items, const int32_t* rows, int count, uint32_t* mask_scratch,
+                             void* stream);
 
 #ifdef __cplusplus
 }
