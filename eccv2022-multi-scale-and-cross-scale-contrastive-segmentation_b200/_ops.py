@@ -704,6 +704,19 @@ def _step_plan(dev, label_shape, feat_shapes, spec, single_scale, world=1, rank=
     return p
 
 
+_hp_streams = {}
+
+
+def _hp_stream(dev):
+    """High-priority stream for the small, latency-bound sampling kernels: the 535 MB zero fill of the dense
+    gradients runs concurrently on a default-priority side stream, and with equal priorities its ~100k blocks
+    queue in front of them (+65 us on the sampling stage at cfg-2)."""
+    st = _hp_streams.get(dev)
+    if st is None:
+        st = _hp_streams[dev] = torch.cuda.Stream(device=dev, priority=-1)
+    return st
+
+
 class _StepState:
     """Buffers of one call (kept alive for the backward)."""
     pass
@@ -738,10 +751,20 @@ def run_forward(sp, labels, feats32, needs, comm=None):
         slab = torch.empty(sp.slab_bytes, dtype=u8, device=dev)
         sb, so = slab.data_ptr(), sp.slab_off
         ws, plan_dev = _Ptr(sb + so["ws"]), _Ptr(sb + so["plan"])
+    # device-driven order (selection, gather and similarity forward enqueued before the host sees the plan): single
+    # process, every plane a multiple of 8 pixels (slot maps), selection smem within limits
+    device_driven = not pooled and all(x != 0 for x in sp.slot_sizes) and sp.v_cap * 12 <= 200 * 1024
+    hp = _hp_stream(dev) if (device_driven and os.environ.get("MSCS_HP", "1") != "0") else None
+    st_s = st                      # stream of the sampling kernels
+    if hp is not None:
+        hp.wait_stream(_cur_stream())
+        slab.record_stream(hp)
+        labels.record_stream(hp)
+        st_s = C.c_void_p(hp.cuda_stream)
     with _timed("sample"):
         if not pooled:
             _lib.check(lib.mscs_sample_plan(C.byref(sp.cfg), labels.data_ptr(), ws.data_ptr(), plan_dev.data_ptr(),
-                                            st), "mscs_sample_plan")
+                                            st_s), "mscs_sample_plan")
         else:
             # local histograms -> all-gather of the (image, class) counts -> identical global plan on every rank
             _lib.check(lib.mscs_sample_hist(C.byref(sp.cfg), labels.data_ptr(), ws.data_ptr(), st), "mscs_sample_hist")
@@ -780,7 +803,7 @@ def run_forward(sp, labels, feats32, needs, comm=None):
                 slots.append(_Ptr(off) if x else None)
                 off += 4 * x
             _lib.check(lib.mscs_fill_bytes(_lib.ptr_array([sb + so["stats"], sb + so["slot"]]), (C.c_int32 * 2)(0, 0xFF),
-                                           (C.c_size_t * 2)(4 * sp.stats_n, 4 * sum(sizes)), 2, st), "mscs_fill_bytes")
+                                           (C.c_size_t * 2)(4 * sp.stats_n, 4 * sum(sizes)), 2, st_s), "mscs_fill_bytes")
         _t = _seg("fwd: alloc + plan kernels", _t)
         # dense gradients: pre-zeroed on a side stream, sampled sectors rewritten by the backward (MSCS_DENSE=1: the
         # backward writes them in one streaming pass instead -- measured equal, see gather.cu)
@@ -795,6 +818,8 @@ def run_forward(sp, labels, feats32, needs, comm=None):
         _t = _seg("fwd: grad buffers", _t)
         mt, pos = torch_mt_state()
         draws = _stream_cache(dev).acquire(mt, pos, sp.max_draws + _MT_N)
+        if hp is not None:
+            hp.wait_event(_stream_cache(dev).ready)
         _t = _seg("fwd: rng state + stream acquire", _t)
         plan = (_lib.ScalePlan * S)()
         ibase = islab.data_ptr()
@@ -823,14 +848,15 @@ def run_forward(sp, labels, feats32, needs, comm=None):
         nt = len(sp.terms)
         job.term_loss, job.total_loss = mbase + 4 * sp.out_off, mbase + 4 * (sp.out_off + nt)
         job.work = work.data_ptr()
-        device_driven = not pooled and all(x is not None for x in slots) and sp.v_cap * 12 <= 200 * 1024
         if device_driven:
             # Selection, gather AND the similarity forward are driven by the DEVICE plan records and enqueued before
             # the host looks at the plan: the one host wait of the forward pass (needed to raise the reference's
             # errors and to size the backward) then overlaps ~0.5 ms of queued GPU work instead of draining the stream.
-            _lib.check(lib.mscs_plan_fetch_begin(plan_dev.data_ptr(), S, st), "mscs_plan_fetch_begin")
+            _lib.check(lib.mscs_plan_fetch_begin(plan_dev.data_ptr(), S, st_s), "mscs_plan_fetch_begin")
             _lib.check(lib.mscs_sample_select_async(C.byref(sp.cfg), plan_dev.data_ptr(), sp.v_cap, ws.data_ptr(),
-                                                    draws.data_ptr(), *arrs, sarr, st), "mscs_sample_select_async")
+                                                    draws.data_ptr(), *arrs, sarr, st_s), "mscs_sample_select_async")
+        if hp is not None:
+            _cur_stream().wait_stream(hp)
     if device_driven:
         with _timed("gather"):
             items = (_lib.GatherItem * S)()
