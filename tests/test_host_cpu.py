@@ -86,3 +86,29 @@ def test_workspace_queries_and_arg_validation():
     cfg.fw[0] = 256                      # wider than the label map
     assert lib.mscs_sample_workspace_bytes(ctypes.byref(cfg)) == 0
     assert b"wider" in lib.mscs_last_error()
+
+
+def test_step_plan_slab_layout():
+    """The single allocation of a forward call (_StepPlan.slab_off): parts are 256-byte aligned, do not overlap, and
+    are large enough for the upper bounds they are sized by."""
+    import ctypes
+    import torch
+    from mscs_b200 import _lib, _ops
+    spec = _ops.LossSpec(num_classes=20, temperature=0.1, cs_temperature=0.1, max_views=2500, max_total=10000,
+                         weights=[1.0, 0.7, 0.4, 0.1], cross_scale=True)
+    shapes = [(12, 256, 128, 256), (12, 256, 64, 128), (12, 256, 32, 64), (12, 256, 16, 32)]
+    sp = _ops._StepPlan(torch.device("cpu"), (12, 512, 1024), shapes, spec, False)
+    sizes = {"ws": sp.ws_bytes, "plan": 4 * ctypes.sizeof(_lib.ScalePlan), "work": sp.work_bytes, "stats": 4 * sp.stats_n,
+             "misc": 4 * sp.misc_n, "fslab": 4 * sp.fslab_n, "islab": 4 * sp.islab_n, "slot": 4 * sum(sp.slot_sizes),
+             "bslab": 2 * sp.bslab_n}
+    spans = sorted((sp.slab_off[k], sp.slab_off[k] + v, k) for k, v in sizes.items())
+    for (b0, e0, k0), (b1, e1, k1) in zip(spans, spans[1:]):
+        assert e0 <= b1, (k0, k1)
+    assert all(b % 256 == 0 for b, _, _ in spans) and spans[-1][1] <= sp.slab_bytes
+    assert sp.v_cap == 2500 and sp.Ncap == [10000, 10000, 10000, 12 * 16 * 32]      # N <= min(max_features_total, pixels)
+    assert len(sp.terms) == 6 and sp.cs_logged == [4, 5]              # 4 ms terms + cs(0,3) + cs(0,2)   (_ms.py:62-80)
+    assert sp.slot_sizes == [12 * 128 * 256, 12 * 64 * 128, 12 * 32 * 64, 12 * 16 * 32]
+    # a plane that is not a multiple of 8 pixels has no slot map (general scatter path)
+    sp2 = _ops._StepPlan(torch.device("cpu"), (2, 60, 100), [(2, 32, 15, 25)], spec, True)
+    assert sp2.slot_sizes == [0]
+    assert _ops.LAUNCHES_PER_STEP(4, False) == 16

@@ -58,7 +58,18 @@ def _worker(rank, world, port, out):
     allc = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(allc, mine)
     ok_gather = all(int(allc[r][0, 0]) == r for r in range(world))
-    out[rank] = (ok_stats, ok_cover, ok_gather)
+    # gradient rows: every rank holds the complete rows of its 128-aligned block; the product exchanges them with an
+    # in-place block all-gather (TorchDistComm.all_gather_blocks_async) instead of an all-reduce of a zero-filled buffer
+    from mscs_b200 import TorchDistComm
+    comm = TorchDistComm()
+    Cp = 8
+    per = ((N + 127) // 128 + world - 1) // world * 128
+    rows_full = torch.from_numpy(rng.randn(world * per, Cp)).float()          # same on every rank (same seed)
+    buf = torch.zeros(world * per * Cp + 3 * Cp)                               # slack like the dF slab
+    buf[rank * per * Cp:(rank + 1) * per * Cp] = rows_full[rank * per:(rank + 1) * per].reshape(-1)
+    comm.all_gather_blocks_async(buf[:world * per * Cp], per * Cp).wait()
+    ok_blocks = torch.equal(buf[:world * per * Cp], rows_full.reshape(-1)) and float(buf[world * per * Cp:].abs().max()) == 0.0
+    out[rank] = (ok_stats, ok_cover, ok_gather and ok_blocks)
     dist.destroy_process_group()
 
 
