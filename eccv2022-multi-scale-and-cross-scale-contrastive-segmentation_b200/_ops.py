@@ -684,6 +684,7 @@ class _StepPlan:
             self.slab_off[name] = off
             off += (nbytes + 255) // 256 * 256
         self.slab_bytes = off
+        self.ws_pool = []           # reusable _Workspace objects of the single-process fast path
         self.dF_off, off = [], 0
         for s in range(S):
             self.dF_off.append(off)
@@ -717,11 +718,6 @@ def _hp_stream(dev):
     return st
 
 
-class _StepState:
-    """Buffers of one call (kept alive for the backward)."""
-    pass
-
-
 class _Ptr:
     """Address inside a slab (quacks like a tensor for data_ptr()): a torch view costs a few microseconds of
     Python each and most buffers of a step are only ever passed to the library as raw pointers."""
@@ -734,37 +730,205 @@ class _Ptr:
         return self.p
 
 
+def _raise_plan_errors(plan, S, spec):
+    for s in range(S):
+        if plan[s].error == 1:   # reference: torch.min() of an empty tensor raises (V2.py:110)
+            raise RuntimeError(f"scale {s}: no (image, class) pair has >= min_views_per_class="
+                               f"{spec.min_views} pixels (the reference raises here too, V2.py:110)")
+        if plan[s].error == 2:   # reference: 0-d squeeze then .shape[0] raises (V2.py:119-121)
+            raise IndexError(f"scale {s}: a kept class has a single pixel (the reference raises here too)")
+
+
+def _fill_job(job, sp, A, bbase, ibase, sbase, cbase, work_ptr):
+    """Everything of the similarity job that follows from the slab layouts (sized by upper bounds)."""
+    job.num_terms, job.C_pad, job.num_classes = len(sp.terms), sp.C_pad, A
+    for i, (a, k, self_mask, weight, tau, need_dk) in enumerate(sp.terms):
+        t = job.terms[i]
+        t.a_bf16, t.k_bf16 = bbase + 2 * sp.boff[a], bbase + 2 * sp.boff[k]
+        t.a_cls, t.k_seg = ibase + 4 * sp.ioff[a][3], ibase + 4 * sp.ioff[k][4]
+        t.k_cls, t.a_seg = ibase + 4 * sp.ioff[k][3], ibase + 4 * sp.ioff[a][4]
+        t.self_mask, t.need_dk = int(self_mask), int(need_dk)
+        t.temperature, t.weight, t.a_set, t.k_set = tau, weight, a, k
+        n1 = (sp.Ncap[a] + 15) // 16 * 16
+        t.neg_sum = sbase + 4 * sp.soff[i]
+        t.pos_sum = sbase + 4 * (sp.soff[i] + n1)
+        t.s_sum = sbase + 4 * (sp.soff[i] + 2 * n1)
+        t.coef_s = cbase + 4 * sp.coff[i]
+        t.coef_pn = cbase + 4 * (sp.coff[i] + n1)
+    job.work = work_ptr
+
+
+class _Workspace:
+    """Reusable device workspace of the single-process fast path, with every ctypes structure that depends only on
+    its addresses built ONCE: the two similarity jobs (forward: upper bounds + device-resident row counts; backward:
+    actual counts), the index-array pointer tables, the gather items, the byte-fill lists.  A call takes one from the
+    pool of its step plan and the call's state gives it back when it dies (after the backward, or when the module
+    replaces ``last_state``), so steady-state training ping-pongs between two of them and does no per-call slab
+    allocation or structure filling.  The scalars handed to the caller live in a fresh tensor per call."""
+
+    def __init__(self, sp):
+        dev, S, A = sp.dev, sp.S, sp.A
+        self.slab = slab = torch.empty(sp.slab_bytes, dtype=torch.uint8, device=dev)
+        sb, so = slab.data_ptr(), sp.slab_off
+        self.islab = slab[so["islab"]:so["islab"] + 4 * sp.islab_n].view(torch.int32)
+        self.stats = slab[so["stats"]:so["stats"] + 4 * sp.stats_n].view(torch.float32)
+        self.ws, self.plan_dev = sb + so["ws"], sb + so["plan"]
+        self.fbase, self.bbase = sb + so["fslab"], sb + so["bslab"]
+        self.fslab = _Ptr(self.fbase)
+        self.slots, off = [], sb + so["slot"]
+        for x in sp.slot_sizes:
+            self.slots.append(_Ptr(off) if x else None)
+            off += 4 * x
+        ibase = self.islab.data_ptr()
+        self.arrs = [_lib.ptr_array([ibase + 4 * sp.ioff[s][k] for s in range(S)]) for k in range(5)]
+        self.sarr = _lib.ptr_array([x.data_ptr() if x is not None else 0 for x in self.slots])
+        self.fill_ptrs = _lib.ptr_array([sb + so["stats"], sb + so["slot"]])
+        self.fill_vals = (C.c_int32 * 2)(0, 0xFF)
+        self.fill_bytes = (C.c_size_t * 2)(4 * sp.stats_n, 4 * sum(sp.slot_sizes))
+        plan_sz = C.sizeof(_lib.ScalePlan)
+        self.job_fwd, self.job_bwd = _lib.SimJob(), _lib.SimJob()
+        for job in (self.job_fwd, self.job_bwd):
+            _fill_job(job, sp, A, self.bbase, ibase, sb + so["stats"], sb + so["misc"], sb + so["work"])
+        for i, (a, k, *_rest) in enumerate(sp.terms):
+            t = self.job_fwd.terms[i]
+            t.N1, t.N2 = sp.Ncap[a], sp.Ncap[k]
+            t.n1_dev, t.n2_dev = self.plan_dev + a * plan_sz + 8, self.plan_dev + k * plan_sz + 8
+        self.gitems = (_lib.GatherItem * S)()
+        for s in range(S):
+            n, Cc, h, w = sp.feat_shapes[s]
+            it = self.gitems[s]
+            it.n, it.C, it.plane = n, Cc, h * w
+            it.slot, it.n_rows_dev = self.slots[s].data_ptr(), self.plan_dev + s * plan_sz + 8
+            it.anc_bf16, it.anc_f32 = self.bbase + 2 * sp.boff[s], self.fbase + 4 * sp.foff[s][0]
+            it.inv_norm = self.fbase + 4 * sp.foff[s][1]
+        self.plan = (_lib.ScalePlan * S)()
+        self.last_stream = None
+
+
+class _StepState:
+    """Buffers of one call (kept alive for the backward)."""
+    entry = None
+
+    def __del__(self):
+        e, self.entry = self.entry, None
+        if e is not None:
+            self.sp.ws_pool.append(e)
+
+
 def run_forward(sp, labels, feats32, needs, comm=None):
+    pooled = comm is not None and comm.world > 1
+    # device-driven order (selection, gather and similarity forward enqueued before the host sees the plan): single
+    # process, every plane a multiple of 8 pixels (slot maps), selection shared memory within limits
+    if not pooled and all(x != 0 for x in sp.slot_sizes) and sp.v_cap * 12 <= 200 * 1024:
+        return _run_forward_fast(sp, labels, feats32, needs)
+    return _run_forward_general(sp, labels, feats32, needs, comm, pooled)
+
+
+def _finish_rng(sp, dev, mt, pos, total):
+    """Host-side generator bookkeeping, off the GPU's critical path: publish the state the reference's randperm
+    calls would leave and start producing the next call's stream."""
+    nxt = _stream_cache(dev).state_after(mt, pos, total)
+    if nxt is None:
+        mt2, pos2 = torch_mt_advance(mt, pos, total)
+    else:
+        mt2, pos2 = nxt
+        if total > 0:
+            _publish_mt_state(mt2, pos2)
+    _stream_cache(dev).release_and_prefetch(mt2, pos2, sp.max_draws + _MT_N)
+
+
+def _run_forward_fast(sp, labels, feats32, needs):
+    """Single process.  Selection, gather AND the similarity forward are driven by the DEVICE plan records and enqueued
+    before the host looks at the plan: the one host wait of the forward pass (needed to raise the reference's errors
+    and to size the backward) overlaps ~0.5 ms of queued GPU work instead of draining the stream."""
+    lib = _lib.load()
+    dev, S, A, spec = sp.dev, sp.S, sp.A, sp.spec
+    st, cur = _stream(), _cur_stream()
+    import time
+    _t = time.perf_counter() if HOST_SEG is not None else 0.0
+    e = sp.ws_pool.pop() if sp.ws_pool else _Workspace(sp)
+    if e.last_stream is not None and e.last_stream != cur:
+        cur.wait_stream(e.last_stream)          # reuse on another stream: order after its previous user
+    e.last_stream = cur
+    nt = len(sp.terms)
+    out = torch.empty(nt + 2, dtype=torch.float32, device=dev)      # term losses, total, inf/NaN flag
+    for job in (e.job_fwd, e.job_bwd):
+        job.term_loss, job.total_loss = out.data_ptr(), out.data_ptr() + 4 * nt
+    # the small, latency-bound sampling kernels run on a high-priority stream (see _hp_stream)
+    hp = _hp_stream(dev) if os.environ.get("MSCS_HP", "1") != "0" else None
+    st_s = st
+    if hp is not None:
+        hp.wait_stream(cur)
+        st_s = C.c_void_p(hp.cuda_stream)
+    with _timed("sample"):
+        _lib.check(lib.mscs_sample_plan(C.byref(sp.cfg), labels.data_ptr(), e.ws, e.plan_dev, st_s), "mscs_sample_plan")
+        _lib.check(lib.mscs_fill_bytes(e.fill_ptrs, e.fill_vals, e.fill_bytes, 2, st_s), "mscs_fill_bytes")
+        _t = _seg("fwd: workspace + plan kernels", _t)
+        # dense gradients: pre-zeroed on a side stream, sampled sectors rewritten by the backward (MSCS_DENSE=1: the
+        # backward writes them in one streaming pass instead -- measured equal, see gather.cu).  Started here, next
+        # to the small sampling kernels: the fill (535 MB at cfg-2) costs ~70 us of step time WHEREVER it runs
+        # (measured next to the sampling kernels, under the forward, under the backward, and as a device-to-device
+        # copy from a persistent zero buffer) -- memset and D2D copies run on the SMs.
+        gradbufs = _GradBuffers(feats32, needs) if (any(needs) and os.environ.get("MSCS_DENSE") != "1") else None
+        if gradbufs is not None:
+            gradbufs.start_fill()
+        _t = _seg("fwd: grad buffers", _t)
+        mt, pos = torch_mt_state()
+        draws = _stream_cache(dev).acquire(mt, pos, sp.max_draws + _MT_N)
+        if hp is not None:
+            hp.wait_event(_stream_cache(dev).ready)
+        _t = _seg("fwd: rng state + stream acquire", _t)
+        _lib.check(lib.mscs_plan_fetch_begin(e.plan_dev, S, st_s), "mscs_plan_fetch_begin")
+        _lib.check(lib.mscs_sample_select_async(C.byref(sp.cfg), e.plan_dev, sp.v_cap, e.ws, draws.data_ptr(), *e.arrs,
+                                                e.sarr, st_s), "mscs_sample_select_async")
+        if hp is not None:
+            cur.wait_stream(hp)
+    with _timed("gather"):
+        for s in range(S):
+            e.gitems[s].feat = feats32[s].data_ptr()
+        _lib.check(lib.mscs_gather_normalize_sectors_batch(e.gitems, S, st), "mscs_gather_normalize_sectors_batch")
+    with _timed("sim_fwd"):
+        _lib.check(lib.mscs_sim_forward(C.byref(e.job_fwd), st), "mscs_sim_forward")
+    _t = _seg("fwd: select + gather + sim_forward", _t)
+    if HOST_WAIT is not None:
+        _t0 = time.perf_counter()
+    plan = e.plan
+    _lib.check(lib.mscs_plan_fetch_end(plan, S), "mscs_plan_fetch_end")       # the host wait (plan records only)
+    if HOST_WAIT is not None:
+        HOST_WAIT.append(time.perf_counter() - _t0)
+    _t = time.perf_counter() if HOST_SEG is not None else 0.0
+    state = _StepState()
+    state.sp, state.entry = sp, e          # (from here on an exception returns the workspace to the pool)
+    _raise_plan_errors(plan, S, spec)
+    total = sum(int(plan[s].draws) for s in range(S))
+    samples = [ScaleSample(plan[s].T, plan[s].V, plan[s].N, bool(plan[s].log_flag), plan[s].dl_h, plan[s].dl_w,
+                           e.islab, sp.ioff[s], A) for s in range(S)]
+    for i, (a, k, *_rest) in enumerate(sp.terms):      # the backward is launched with the actual counts
+        t = e.job_bwd.terms[i]
+        t.N1, t.N2 = samples[a].N, samples[k].N
+    _t = _seg("fwd: after wait", _t)
+    _finish_rng(sp, dev, mt, pos, total)
+    _t = _seg("fwd: rng advance + prefetch", _t)
+    state.job, state.samples, state.gradbufs, state.slots = e.job_bwd, samples, gradbufs, e.slots
+    state.keep, state.stats, state.fslab = out, e.stats, e.fslab
+    state.term_loss, state.total, state.scalars = out[:nt], out[nt], out
+    state.num_ms, state.cs_logged, state.comm = S, sp.cs_logged, None
+    return state
+
+
+def _run_forward_general(sp, labels, feats32, needs, comm, pooled):
+    """Host-driven order on one stream: plan, fetch (host sync), select, gather, forward.  Used by the pooled
+    multi-rank mode (collectives in between) and by planes that are not a multiple of 8 pixels."""
     lib = _lib.load()
     dev, S, A, spec = sp.dev, sp.S, sp.A, sp.spec
     st = _stream()
     i32, f32, u8 = torch.int32, torch.float32, torch.uint8
-    # ---- everything that does not need the plan: before the sync ----
-    import time
-    _t = time.perf_counter() if HOST_SEG is not None else 0.0
-    pooled = comm is not None and comm.world > 1
-    if pooled:
-        ws = torch.empty(sp.ws_bytes, dtype=u8, device=dev)
-        plan_dev = torch.empty(S * C.sizeof(_lib.ScalePlan), dtype=u8, device=dev)
-    else:
-        # one allocation per call; raw addresses for everything the library alone touches
-        slab = torch.empty(sp.slab_bytes, dtype=u8, device=dev)
-        sb, so = slab.data_ptr(), sp.slab_off
-        ws, plan_dev = _Ptr(sb + so["ws"]), _Ptr(sb + so["plan"])
-    # device-driven order (selection, gather and similarity forward enqueued before the host sees the plan): single
-    # process, every plane a multiple of 8 pixels (slot maps), selection smem within limits
-    device_driven = not pooled and all(x != 0 for x in sp.slot_sizes) and sp.v_cap * 12 <= 200 * 1024
-    hp = _hp_stream(dev) if (device_driven and os.environ.get("MSCS_HP", "1") != "0") else None
-    st_s = st                      # stream of the sampling kernels
-    if hp is not None:
-        hp.wait_stream(_cur_stream())
-        slab.record_stream(hp)
-        labels.record_stream(hp)
-        st_s = C.c_void_p(hp.cuda_stream)
+    ws = torch.empty(sp.ws_bytes, dtype=u8, device=dev)
+    plan_dev = torch.empty(S * C.sizeof(_lib.ScalePlan), dtype=u8, device=dev)
     with _timed("sample"):
         if not pooled:
             _lib.check(lib.mscs_sample_plan(C.byref(sp.cfg), labels.data_ptr(), ws.data_ptr(), plan_dev.data_ptr(),
-                                            st_s), "mscs_sample_plan")
+                                            st), "mscs_sample_plan")
         else:
             # local histograms -> all-gather of the (image, class) counts -> identical global plan on every rank
             _lib.check(lib.mscs_sample_hist(C.byref(sp.cfg), labels.data_ptr(), ws.data_ptr(), st), "mscs_sample_hist")
@@ -776,181 +940,82 @@ def run_forward(sp, labels, feats32, needs, comm=None):
             _lib.check(lib.mscs_sample_plan_from_counts(C.byref(sp.cfg), cptr, ws.data_ptr(), plan_dev.data_ptr(),
                                                         st), "mscs_sample_plan_from_counts")
         sizes = sp.slot_sizes
-        if pooled:
-            islab = torch.zeros(sp.islab_n, dtype=i32, device=dev)
-            fslab = torch.empty(sp.fslab_n, dtype=f32, device=dev)
-            bslab = torch.zeros(sp.bslab_n, dtype=torch.bfloat16, device=dev)   # rows of other ranks must be zero for
-            # the all-reduce
-            stats = torch.zeros(sp.stats_n, dtype=f32, device=dev)
-            misc = torch.empty(sp.misc_n, dtype=f32, device=dev)
-            work = torch.empty(sp.work_bytes, dtype=u8, device=dev)
-            # pixel -> row maps (filled by the selection kernel): drive the address-ordered gather and the
-            # sector scatter of the backward
-            slot_slab = torch.full((sum(sizes),), -1, dtype=i32, device=dev) if sum(sizes) else None     # one fill
-            slots, off = [], 0
-            for x in sizes:
-                slots.append(slot_slab[off:off + x] if x else None)
-                off += x
-            keep = (ws, islab, fslab, bslab, stats, misc, work, slot_slab)
-        else:
-            keep = slab      # (two byte fills in one call below)
-            islab = slab[so["islab"]:so["islab"] + 4 * sp.islab_n].view(i32)
-            stats = slab[so["stats"]:so["stats"] + 4 * sp.stats_n].view(f32)
-            misc = slab[so["misc"]:so["misc"] + 4 * sp.misc_n].view(f32)
-            fslab, bslab, work = _Ptr(sb + so["fslab"]), _Ptr(sb + so["bslab"]), _Ptr(sb + so["work"])
-            slots, off = [], sb + so["slot"]
-            for x in sizes:
-                slots.append(_Ptr(off) if x else None)
-                off += 4 * x
-            _lib.check(lib.mscs_fill_bytes(_lib.ptr_array([sb + so["stats"], sb + so["slot"]]), (C.c_int32 * 2)(0, 0xFF),
-                                           (C.c_size_t * 2)(4 * sp.stats_n, 4 * sum(sizes)), 2, st_s), "mscs_fill_bytes")
-        _t = _seg("fwd: alloc + plan kernels", _t)
-        # dense gradients: pre-zeroed on a side stream, sampled sectors rewritten by the backward (MSCS_DENSE=1: the
-        # backward writes them in one streaming pass instead -- measured equal, see gather.cu)
-        gradbufs = _GradBuffers(feats32, needs) if (any(needs) and (pooled or os.environ.get("MSCS_DENSE") != "1")) \
-            else None
+        islab = (torch.zeros if pooled else torch.empty)(sp.islab_n, dtype=i32, device=dev)
+        fslab = torch.empty(sp.fslab_n, dtype=f32, device=dev)
+        # pooled: rows of other ranks must be zero for the all-reduce
+        bslab = (torch.zeros if pooled else torch.empty)(sp.bslab_n, dtype=torch.bfloat16, device=dev)
+        stats = torch.zeros(sp.stats_n, dtype=f32, device=dev)
+        misc = torch.empty(sp.misc_n, dtype=f32, device=dev)
+        work = torch.empty(sp.work_bytes, dtype=u8, device=dev)
+        # pixel -> row maps (filled by the selection kernel): drive the address-ordered gather and the
+        # sector scatter of the backward
+        slot_slab = torch.full((sum(sizes),), -1, dtype=i32, device=dev) if sum(sizes) else None     # one fill
+        slots, off = [], 0
+        for x in sizes:
+            slots.append(slot_slab[off:off + x] if x else None)
+            off += x
+        gradbufs = _GradBuffers(feats32, needs) if any(needs) else None
         if gradbufs is not None:
-            # Started here, next to the small sampling kernels.  The fill (535 MB at cfg-2) costs ~70 us of step time
-            # WHEREVER it runs: measured next to the sampling kernels (+65 us there), under the forward (+80), under
-            # the backward (+77), and as a device-to-device copy from a persistent zero buffer (worse everywhere) --
-            # memset and D2D copies run on the SMs and take them away from whatever they overlap.
             gradbufs.start_fill()
-        _t = _seg("fwd: grad buffers", _t)
         mt, pos = torch_mt_state()
         draws = _stream_cache(dev).acquire(mt, pos, sp.max_draws + _MT_N)
-        if hp is not None:
-            hp.wait_event(_stream_cache(dev).ready)
-        _t = _seg("fwd: rng state + stream acquire", _t)
         plan = (_lib.ScalePlan * S)()
         ibase = islab.data_ptr()
         arrs = [_lib.ptr_array([ibase + 4 * sp.ioff[s][k] for s in range(S)]) for k in range(5)]
         sarr = _lib.ptr_array([x.data_ptr() if x is not None else 0 for x in slots])
         fbase, bbase = fslab.data_ptr(), bslab.data_ptr()
-        plan_sz = C.sizeof(_lib.ScalePlan)
-        # the similarity job: every pointer is known from the slab layouts (sized by upper bounds), so it is
-        # filled in BEFORE the host waits for the plan; only the row counts are patched in afterwards
         job = _lib.SimJob()
-        job.num_terms, job.C_pad, job.num_classes = len(sp.terms), sp.C_pad, A
-        sbase, mbase = stats.data_ptr(), misc.data_ptr()
-        for i, (a, k, self_mask, weight, tau, need_dk) in enumerate(sp.terms):
-            t = job.terms[i]
-            t.a_bf16, t.k_bf16 = bbase + 2 * sp.boff[a], bbase + 2 * sp.boff[k]
-            t.a_cls, t.k_seg = ibase + 4 * sp.ioff[a][3], ibase + 4 * sp.ioff[k][4]
-            t.k_cls, t.a_seg = ibase + 4 * sp.ioff[k][3], ibase + 4 * sp.ioff[a][4]
-            t.self_mask, t.need_dk = int(self_mask), int(need_dk)
-            t.temperature, t.weight, t.a_set, t.k_set = tau, weight, a, k
-            n1 = (sp.Ncap[a] + 15) // 16 * 16
-            t.neg_sum = sbase + 4 * sp.soff[i]
-            t.pos_sum = sbase + 4 * (sp.soff[i] + n1)
-            t.s_sum = sbase + 4 * (sp.soff[i] + 2 * n1)
-            t.coef_s = mbase + 4 * sp.coff[i]
-            t.coef_pn = mbase + 4 * (sp.coff[i] + n1)
+        _fill_job(job, sp, A, bbase, ibase, stats.data_ptr(), misc.data_ptr(), work.data_ptr())
         nt = len(sp.terms)
+        mbase = misc.data_ptr()
         job.term_loss, job.total_loss = mbase + 4 * sp.out_off, mbase + 4 * (sp.out_off + nt)
-        job.work = work.data_ptr()
-        if device_driven:
-            # Selection, gather AND the similarity forward are driven by the DEVICE plan records and enqueued before
-            # the host looks at the plan: the one host wait of the forward pass (needed to raise the reference's
-            # errors and to size the backward) then overlaps ~0.5 ms of queued GPU work instead of draining the stream.
-            _lib.check(lib.mscs_plan_fetch_begin(plan_dev.data_ptr(), S, st_s), "mscs_plan_fetch_begin")
-            _lib.check(lib.mscs_sample_select_async(C.byref(sp.cfg), plan_dev.data_ptr(), sp.v_cap, ws.data_ptr(),
-                                                    draws.data_ptr(), *arrs, sarr, st_s), "mscs_sample_select_async")
-        if hp is not None:
-            _cur_stream().wait_stream(hp)
-    if device_driven:
-        with _timed("gather"):
-            items = (_lib.GatherItem * S)()
-            for s in range(S):
-                n, Cc, h, w = sp.feat_shapes[s]
-                it = items[s]
-                it.feat, it.n, it.C, it.plane = feats32[s].data_ptr(), n, Cc, h * w
-                it.slot, it.n_rows_dev = slots[s].data_ptr(), plan_dev.data_ptr() + s * plan_sz + 8
-                it.anc_bf16, it.anc_f32 = bbase + 2 * sp.boff[s], fbase + 4 * sp.foff[s][0]
-                it.inv_norm = fbase + 4 * sp.foff[s][1]
-            _lib.check(lib.mscs_gather_normalize_sectors_batch(items, S, st), "mscs_gather_normalize_sectors_batch")
-        # the similarity forward too: row counts are read on the device, the job carries their upper bounds
-        pbase = plan_dev.data_ptr()
-        for i, (a, k, *_rest) in enumerate(sp.terms):
-            t = job.terms[i]
-            t.N1, t.N2 = sp.Ncap[a], sp.Ncap[k]
-            t.n1_dev, t.n2_dev = pbase + a * plan_sz + 8, pbase + k * plan_sz + 8
-        with _timed("sim_fwd"):
-            _lib.check(lib.mscs_sim_forward(C.byref(job), st), "mscs_sim_forward")
-        _t = _seg("fwd: job + select + gather + sim_forward", _t)
-        if HOST_WAIT is not None:
-            _t0 = time.perf_counter()
-        _lib.check(lib.mscs_plan_fetch_end(plan, S), "mscs_plan_fetch_end")       # the host sync (plan records only)
-        if HOST_WAIT is not None:
-            HOST_WAIT.append(time.perf_counter() - _t0)
-        _t = time.perf_counter() if HOST_SEG is not None else 0.0
-    else:
         _lib.check(lib.mscs_plan_fetch(plan_dev.data_ptr(), plan, S, st), "mscs_plan_fetch")     # the host sync
-    for s in range(S):
-        if plan[s].error == 1:   # reference: torch.min() of an empty tensor raises (V2.py:110)
-            raise RuntimeError(f"scale {s}: no (image, class) pair has >= min_views_per_class="
-                               f"{spec.min_views} pixels (the reference raises here too, V2.py:110)")
-        if plan[s].error == 2:   # reference: 0-d squeeze then .shape[0] raises (V2.py:119-121)
-            raise IndexError(f"scale {s}: a kept class has a single pixel (the reference raises here too)")
-    total = sum(int(plan[s].draws) for s in range(S))
-    if not device_driven:
-        with _timed("sample"):
-            if pooled:       # rows of other ranks keep pix = -1 (not gathered / scattered here)
-                for s in range(S):
-                    islab[sp.ioff[s][2]:sp.ioff[s][2] + sp.Ncap[s]].fill_(-1)
-            _lib.check(lib.mscs_sample_select(C.byref(sp.cfg), plan, ws.data_ptr(), draws.data_ptr(), *arrs, sarr, st),
-                       "mscs_sample_select")
+        _raise_plan_errors(plan, S, spec)
+        total = sum(int(plan[s].draws) for s in range(S))
+        if pooled:       # rows of other ranks keep pix = -1 (not gathered / scattered here)
+            for s in range(S):
+                islab[sp.ioff[s][2]:sp.ioff[s][2] + sp.Ncap[s]].fill_(-1)
+        _lib.check(lib.mscs_sample_select(C.byref(sp.cfg), plan, ws.data_ptr(), draws.data_ptr(), *arrs, sarr, st),
+                   "mscs_sample_select")
     samples = [ScaleSample(plan[s].T, plan[s].V, plan[s].N, bool(plan[s].log_flag), plan[s].dl_h, plan[s].dl_w,
                            islab, sp.ioff[s], A) for s in range(S)]
     if pooled:           # class of every row on every rank (disjoint supports: the sum is the union)
         comm.all_reduce(islab[sp.cls_begin:])
-    if not device_driven:
-        with _timed("gather"):
-            for s in range(S):
-                n, Cc, h, w = sp.feat_shapes[s]
-                if slots[s] is not None:
-                    _lib.check(lib.mscs_gather_normalize_sectors(feats32[s].data_ptr(), n, Cc, h * w, slots[s].data_ptr(),
-                                                                 samples[s].N, bbase + 2 * sp.boff[s],
-                                                                 fbase + 4 * sp.foff[s][0], fbase + 4 * sp.foff[s][1], st),
-                               "mscs_gather_normalize_sectors")
-                else:
-                    _lib.check(lib.mscs_gather_normalize(feats32[s].data_ptr(), n, Cc, h * w, samples[s].ptr(2),
-                                                         samples[s].N, bbase + 2 * sp.boff[s], fbase + 4 * sp.foff[s][0],
-                                                         fbase + 4 * sp.foff[s][1], st), "mscs_gather_normalize")
+    with _timed("gather"):
+        for s in range(S):
+            n, Cc, h, w = sp.feat_shapes[s]
+            if slots[s] is not None:
+                _lib.check(lib.mscs_gather_normalize_sectors(feats32[s].data_ptr(), n, Cc, h * w, slots[s].data_ptr(),
+                                                             samples[s].N, bbase + 2 * sp.boff[s],
+                                                             fbase + 4 * sp.foff[s][0], fbase + 4 * sp.foff[s][1], st),
+                           "mscs_gather_normalize_sectors")
+            else:
+                _lib.check(lib.mscs_gather_normalize(feats32[s].data_ptr(), n, Cc, h * w, samples[s].ptr(2),
+                                                     samples[s].N, bbase + 2 * sp.boff[s], fbase + 4 * sp.foff[s][0],
+                                                     fbase + 4 * sp.foff[s][1], st), "mscs_gather_normalize")
     if pooled:
         # normalised rows of all ranks: all-gather expressed as a sum of disjoint supports (the slab is
         # zero-initialised).  One collective: per-scale asynchronous pieces overlapping the gather measured much
         # slower at 2 GPUs (17.1 vs 13.2 ms per step).
         comm.all_reduce(bslab)
-    for i, (a, k, *_rest) in enumerate(sp.terms):      # the only plan-dependent fields of the job
+    for i, (a, k, *_rest) in enumerate(sp.terms):      # the plan-dependent fields of the job
         t = job.terms[i]
         t.N1, t.N2 = samples[a].N, samples[k].N
-        t.n1_dev = t.n2_dev = None          # (the backward is launched with the actual counts)
         if pooled:       # anchor (and key) rows are sharded over the ranks in 128-row granules
             t.row_begin, t.row_end = shard_rows(samples[a].N, comm.world, comm.rank)
             t.krow_begin, t.krow_end = shard_rows(samples[k].N, comm.world, comm.rank)
-    if not device_driven:        # (device-driven: already enqueued, before the host waited for the plan)
-        with _timed("sim_fwd"):
-            if not pooled:
-                _lib.check(lib.mscs_sim_forward(C.byref(job), st), "mscs_sim_forward")
-            else:
-                _lib.check(lib.mscs_sim_forward_sweeps(C.byref(job), st), "mscs_sim_forward_sweeps")
-                comm.all_reduce(stats)       # row statistics of all ranks' rows
-                _lib.check(lib.mscs_sim_finalize(C.byref(job), st), "mscs_sim_finalize")
-    _t = _seg("fwd: after wait -> sim_forward enqueued", _t)
-    # host-side generator bookkeeping, off the GPU's critical path
-    if comm is None or comm.owns_rng:
-        nxt = _stream_cache(dev).state_after(mt, pos, total)
-        if nxt is None:
-            mt2, pos2 = torch_mt_advance(mt, pos, total)
+    with _timed("sim_fwd"):
+        if not pooled:
+            _lib.check(lib.mscs_sim_forward(C.byref(job), st), "mscs_sim_forward")
         else:
-            mt2, pos2 = nxt
-            if total > 0:
-                _publish_mt_state(mt2, pos2)
-        _stream_cache(dev).release_and_prefetch(mt2, pos2, sp.max_draws + _MT_N)
-    _t = _seg("fwd: rng advance + prefetch", _t)
+            _lib.check(lib.mscs_sim_forward_sweeps(C.byref(job), st), "mscs_sim_forward_sweeps")
+            comm.all_reduce(stats)       # row statistics of all ranks' rows
+            _lib.check(lib.mscs_sim_finalize(C.byref(job), st), "mscs_sim_finalize")
+    if comm is None or comm.owns_rng:
+        _finish_rng(sp, dev, mt, pos, total)
     state = _StepState()
     state.sp, state.job, state.samples, state.gradbufs, state.slots = sp, job, samples, gradbufs, slots
-    state.keep = keep
+    state.keep = (ws, islab, fslab, bslab, stats, misc, work, slot_slab)
     state.stats = stats
     state.fslab, state.term_loss = fslab, misc[sp.out_off:sp.out_off + nt]
     state.total = misc[sp.out_off + nt]
