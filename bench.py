@@ -165,6 +165,9 @@ def main():
     ap.add_argument("--impl", default="mscs", choices=["mscs", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layout", default="nchw", choices=["nchw", "nhwc"],
+                    help="memory order of the feature maps: nchw = what the reference's projector emits (headline); "
+                         "nhwc = torch.channels_last (row gather / scatter)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -192,11 +195,17 @@ def main():
         feats_h = [f[rank * nl:(rank + 1) * nl].contiguous() for f in feats_h]
         comm = mscs_b200.TorchDistComm()
     labels_h = labels_h.pin_memory()
-    feats_h = [f.pin_memory() for f in feats_h]
+    if args.layout == "nhwc":       # pinned [n][h][w][C] storage viewed as (n, C, h, w)
+        feats_h = [torch.empty((f.shape[0], f.shape[2], f.shape[3], f.shape[1]), pin_memory=True)
+                   .permute(0, 3, 1, 2).copy_(f) for f in feats_h]
+    else:
+        feats_h = [f.pin_memory() for f in feats_h]
     cls = mscs_b200.DenseContrastiveLossV2 if cfg["single_scale"] else mscs_b200.DenseContrastiveLossV2_ms
     mod = cls(dict(cfg["loss"]), comm=comm) if comm is not None else cls(dict(cfg["loss"]))
     labels = labels_h.to(dev)
     feats = [f.to(dev).requires_grad_(True) for f in feats_h]
+    if args.layout == "nhwc":
+        assert all(f.is_contiguous(memory_format=torch.channels_last) and not f.is_contiguous() for f in feats)
 
     torch.manual_seed(0)      # seeded once, like a training run: the generator then only advances
 
@@ -216,6 +225,7 @@ def main():
     for i in range(args.warmup):
         step(labels, feats, i)
     NS = [s.N for s in mod.last_samples]
+    assert mod.last_state.sp.nhwc == (args.layout == "nhwc"), "feature layout did not select the expected kernels"
     pairs = pairs_per_step(NS, mod._spec.cross_scale and not cfg["single_scale"])
     sampler = ClockSampler(local)
     barrier()
@@ -302,7 +312,7 @@ def main():
                 "cfg2": "HRNet-W48 Cityscapes ms+cs loss, 4 scales, 512x1024 crops, bs 12, 256-d projector",
                 "cfg5": "pooled cross-batch anchors, bs 64 in total, ms+cs, max_features_total 65536"}.get(
                     args.workload, args.workload),
-                "anchors_per_scale": NS, "anchor_pairs_per_step": pairs, "per_gpu_batch": cfg["n"],
+                "layout": args.layout, "anchors_per_scale": NS, "anchor_pairs_per_step": pairs, "per_gpu_batch": cfg["n"],
                 "l2": "inputs (535 MB of features per step) exceed the 126 MB L2; no explicit flush",
                 "parallelism": (f"pooled anchors, rows sharded x{world}, keys/statistics/gradient rows exchanged "
                                 f"with NCCL all-reduce" if pooled else

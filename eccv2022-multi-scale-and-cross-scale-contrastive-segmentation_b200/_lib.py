@@ -32,6 +32,12 @@ class ScatterItem(C.Structure):
                 ("slot", C.c_void_p), ("n", C.c_int32), ("C", C.c_int32), ("plane", C.c_int32), ("dfeat", C.c_void_p)]
 
 
+class RowsItem(C.Structure):
+    _fields_ = [("feat", C.c_void_p), ("pix", C.c_void_p), ("n_rows_dev", C.c_void_p), ("rows", C.c_int32),
+                ("C", C.c_int32), ("anc_bf16", C.c_void_p), ("anc_f32", C.c_void_p), ("inv_norm", C.c_void_p),
+                ("dF", C.c_void_p), ("ldF", C.c_int32), ("dfeat", C.c_void_p)]
+
+
 class Term(C.Structure):
     _fields_ = [("a_bf16", C.c_void_p), ("k_bf16", C.c_void_p),
                 ("a_cls", C.c_void_p), ("k_seg", C.c_void_p), ("k_cls", C.c_void_p), ("a_seg", C.c_void_p),
@@ -75,6 +81,8 @@ _SIGNATURES = {
                                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mscs_gather_normalize_sectors_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "mscs_scatter_sectors_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "mscs_gather_rows_nhwc_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "mscs_scatter_rows_nhwc_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "mscs_scatter_dense_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.c_void_p, C.c_void_p]),
     "mscs_mt19937_stream": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]),
     "mscs_sample_select": (C.c_int, [C.POINTER(SampleCfg), C.POINTER(ScalePlan), C.c_void_p, C.c_void_p,

@@ -464,16 +464,23 @@ class _GradBuffers:
     scales and one fill: the per-scale tensors handed to autograd are views of it."""
     _side = {}
 
-    def __init__(self, feats, needs):
+    def __init__(self, feats, needs, nhwc=False):
         dev = feats[0].device
         side = self._side.get(dev)
         if side is None:
             side = self._side[dev] = torch.cuda.Stream(device=dev)
-        sizes = [f.numel() if (need and (f.shape[2] * f.shape[3]) % 8 == 0) else 0 for f, need in zip(feats, needs)]
+        sizes = [f.numel() if (need and (nhwc or (f.shape[2] * f.shape[3]) % 8 == 0)) else 0
+                 for f, need in zip(feats, needs)]
         self.slab = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
         self.bufs, off = [], 0
         for f, n_ in zip(feats, sizes):
-            self.bufs.append(self.slab[off:off + n_].view(f.shape) if n_ else None)
+            if not n_:
+                self.bufs.append(None)
+            elif nhwc:      # same (n, C, h, w) shape, channels-last strides like the input
+                n, Cc, h, w = f.shape
+                self.bufs.append(self.slab[off:off + n_].view(n, h, w, Cc).permute(0, 3, 1, 2))
+            else:
+                self.bufs.append(self.slab[off:off + n_].view(f.shape))
             off += n_
         self.side, self.ready = side, None
 
@@ -588,9 +595,10 @@ class _StepPlan:
     every allocation and the MT19937 stream lookup happen BEFORE the one host sync of the forward
     pass, and only three kinds of C calls remain after it (select, gather, similarity forward)."""
 
-    def __init__(self, dev, label_shape, feat_shapes, spec, single_scale, world=1, rank=0):
+    def __init__(self, dev, label_shape, feat_shapes, spec, single_scale, world=1, rank=0, nhwc=False):
         lib = _lib.load()
         self.dev, self.spec, self.single_scale = dev, spec, single_scale
+        self.nhwc = nhwc            # feature maps are channels-last in memory ([n][h][w][C]): row gather / scatter
         self.world, self.rank = world, rank
         n, H, W = label_shape
         self.n_local, self.n_global = n, n * world
@@ -695,14 +703,20 @@ class _StepPlan:
 _step_plans = {}
 
 
-def _step_plan(dev, label_shape, feat_shapes, spec, single_scale, world=1, rank=0):
+def _step_plan(dev, label_shape, feat_shapes, spec, single_scale, world=1, rank=0, nhwc=False):
     key = (dev, tuple(label_shape), tuple(feat_shapes), spec.num_classes, spec.temperature, spec.cs_temperature,
            spec.min_views, spec.max_views, spec.max_total, tuple(spec.weights), spec.cross_scale,
-           spec.detach_deepest, spec.w_high_low, spec.w_high_mid, single_scale, world, rank)
+           spec.detach_deepest, spec.w_high_low, spec.w_high_mid, single_scale, world, rank, nhwc)
     p = _step_plans.get(key)
     if p is None:
-        p = _step_plans[key] = _StepPlan(dev, label_shape, feat_shapes, spec, single_scale, world, rank)
+        p = _step_plans[key] = _StepPlan(dev, label_shape, feat_shapes, spec, single_scale, world, rank, nhwc)
     return p
+
+
+def fast_path_ok(spec, world):
+    """Single process and selection shared memory within limits: the device-driven order can be used."""
+    v_cap = min(spec.max_total, 16384) if spec.max_views == 1 else min(spec.max_views, spec.max_total, 16384)
+    return world == 1 and v_cap * 12 <= 200 * 1024
 
 
 _hp_streams = {}
@@ -781,10 +795,12 @@ class _Workspace:
             off += 4 * x
         ibase = self.islab.data_ptr()
         self.arrs = [_lib.ptr_array([ibase + 4 * sp.ioff[s][k] for s in range(S)]) for k in range(5)]
+        if sp.nhwc:                 # row gather / scatter: no slot maps
+            self.slots = [None] * S
         self.sarr = _lib.ptr_array([x.data_ptr() if x is not None else 0 for x in self.slots])
         self.fill_ptrs = _lib.ptr_array([sb + so["stats"], sb + so["slot"]])
         self.fill_vals = (C.c_int32 * 2)(0, 0xFF)
-        self.fill_bytes = (C.c_size_t * 2)(4 * sp.stats_n, 4 * sum(sp.slot_sizes))
+        self.fill_bytes = (C.c_size_t * 2)(4 * sp.stats_n, 0 if sp.nhwc else 4 * sum(sp.slot_sizes))
         plan_sz = C.sizeof(_lib.ScalePlan)
         self.job_fwd, self.job_bwd = _lib.SimJob(), _lib.SimJob()
         for job in (self.job_fwd, self.job_bwd):
@@ -793,12 +809,18 @@ class _Workspace:
             t = self.job_fwd.terms[i]
             t.N1, t.N2 = sp.Ncap[a], sp.Ncap[k]
             t.n1_dev, t.n2_dev = self.plan_dev + a * plan_sz + 8, self.plan_dev + k * plan_sz + 8
-        self.gitems = (_lib.GatherItem * S)()
+        if sp.nhwc:
+            self.gitems = (_lib.RowsItem * S)()
+        else:
+            self.gitems = (_lib.GatherItem * S)()
         for s in range(S):
             n, Cc, h, w = sp.feat_shapes[s]
             it = self.gitems[s]
-            it.n, it.C, it.plane = n, Cc, h * w
-            it.slot, it.n_rows_dev = self.slots[s].data_ptr(), self.plan_dev + s * plan_sz + 8
+            if sp.nhwc:
+                it.pix, it.rows, it.C = ibase + 4 * sp.ioff[s][2], sp.Ncap[s], Cc
+            else:
+                it.n, it.C, it.plane, it.slot = n, Cc, h * w, self.slots[s].data_ptr()
+            it.n_rows_dev = self.plan_dev + s * plan_sz + 8
             it.anc_bf16, it.anc_f32 = self.bbase + 2 * sp.boff[s], self.fbase + 4 * sp.foff[s][0]
             it.inv_norm = self.fbase + 4 * sp.foff[s][1]
         self.plan = (_lib.ScalePlan * S)()
@@ -819,8 +841,9 @@ def run_forward(sp, labels, feats32, needs, comm=None):
     pooled = comm is not None and comm.world > 1
     # device-driven order (selection, gather and similarity forward enqueued before the host sees the plan): single
     # process, every plane a multiple of 8 pixels (slot maps), selection shared memory within limits
-    if not pooled and all(x != 0 for x in sp.slot_sizes) and sp.v_cap * 12 <= 200 * 1024:
+    if fast_path_ok(sp.spec, 1 if not pooled else comm.world) and (sp.nhwc or all(x != 0 for x in sp.slot_sizes)):
         return _run_forward_fast(sp, labels, feats32, needs)
+    assert not sp.nhwc, "channels-last inputs are converted by the caller unless the fast path applies"
     return _run_forward_general(sp, labels, feats32, needs, comm, pooled)
 
 
@@ -869,7 +892,8 @@ def _run_forward_fast(sp, labels, feats32, needs):
         # to the small sampling kernels: the fill (535 MB at cfg-2) costs ~70 us of step time WHEREVER it runs
         # (measured next to the sampling kernels, under the forward, under the backward, and as a device-to-device
         # copy from a persistent zero buffer) -- memset and D2D copies run on the SMs.
-        gradbufs = _GradBuffers(feats32, needs) if (any(needs) and os.environ.get("MSCS_DENSE") != "1") else None
+        gradbufs = _GradBuffers(feats32, needs, sp.nhwc) \
+            if (any(needs) and (sp.nhwc or os.environ.get("MSCS_DENSE") != "1")) else None
         if gradbufs is not None:
             gradbufs.start_fill()
         _t = _seg("fwd: grad buffers", _t)
@@ -886,7 +910,10 @@ def _run_forward_fast(sp, labels, feats32, needs):
     with _timed("gather"):
         for s in range(S):
             e.gitems[s].feat = feats32[s].data_ptr()
-        _lib.check(lib.mscs_gather_normalize_sectors_batch(e.gitems, S, st), "mscs_gather_normalize_sectors_batch")
+        if sp.nhwc:
+            _lib.check(lib.mscs_gather_rows_nhwc_batch(e.gitems, S, st), "mscs_gather_rows_nhwc_batch")
+        else:
+            _lib.check(lib.mscs_gather_normalize_sectors_batch(e.gitems, S, st), "mscs_gather_normalize_sectors_batch")
     with _timed("sim_fwd"):
         _lib.check(lib.mscs_sim_forward(C.byref(e.job_fwd), st), "mscs_sim_forward")
     _t = _seg("fwd: select + gather + sim_forward", _t)
@@ -1058,6 +1085,28 @@ def run_backward(state, grad_out, needs, shapes, dtypes):
                 handles[s] = comm.all_gather_blocks_async(rows, per * sp.C_pad)
     grads = []
     fbase = state.fslab.data_ptr()
+    if sp.nhwc:
+        with _timed("scatter"):
+            gb = state.gradbufs
+            if gb is not None:
+                _cur_stream().wait_event(gb.ready)
+            idx = [s for s in range(S) if needs[s]]
+            items = (_lib.RowsItem * max(1, len(idx)))()
+            outs = {}
+            for j, s in enumerate(idx):
+                n, Cc, h, w = shapes[s]
+                pre = gb.take(s) if gb is not None else None
+                if pre is None:      # second backward through the same graph
+                    pre = torch.zeros((n, h, w, Cc), dtype=torch.float32, device=dev).permute(0, 3, 1, 2)
+                outs[s] = pre
+                it = items[j]
+                it.pix, it.rows, it.C = state.samples[s].ptr(2), state.samples[s].N, Cc
+                it.anc_f32, it.inv_norm = fbase + 4 * sp.foff[s][0], fbase + 4 * sp.foff[s][1]
+                it.dF, it.ldF, it.dfeat = ptrs[s], sp.C_pad, pre.data_ptr()
+            if idx:
+                _lib.check(lib.mscs_scatter_rows_nhwc_batch(items, len(idx), st), "mscs_scatter_rows_nhwc_batch")
+            return [None if not needs[s] else (outs[s] if dtypes[s] == torch.float32 else outs[s].to(dtypes[s]))
+                    for s in range(S)]
     dense = state.comm is None and state.gradbufs is None and \
         all((not needs[s]) or (state.slots[s] is not None) for s in range(S))
     if dense:
@@ -1140,13 +1189,18 @@ class MsCsContrastiveFn(torch.autograd.Function):
             if not _lib.load().mscs_device_ok():
                 raise RuntimeError("mscs_b200 needs a compute-capability 10.x (B200) device; no fallback exists")
             _device_checked[0] = True
+        # channels-last feature maps (memory order [n][h][w][C]) are consumed as they are by the single-process fast
+        # path: an anchor is then one contiguous row (gather / scatter become row copies)
+        world = comm.world if comm is not None else 1
+        nhwc = fast_path_ok(spec, world) and all(
+            f.dim() == 4 and f.is_contiguous(memory_format=torch.channels_last) and not f.is_contiguous() for f in feats)
         feats32 = []
         for f in feats:
             _require_device(f)
             f32 = f.detach()
             if f32.dtype != torch.float32:
                 f32 = f32.float()
-            feats32.append(f32.contiguous())
+            feats32.append(f32 if nhwc else f32.contiguous())
         if labels.device != feats32[0].device:
             labels = labels.to(feats32[0].device)
         needs = [bool(ctx.needs_input_grad[4 + i]) for i in range(len(feats))]
@@ -1156,7 +1210,7 @@ class MsCsContrastiveFn(torch.autograd.Function):
         with torch.cuda.device(feats32[0].device), _pin_stream():
             world, rank = (comm.world, comm.rank) if comm is not None else (1, 0)
             sp = _step_plan(feats32[0].device, labels.shape, [tuple(f.shape) for f in feats32], spec, single_scale,
-                            world, rank)
+                            world, rank, nhwc)
             state = run_forward(sp, labels, feats32, needs, comm)
         holder["samples"], holder["state"] = state.samples, state
         ctx.state, ctx.needs = state, needs

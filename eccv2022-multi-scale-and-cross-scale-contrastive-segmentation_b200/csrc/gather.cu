@@ -327,6 +327,88 @@ __global__ void __launch_bounds__(256) k_dense_write(const __grid_constant__ Den
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Channels-last feature maps (memory order [n][h][w][C], e.g. a projector run in torch.channels_last): an anchor is
+// ONE contiguous row of C floats instead of C sectors `plane` floats apart, so gather and scatter become plain row
+// copies (33 MB instead of 354 MB of DRAM reads at cfg-2).  Warp per sorted anchor row; lane l handles the channels
+// l + 32 q -- the same lane/channel assignment as the NCHW kernels, so the results are bit-identical.
+// ---------------------------------------------------------------------------------------
+struct RowsBatch {
+  const float* feat[MSCS_MAX_SCALES]; const int* pix[MSCS_MAX_SCALES]; const int* n_rows_dev[MSCS_MAX_SCALES];
+  __nv_bfloat16* bf16[MSCS_MAX_SCALES]; float* f32[MSCS_MAX_SCALES]; float* inv[MSCS_MAX_SCALES];
+  const float* dF[MSCS_MAX_SCALES]; float* dfeat[MSCS_MAX_SCALES];
+  int C[MSCS_MAX_SCALES], ldF[MSCS_MAX_SCALES], rows[MSCS_MAX_SCALES], block0[MSCS_MAX_SCALES + 1];
+  int count;
+};
+
+__global__ void __launch_bounds__(256) k_gather_rows_nhwc(const __grid_constant__ RowsBatch g) {
+  int s = 0;
+  while (s + 1 < g.count && (int)blockIdx.x >= g.block0[s + 1]) ++s;
+  const int lane = threadIdx.x & 31;
+  const int row = ((int)blockIdx.x - g.block0[s]) * 8 + (threadIdx.x >> 5);
+  const int N = g.n_rows_dev[s] ? *g.n_rows_dev[s] : g.rows[s], N_pad = (N + 255) / 256 * 256;
+  if (row >= N_pad) return;
+  const int C = g.C[s], C_pad = (C + 63) / 64 * 64;
+  __nv_bfloat16* orow = g.bf16[s] + (size_t)row * C_pad;
+  const int gp = row < N ? g.pix[s][row] : -1;
+  if (gp < 0) {                         // padding row, or (pooled mode) a row owned by another rank
+    for (int c = lane; c < C_pad; c += 32) orow[c] = __float2bfloat16(0.f);
+    return;
+  }
+  const float* src = g.feat[s] + (size_t)gp * C;
+  float v[kMaxC / 32];
+  float ss = 0.f;
+#pragma unroll
+  for (int q = 0; q < kMaxC / 32; ++q) {
+    const int c = lane + 32 * q;
+    v[q] = (c < C) ? __ldg(src + c) : 0.f;
+  }
+#pragma unroll
+  for (int q = 0; q < kMaxC / 32; ++q) ss = fmaf(v[q], v[q], ss);
+  ss = warp_sum(ss);
+  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  if (lane == 0) g.inv[s][row] = inv;
+#pragma unroll
+  for (int q = 0; q < kMaxC / 32; ++q) {
+    const int c = lane + 32 * q;
+    const float f = v[q] * inv;
+    if (c < C) g.f32[s][(size_t)row * C + c] = f;
+    if (c < C_pad) orow[c] = __float2bfloat16(c < C ? f : 0.f);
+  }
+}
+
+// normalisation backward + row store into the (pre-zeroed) channels-last dense gradient
+__global__ void __launch_bounds__(256) k_scatter_rows_nhwc(const __grid_constant__ RowsBatch g) {
+  int s = 0;
+  while (s + 1 < g.count && (int)blockIdx.x >= g.block0[s + 1]) ++s;
+  const int lane = threadIdx.x & 31;
+  const int row = ((int)blockIdx.x - g.block0[s]) * 8 + (threadIdx.x >> 5);
+  if (row >= g.rows[s]) return;
+  const int gp = g.pix[s][row];
+  if (gp < 0) return;
+  const int C = g.C[s];
+  const float* gr = g.dF[s] + (size_t)row * g.ldF[s];
+  const float* f = g.f32[s] + (size_t)row * C;
+  float gv[kMaxC / 32], fv[kMaxC / 32], dot = 0.f;
+#pragma unroll
+  for (int q = 0; q < kMaxC / 32; ++q) {
+    const int c = lane + 32 * q;
+    gv[q] = (c < C) ? gr[c] : 0.f;
+    fv[q] = (c < C) ? f[c] : 0.f;
+    dot = fmaf(gv[q], fv[q], dot);
+  }
+  dot = warp_sum(dot);
+  const float inv = g.inv[s][row];
+  const bool clamped = inv >= 1e12f;        // ||x|| <= eps: F.normalize divides by the constant eps
+  float* dst = g.dfeat[s] + (size_t)gp * C;
+#pragma unroll
+  for (int q = 0; q < kMaxC / 32; ++q) {
+    const int c = lane + 32 * q;
+    if (c < C) dst[c] = (clamped ? gv[q] : (gv[q] - fv[q] * dot)) * inv;
+  }
+}
+
 }  // namespace mscs
 
 using namespace mscs;
@@ -498,6 +580,48 @@ extern "C" int mscs_scatter_dense_batch(const mscs_scatter_item* items, const in
   k_dx_rows<<<rb + mblk, 256, 0, st>>>(g);
   MSCS_LAUNCH_CHECK();
   k_dense_write<<<(unsigned)v4, 256, 0, st>>>(g);
+  MSCS_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- channels-last (NHWC) row gather / scatter, every scale in one launch (see mscs.h) ----
+static int rows_batch(const mscs_rows_item* items, int count, bool gather, RowsBatch* g, int* blocks_out) {
+  MSCS_CHECK_ARG(items && count >= 1 && count <= MSCS_MAX_SCALES, "bad item count %d", count);
+  g->count = count;
+  int blocks = 0;
+  for (int s = 0; s < count; ++s) {
+    const mscs_rows_item& it = items[s];
+    MSCS_CHECK_ARG(it.pix && it.anc_f32 && it.inv_norm, "item %d: null pointer argument", s);
+    MSCS_CHECK_ARG(it.C >= 1 && it.C <= kMaxC && it.rows >= 0, "item %d: C=%d unsupported (1..%d)", s, it.C, kMaxC);
+    if (gather) MSCS_CHECK_ARG(it.feat && it.anc_bf16, "item %d: null pointer argument", s);
+    else MSCS_CHECK_ARG(it.dF && it.dfeat && it.ldF >= it.C, "item %d: bad gradient arguments", s);
+    g->feat[s] = it.feat; g->pix[s] = it.pix; g->n_rows_dev[s] = it.n_rows_dev;
+    g->bf16[s] = (__nv_bfloat16*)it.anc_bf16; g->f32[s] = it.anc_f32; g->inv[s] = it.inv_norm;
+    g->dF[s] = it.dF; g->dfeat[s] = it.dfeat; g->C[s] = it.C; g->ldF[s] = it.ldF; g->rows[s] = it.rows;
+    g->block0[s] = blocks;
+    blocks += ceil_div(gather ? (it.rows + 255) / 256 * 256 : it.rows, 8);
+  }
+  g->block0[count] = blocks;
+  *blocks_out = blocks;
+  return 0;
+}
+
+extern "C" int mscs_gather_rows_nhwc_batch(const mscs_rows_item* items, int count, void* stream_) {
+  RowsBatch g{};
+  int blocks = 0;
+  if (int rc = rows_batch(items, count, true, &g, &blocks)) return rc;
+  if (blocks == 0) return 0;
+  k_gather_rows_nhwc<<<blocks, 256, 0, (cudaStream_t)stream_>>>(g);
+  MSCS_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int mscs_scatter_rows_nhwc_batch(const mscs_rows_item* items, int count, void* stream_) {
+  RowsBatch g{};
+  int blocks = 0;
+  if (int rc = rows_batch(items, count, false, &g, &blocks)) return rc;
+  if (blocks == 0) return 0;
+  k_scatter_rows_nhwc<<<blocks, 256, 0, (cudaStream_t)stream_>>>(g);
   MSCS_LAUNCH_CHECK();
   return 0;
 }

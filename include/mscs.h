@@ -259,6 +259,17 @@ typedef struct {
   int32_t n, C, plane; float* dfeat;
 } mscs_scatter_item;
 int mscs_scatter_sectors_batch(const mscs_scatter_item* items, int count, void* stream);
+/* Channels-last feature maps (memory order [n][h][w][C]): an anchor is one contiguous row of C floats, so the gather
+ * (+ L2 normalisation) and the scatter (normalisation backward into the pre-zeroed channels-last dense gradient) are
+ * row copies driven by `pix` (global pixel id = image * plane + pixel of every sorted anchor row, -1 = not local).
+ * `rows`: number of anchor rows, or their upper bound when `n_rows_dev` (device-resident count, gather only) is set. */
+typedef struct {
+  const float* feat; const int32_t* pix; const int32_t* n_rows_dev; int32_t rows, C;
+  void* anc_bf16; float* anc_f32; float* inv_norm;          /* gather outputs / scatter inputs */
+  const float* dF; int32_t ldF; float* dfeat;               /* scatter only */
+} mscs_rows_item;
+int mscs_gather_rows_nhwc_batch(const mscs_rows_item* items, int count, void* stream);
+int mscs_scatter_rows_nhwc_batch(const mscs_rows_item* items, int count, void* stream);
 /* Dense gradients of every scale written in ONE streaming pass, zeros included (no pre-zeroed buffer needed):
  * dF rows are first turned into dx rows IN PLACE (rows[s] rows of item s), then every float4 of every dfeat is
  * written once.  plane must be a multiple of 4.  mask_scratch: sum over items of ceil(n*plane/32) uint32 words

@@ -595,3 +595,96 @@ def test_generator_state_after_call_matches_host_advance(dev):
                    "advance")
         assert got_pos == cpos.value
         assert np.array_equal(got_mt, want)
+
+
+# ---- channels-last feature maps (torch.channels_last projector output): row gather / scatter ----------------
+def _nhwc(t):
+    """Same values and shape, memory order [n][h][w][C] (never plain-contiguous, even for degenerate shapes)."""
+    n, Cc, h, w = t.shape
+    out = torch.empty((n, h, w, Cc), dtype=t.dtype, device=t.device).permute(0, 3, 1, 2)
+    out.copy_(t)
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", SMALL)
+def test_channels_last_small_vs_reference(name, golden, dev):
+    """Channels-last inputs take the row kernels (k_gather_rows_nhwc / k_scatter_rows_nhwc); the results are held to
+    the same bar against the reference's recorded outputs as the NCHW path, odd plane sizes included."""
+    meta = golden[name]
+    labels, feats, z = small_case_inputs(name)
+    mod = make_module(meta)
+    fg = [_nhwc(f.to(dev)).requires_grad_(True) for f in feats]
+    assert all(not f.is_contiguous() for f in fg)
+    torch.set_rng_state(torch.from_numpy(z["rng_state0"]))
+    loss = mod(labels.to(dev), fg[0] if meta["single_scale"] else fg)
+    loss.backward()
+    assert mod.last_state.sp.nhwc, "channels-last inputs must select the row kernels"
+    assert abs(float(loss) - meta["total"]) < 1e-3 * abs(meta["total"])
+    for s, smp in enumerate(mod.last_samples):
+        assert np.array_equal(smp.idx_ref.cpu().numpy(), z[f"idx{s}"])
+    for s, f in enumerate(fg):
+        assert f.grad.shape == f.shape
+        got, want = f.grad.cpu().numpy(), z[f"grad{s}"]
+        cs, err = cosine(got, want), np.abs(got - want).max()
+        print(f"{name} nhwc scale {s}: grad cosine {cs:.7f} max-abs {err:.3e}")
+        assert cs >= 0.999
+        assert np.array_equal(got != 0, want != 0) or np.abs(got[(got != 0) != (want != 0)]).max() < 1e-12
+    assert torch.equal(torch.get_rng_state(), torch.from_numpy(z["rng_state1"]))
+
+
+@pytest.mark.gpu
+def test_channels_last_matches_nchw_full_size(dev):
+    """cfg-2 at full size: the same inputs in both memory orders give the same sampled pixels, the same loss and the
+    same dense gradients (the similarity kernels see identical operand rows up to the rounding of the norm)."""
+    import mscs_b200
+    from mscs_b200 import synth
+    labels, feats = synth.make_inputs("cfg2")
+    mod = mscs_b200.DenseContrastiveLossV2_ms(dict(synth.CONFIGS["cfg2"]["loss"]))
+    lab = labels.to(dev)
+    res = {}
+    for layout in ("nchw", "nhwc"):
+        fg = [(f.to(dev) if layout == "nchw" else _nhwc(f.to(dev))).requires_grad_(True) for f in feats]
+        torch.manual_seed(0)
+        loss = mod(lab, fg)
+        loss.backward()
+        assert mod.last_state.sp.nhwc == (layout == "nhwc")
+        res[layout] = (float(loss), [s.pix.clone() for s in mod.last_samples], [f.grad.contiguous() for f in fg])
+    (la, pa, ga), (lb, pb, gb) = res["nchw"], res["nhwc"]
+    assert all(torch.equal(a, b) for a, b in zip(pa, pb))
+    assert abs(la - lb) <= 2e-6 * abs(la)
+    for s, (a, b) in enumerate(zip(ga, gb)):
+        err, ref = float((a - b).abs().max()), float(a.abs().max())
+        print(f"cfg2 nhwc vs nchw scale {s}: max-abs {err:.3e} (max {ref:.3e})")
+        assert err <= 1e-4 * ref
+        assert torch.equal(a != 0, b != 0)
+
+
+@pytest.mark.gpu
+def test_channels_last_second_backward_half_and_no_grad(dev):
+    import mscs_b200
+    from mscs_b200 import synth
+    cfg = dict(dataset="CITYSCAPES", experiment=1, temperature=0.1, max_views_per_class=20)
+    labels = synth.synth_labels(2, 64, 128, 19, 5, 8, 0.05, 51).to(dev)
+    base = synth.synth_features(2, 32, 64, 128, [4], 52)[0].to(dev)
+    feat = _nhwc(base).requires_grad_(True)
+    mod = mscs_b200.DenseContrastiveLossV2(cfg)
+    torch.manual_seed(1)
+    loss = mod(labels, feat)
+    loss.backward(retain_graph=True)
+    g1 = feat.grad.clone()
+    feat.grad = None
+    loss.backward()
+    assert torch.allclose(feat.grad, g1, rtol=1e-4, atol=1e-9)
+    ref = base.clone().requires_grad_(True)
+    torch.manual_seed(1)
+    mod(labels, ref).backward()
+    assert torch.allclose(ref.grad, g1, rtol=1e-4, atol=1e-7)
+    fh = _nhwc(base.half()).requires_grad_(True)
+    torch.manual_seed(1)
+    mod(labels, fh).backward()
+    assert fh.grad.dtype == torch.float16 and torch.isfinite(fh.grad).all() and fh.grad.shape == fh.shape
+    torch.manual_seed(1)
+    with torch.no_grad():
+        l2 = mod(labels, _nhwc(base))
+    assert abs(float(l2) - float(loss)) <= 1e-6 * abs(float(loss))
