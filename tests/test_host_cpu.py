@@ -32,6 +32,37 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.Term) == 6 * 8 + 4 * 4 + 2 * 4 + 2 * 4 + 4 * 4 + 5 * 8 + 2 * 8      # + n1_dev, n2_dev
 
 
+def test_struct_layouts_match_compiler(tmp_path):
+    """Every struct of include/mscs.h as a C compiler lays it out (gcc, plain C: the header must stay C-clean) against
+    the ctypes mirror the host side passes through the ABI: size and the offset of every field."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    pairs = {"mscs_sample_cfg": _lib.SampleCfg, "mscs_scale_plan": _lib.ScalePlan, "mscs_gather_item": _lib.GatherItem,
+             "mscs_scatter_item": _lib.ScatterItem, "mscs_rows_item": _lib.RowsItem, "mscs_term": _lib.Term,
+             "mscs_sim_job": _lib.SimJob}
+    header = open(os.path.join(ROOT, "include", "mscs.h")).read()
+    assert set(re.findall(r"^}\s*(mscs_[a-z_]+);", header, re.M)) == set(pairs), "a header struct has no ctypes mirror"
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "mscs.h"', "int main(void) {"]
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, *_ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True,
+                                                       text=True).stdout.splitlines())
+    for cname, cls in pairs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, *_ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+
+
 def test_mt_advance_host_matches_torch():
     lib = mscs_b200.load()
     for seed, k in [(0, 9), (1, 623), (2, 624), (3, 625), (4, 100000)]:
