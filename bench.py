@@ -361,7 +361,7 @@ def main():
                 "parallelism": (f"pooled anchors, rows sharded x{world}, keys/statistics/gradient rows exchanged "
                                 f"with NCCL all-reduce" if pooled else
                                 f"replicas x{world} (loss evaluated per rank on its local batch, as under DDP)"),
-                "loss": float(loss)},
+                "loss": float(loss.detach())},
             "roofline": roofline, "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": n_e2e,
