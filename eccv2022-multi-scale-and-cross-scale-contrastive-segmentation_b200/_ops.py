@@ -56,8 +56,9 @@ class _timed:
 def LAUNCHES_PER_STEP(num_scales, single_scale):
     """Kernels of libmscs.so launched by one forward+backward (torch fills not counted; checked against the ncu
     launch list in profiles/): K1 hist, tile-scan, plan, MT19937 stream, select (5); K2 (1); K3 row ranges,
-    2 x (work table + sweep), 2 finalise kernels (7); K4 work table + backward (2); scatter (1)."""
-    return 5 + 1 + 7 + 2 + 1      # gather and scatter: one launch each for all scales
+    work tables of both sweeps (one launch), 2 sweeps, 2 finalise kernels (6); K4 work table + backward (2);
+    scatter (1)."""
+    return 5 + 1 + 6 + 2 + 1      # gather and scatter: one launch each for all scales
 
 
 @dataclass
@@ -464,14 +465,17 @@ class _GradBuffers:
     scales and one fill: the per-scale tensors handed to autograd are views of it."""
     _side = {}
 
-    def __init__(self, feats, needs, nhwc=False):
+    def __init__(self, feats, needs, nhwc=False, extra=0):
         dev = feats[0].device
         side = self._side.get(dev)
         if side is None:
             side = self._side[dev] = torch.cuda.Stream(device=dev)
         sizes = [f.numel() if (need and (nhwc or (f.shape[2] * f.shape[3]) % 8 == 0)) else 0
                  for f, need in zip(feats, needs)]
-        self.slab = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        # `extra` floats after the dense gradients: the gradient-row slab (dF) of the backward, zeroed by the same fill
+        dense = (sum(sizes) + 63) // 64 * 64          # dF starts 256-byte aligned (vector reductions / loads)
+        self.slab = torch.empty(dense + extra if extra else sum(sizes), dtype=torch.float32, device=dev)
+        self.dF = self.slab[dense:] if extra else None
         self.bufs, off = [], 0
         for f, n_ in zip(feats, sizes):
             if not n_:
@@ -500,6 +504,11 @@ class _GradBuffers:
         """The pre-zeroed buffer of scale s (once: a second backward falls back to zero-fill)."""
         b, self.bufs[s] = self.bufs[s], None
         return b
+
+    def take_dF(self):
+        """The pre-zeroed gradient-row slab (once)."""
+        d, self.dF = self.dF, None
+        return d
 
 
 # ---- pooled cross-batch mode: collectives -----------------------------------------------------
@@ -892,7 +901,7 @@ def _run_forward_fast(sp, labels, feats32, needs):
         # to the small sampling kernels: the fill (535 MB at cfg-2) costs ~70 us of step time WHEREVER it runs
         # (measured next to the sampling kernels, under the forward, under the backward, and as a device-to-device
         # copy from a persistent zero buffer) -- memset and D2D copies run on the SMs.
-        gradbufs = _GradBuffers(feats32, needs, sp.nhwc) \
+        gradbufs = _GradBuffers(feats32, needs, sp.nhwc, sp.dF_n) \
             if (any(needs) and (sp.nhwc or os.environ.get("MSCS_DENSE") != "1")) else None
         if gradbufs is not None:
             gradbufs.start_fill()
@@ -981,7 +990,7 @@ def _run_forward_general(sp, labels, feats32, needs, comm, pooled):
         for x in sizes:
             slots.append(slot_slab[off:off + x] if x else None)
             off += x
-        gradbufs = _GradBuffers(feats32, needs) if any(needs) else None
+        gradbufs = _GradBuffers(feats32, needs, False, sp.dF_n) if any(needs) else None
         if gradbufs is not None:
             gradbufs.start_fill()
         mt, pos = torch_mt_state()
@@ -1056,7 +1065,14 @@ def run_backward(state, grad_out, needs, shapes, dtypes):
     sp = state.sp
     dev, S = sp.dev, sp.S
     st = _stream()
-    dF = torch.zeros(sp.dF_n, dtype=torch.float32, device=dev)
+    # gradient rows: zeroed ahead of time together with the dense gradients (side stream, during the forward)
+    dF = None
+    if state.gradbufs is not None:
+        dF = state.gradbufs.take_dF()
+        if dF is not None:
+            _cur_stream().wait_event(state.gradbufs.ready)
+    if dF is None:          # second backward through the same graph, or no pre-zeroed buffers
+        dF = torch.zeros(sp.dF_n, dtype=torch.float32, device=dev)
     base = dF.data_ptr()
     ptrs = [0] * _lib.MAX_SCALES
     lds = (C.c_int32 * _lib.MAX_SCALES)()
@@ -1219,10 +1235,13 @@ class MsCsContrastiveFn(torch.autograd.Function):
         total = state.total.reshape(())
         terms = state.term_loss
         ctx.mark_non_differentiable(terms)
+        ctx.set_materialize_grads(False)       # no zero tensor (a fill launch) for the unused gradient of `terms`
         return total, terms
 
     @staticmethod
     def backward(ctx, grad_total, _grad_terms):
+        if grad_total is None:
+            return (None,) * (4 + len(ctx.needs))
         with torch.cuda.device(ctx.state.sp.dev), _pin_stream():
             grads = run_backward(ctx.state, grad_total, ctx.needs, ctx.shapes, ctx.dtypes)
         return (None, None, None, None, *grads)

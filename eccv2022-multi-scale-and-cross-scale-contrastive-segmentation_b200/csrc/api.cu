@@ -1,6 +1,11 @@
 // api.cu -- library-level entry points: version, error string, device probe.
 #include "common.cuh"
 #include <string.h>
+#include <stdlib.h>
+
+#ifndef MSCS_PDL_DEFAULT
+#define MSCS_PDL_DEFAULT 1
+#endif
 
 namespace mscs {
 static thread_local char g_err[1024] = "";
@@ -11,6 +16,16 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* get_error() { return g_err; }
+
+// programmatic dependent launch between the kernels of a step (common.cuh); MSCS_PDL=0 / 1 overrides the default
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MSCS_PDL");
+    on = e ? (atoi(e) != 0) : MSCS_PDL_DEFAULT;
+  }
+  return on != 0;
+}
 }  // namespace mscs
 
 static unsigned long long* g_trap_host = nullptr;

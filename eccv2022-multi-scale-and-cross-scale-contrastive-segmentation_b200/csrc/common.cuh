@@ -42,6 +42,31 @@ const char* get_error();
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// A step is a chain of ~19 launches, most of them a few microseconds long: with plain stream order every boundary
+// costs the launch latency plus the drain of the previous grid.  Kernels launched through launch_k() carry the
+// programmatic-stream-serialization attribute (unless MSCS_PDL=0): the next grid is scheduled as soon as every CTA of
+// the previous one has executed pdl_trigger() (first statement of every kernel) and SM resources allow, runs its
+// prologue, and blocks in pdl_wait() until the previous grid has COMPLETED and its writes are visible.  Every thread of
+// every kernel executes pdl_wait() before its first global-memory access, so a grid completes only after all of its
+// predecessors did (ordering stays transitive).  Launched without the attribute both instructions are no-ops.
+bool pdl_enabled();        // api.cu: MSCS_PDL environment switch, read once
+
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... P, typename... A>
+static inline cudaError_t launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at{};
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(256)
 k_gather_normalize(const float* __restrict__ feat, int C, int C_pad, int plane, const int* __restrict__ pix,
                    int N, int N_pad, __nv_bfloat16* __restrict__ anc_bf16, float* __restrict__ anc_f32,
                    float* __restrict__ inv_norm) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= N_pad) return;
@@ -139,6 +140,7 @@ __global__ void __launch_bounds__(256)
 k_gather_sectors(const float* __restrict__ feat, int C, int C_pad, int plane, const int* __restrict__ slot,
                  int n_octets, __nv_bfloat16* __restrict__ anc_bf16, float* __restrict__ anc_f32,
                  float* __restrict__ inv_norm, const int* __restrict__ n_rows_dev) {
+  pdl_trigger();
   gather_sectors_body(blockIdx.x, gridDim.x, feat, C, C_pad, plane, slot, n_octets, anc_bf16, anc_f32, inv_norm,
                       n_rows_dev);
 }
@@ -152,6 +154,7 @@ struct GatherBatch {
   int count;
 };
 __global__ void __launch_bounds__(256) k_gather_sectors_batch(const __grid_constant__ GatherBatch g) {
+  pdl_trigger();      // the next kernel of the forward (k_row_ranges) is launched programmatically, see common.cuh
   int s = 0;
   while (s + 1 < g.count && (int)blockIdx.x >= g.block0[s + 1]) ++s;
   gather_sectors_body(blockIdx.x - g.block0[s], g.block0[s + 1] - g.block0[s], g.feat[s], g.C[s],
@@ -343,6 +346,7 @@ struct RowsBatch {
 };
 
 __global__ void __launch_bounds__(256) k_gather_rows_nhwc(const __grid_constant__ RowsBatch g) {
+  pdl_trigger();
   int s = 0;
   while (s + 1 < g.count && (int)blockIdx.x >= g.block0[s + 1]) ++s;
   const int lane = threadIdx.x & 31;

@@ -110,6 +110,7 @@ __device__ __forceinline__ int nearest_src(int dst, float scale, int in_size, in
 __global__ void __launch_bounds__(256)
 k_label_hist(const __grid_constant__ SampleLayout L, const long long* __restrict__ labels, char* ws) {
   extern __shared__ int hist[];
+  pdl_trigger();
   int t = blockIdx.x;
   int s = 0;
 #pragma unroll 1
@@ -150,6 +151,8 @@ k_label_hist(const __grid_constant__ SampleLayout L, const long long* __restrict
 // exclusive prefix over the tiles of each (scale, image, class): tilecnt becomes "number of
 // class-c pixels of image b before this tile"
 __global__ void k_tile_scan(const __grid_constant__ SampleLayout L, char* ws) {
+  pdl_trigger();
+  pdl_wait();
   int s = blockIdx.y;
   const ScaleGeo& g = L.g[s];
   int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -176,6 +179,7 @@ struct PlanCfg { int min_views, max_views, max_total; const int* counts[MSCS_MAX
 
 __global__ void __launch_bounds__(1024)
 k_plan(const __grid_constant__ SampleLayout L, PlanCfg pc, char* ws, mscs_scale_plan* plan) {
+  pdl_wait();
   const int s = blockIdx.x;
   const ScaleGeo& g = L.g[s];
   const int A = L.A, n = L.ng;
@@ -486,7 +490,7 @@ extern "C" int mscs_sample_hist(const mscs_sample_cfg* cfg, const int64_t* label
   k_label_hist<<<L.total_tiles, 256, sizeof(int) * L.A, st>>>(L, (const long long*)labels, ws);
   MSCS_LAUNCH_CHECK();
   dim3 gs(ceil_div(L.n * L.A, 128), L.S);
-  k_tile_scan<<<gs, 128, 0, st>>>(L, ws);
+  MSCS_CUDA(launch_k(k_tile_scan, gs, 128, 0, st, L, ws));
   MSCS_LAUNCH_CHECK();
   return 0;
 }
@@ -501,7 +505,7 @@ extern "C" int mscs_sample_plan_from_counts(const mscs_sample_cfg* cfg, const in
   MSCS_CHECK_ARG(L.ng == L.n || counts_global, "pooled mode needs the all-gathered counts");
   PlanCfg pc{cfg->min_views, cfg->max_views, cfg->max_total, {}};
   for (int s = 0; s < L.S; ++s) pc.counts[s] = counts_global ? counts_global[s] : nullptr;
-  k_plan<<<L.S, 1024, sizeof(int) * (L.A + 1), (cudaStream_t)stream_>>>(L, pc, (char*)workspace, plan_dev);
+  MSCS_CUDA(launch_k(k_plan, L.S, 1024, sizeof(int) * (L.A + 1), (cudaStream_t)stream_, L, pc, (char*)workspace, plan_dev));
   MSCS_LAUNCH_CHECK();
   return 0;
 }

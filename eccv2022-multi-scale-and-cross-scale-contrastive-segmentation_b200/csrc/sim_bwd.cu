@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < kBwdStages; ++i) {
       ptx::mbar_init(&b_full[i], 1);
@@ -99,6 +100,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_sim_bwd(const __grid_constan
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();       // barriers and tensor memory are set up while the previous grid (work-table build) drains
 #if defined(MSCS_WAIT_PROFILE) || defined(MSCS_TRACE)     // effective SM clock of this launch: slot 31 accumulates (ns, cycles) of CTA 0
   const unsigned long long prof_t0 = ptx::globaltimer_ns();
   const long long prof_c0 = clock64();
@@ -413,7 +415,7 @@ static int launch_bwd(const BwdArgs& args, cudaStream_t st) {
   const size_t smem = bwd_smem_bytes(KB);
   if (int rc = ensure_trap_buffer()) return rc;
   MSCS_CUDA(cudaFuncSetAttribute(k_sim_bwd<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_sim_bwd<KB><<<sm_count(), kBwdThreads, smem, st>>>(args);
+  MSCS_CUDA(launch_k(k_sim_bwd<KB>, sm_count(), kBwdThreads, smem, st, args));
   MSCS_LAUNCH_CHECK();
   return 0;
 }

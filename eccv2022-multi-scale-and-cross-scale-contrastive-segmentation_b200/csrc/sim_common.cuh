@@ -90,6 +90,7 @@ static inline int validate_job(const mscs_sim_job* job) {
 }
 
 // launched by both implementations after the two forward sweeps
-int launch_finalize(const mscs_sim_job* job, cudaStream_t st);
+// zero_acc: the caller did not run k_row_ranges (which clears the accumulators) on this job->work before
+int launch_finalize(const mscs_sim_job* job, cudaStream_t st, bool zero_acc = false);
 
 }  // namespace mscs

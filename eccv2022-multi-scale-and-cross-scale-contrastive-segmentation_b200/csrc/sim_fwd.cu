@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  pdl_trigger();
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < kFwdStages; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
     ptx::mbar_init(k_full, 1); ptx::mbar_init(k_empty, 1);
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();       // barriers and tensor memory are set up while the previous grid drains
 #ifdef MSCS_WAIT_PROFILE     // effective SM clock of this launch: slot 31 accumulates (ns, cycles) of CTA 0
   const unsigned long long prof_t0 = ptx::globaltimer_ns();
   const long long prof_c0 = clock64();
@@ -278,8 +280,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
 // per anchor row: positive key range [k_seg[y], k_seg[y+1]); per 32-row group: the union (groups are
 // padded to whole 128-row tiles so the epilogue can index them by tile)
 struct RangeTerm { const int* a_cls; const int* k_seg; int2* row_range; int2* grp_range; int N1; const int* n1_dev; };
-struct RangeArgs { RangeTerm t[MSCS_MAX_TERMS]; };
+struct RangeArgs { RangeTerm t[MSCS_MAX_TERMS]; double* fin_acc; };   // fin_acc: per-term loss accumulators of the finalise
 __global__ void __launch_bounds__(256) k_row_ranges(const __grid_constant__ RangeArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < MSCS_MAX_TERMS) a.fin_acc[threadIdx.x] = 0.0;
   const RangeTerm& t = a.t[blockIdx.y];
   const int r = blockIdx.x * 256 + threadIdx.x;
   const int tN1 = t.n1_dev ? *t.n1_dev : t.N1;
@@ -305,7 +310,13 @@ __global__ void __launch_bounds__(256) k_row_ranges(const __grid_constant__ Rang
 __global__ void __launch_bounds__(1024) k_build_work(const __grid_constant__ BuildArgs a) {
   __shared__ int carry;
   __shared__ int wsum[32];
-  if (threadIdx.x == 0) { carry = 0; a.prefix[0] = 0; }
+  pdl_trigger();
+  pdl_wait();
+  // block 1 (forward only): the table of the second sweep, built in the same launch
+  const int mode = a.mode + (int)blockIdx.x;
+  WorkItem* const items = blockIdx.x ? a.items1 : a.items;
+  int* const prefix = blockIdx.x ? a.prefix1 : a.prefix;
+  if (threadIdx.x == 0) { carry = 0; prefix[0] = 0; }
   __syncthreads();
   for (int base = 0; base < a.nitems; base += blockDim.x) {
     const int i = base + threadIdx.x;
@@ -319,13 +330,13 @@ __global__ void __launch_bounds__(1024) k_build_work(const __grid_constant__ Bui
       int ct0 = 0, ct1 = (tN2 + kTileN - 1) / kTileN;
       if (rb * a.rows_per_item >= tN1) {      // block beyond the actual row count (items are sized by the upper bound)
         ct0 = ct1 = 0;
-      } else if (a.mode == 1) {
+      } else if (mode == 1) {
         const int r0 = rb * a.rows_per_item, r1 = min(tN1, r0 + a.rows_per_item) - 1;
         const int p0 = t.k_seg[t.a_cls[r0]], p1 = t.k_seg[t.a_cls[r1] + 1];
         if (p1 > p0) { ct0 = p0 / kTileN; ct1 = (p1 + kTileN - 1) / kTileN; } else { ct0 = ct1 = 0; }
       }
       ct0 = max(ct0, t.ct_lo); ct1 = max(ct0, min(ct1, t.ct_hi));      // pooled mode: this rank's streamed tiles
-      a.items[i] = WorkItem{ti, rb, ct0, ct1};
+      items[i] = WorkItem{ti, rb, ct0, ct1};
       len = ct1 > ct0 ? ct1 - ct0 + a.pad : 0;
     }
     int s = len;
@@ -341,7 +352,7 @@ __global__ void __launch_bounds__(1024) k_build_work(const __grid_constant__ Bui
     }
     __syncthreads();
     const int incl = carry + wsum[threadIdx.x >> 5] + s;
-    if (i < a.nitems) a.prefix[i + 1] = incl;
+    if (i < a.nitems) prefix[i + 1] = incl;
     __syncthreads();
     if (threadIdx.x == blockDim.x - 1) carry = incl;
     __syncthreads();
@@ -374,7 +385,7 @@ int make_tensor_map(CUtensorMap* out, const void* base, int rows, int c_pad) {
 }
 
 int launch_build_work(const BuildArgs& b, cudaStream_t st) {
-  k_build_work<<<1, 1024, 0, st>>>(b);
+  MSCS_CUDA(launch_k(k_build_work, b.items1 ? 2 : 1, 1024, 0, st, b));
   MSCS_LAUNCH_CHECK();
   return 0;
 }
@@ -391,10 +402,10 @@ static int launch_fwd(const FwdArgs& args, int mode, cudaStream_t st) {
   if (int rc = ensure_trap_buffer()) return rc;
   if (mode == 0) {
     MSCS_CUDA(cudaFuncSetAttribute(k_sim_fwd<KB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_sim_fwd<KB, 0><<<sm_count(), kFwdThreads, smem, st>>>(args);
+    MSCS_CUDA(launch_k(k_sim_fwd<KB, 0>, sm_count(), kFwdThreads, smem, st, args));
   } else {
     MSCS_CUDA(cudaFuncSetAttribute(k_sim_fwd<KB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_sim_fwd<KB, 1><<<sm_count(), kFwdThreads, smem, st>>>(args);
+    MSCS_CUDA(launch_k(k_sim_fwd<KB, 1>, sm_count(), kFwdThreads, smem, st, args));
   }
   MSCS_LAUNCH_CHECK();
   return 0;
@@ -473,20 +484,24 @@ extern "C" int mscs_sim_forward_sweeps(const mscs_sim_job* job, void* stream_) {
                        m.n2_dev, m.n1_dev};      // (blocks are on the key side: rows = keys)
     nitems += ceil_div(m.N2, kFwdKeys);
   }
-  k_row_ranges<<<dim3(ceil_div(maxN1 + 127, 256), job->num_terms), 256, 0, st>>>(ra);
+  ra.fin_acc = (double*)job->work;
+  MSCS_CUDA(launch_k(k_row_ranges, dim3(ceil_div(maxN1 + 127, 256), job->num_terms), 256, 0, st, ra));
   MSCS_LAUNCH_CHECK();
   tl_mark(st);
   b.num_terms = job->num_terms; b.nitems = nitems; b.rows_per_item = kFwdKeys;
   b.pad = 0;      // start-up charge of a key block (128 KB load + pipeline fill), in anchor tiles
   if (const char* e = getenv("MSCS_FWD_PAD")) b.pad = atoi(e);
+  // both work tables (sweep 0: every tile; sweep 1: class-diagonal tiles) depend only on the class arrays: one launch
+  b.mode = 0;
+  b.items = (WorkItem*)w;  w += align_up(sizeof(WorkItem) * (size_t)nitems, 64);
+  b.prefix = (int*)w;      w += align_up(sizeof(int) * (size_t)(nitems + 1), 64);
+  b.items1 = (WorkItem*)w; w += align_up(sizeof(WorkItem) * (size_t)nitems, 64);
+  b.prefix1 = (int*)w;     w += align_up(sizeof(int) * (size_t)(nitems + 1), 64);
+  rc = launch_build_work(b, st);
+  if (rc) return rc;
+  tl_mark(st);
   for (int mode = 0; mode < 2; ++mode) {
-    b.mode = mode;
-    b.items = (WorkItem*)w; w += align_up(sizeof(WorkItem) * (size_t)nitems, 64);
-    b.prefix = (int*)w;     w += align_up(sizeof(int) * (size_t)(nitems + 1), 64);
-    rc = launch_build_work(b, st);
-    if (rc) return rc;
-    tl_mark(st);
-    args.work = WorkTable{b.items, b.prefix, nitems, b.pad};
+    args.work = mode ? WorkTable{b.items1, b.prefix1, nitems, b.pad} : WorkTable{b.items, b.prefix, nitems, b.pad};
     switch (job->C_pad / 64) {
       case 1: rc = launch_fwd<1>(args, mode, st); break;
       case 2: rc = launch_fwd<2>(args, mode, st); break;

@@ -58,7 +58,8 @@ struct Walker {
 // n1_dev / n2_dev: optional device-resident row counts (then N1 / N2 are upper bounds, see mscs_term)
 struct BuildTerm { const int* a_cls; const int* k_seg; int N1, N2, item_base, blk_lo, ct_lo, ct_hi;
                    const int* n1_dev; const int* n2_dev; };
-struct BuildArgs { BuildTerm t[MSCS_MAX_PASSES]; int num_terms, nitems, rows_per_item, mode, pad; WorkItem* items; int* prefix; };
+struct BuildArgs { BuildTerm t[MSCS_MAX_PASSES]; int num_terms, nitems, rows_per_item, mode, pad; WorkItem* items; int* prefix;
+                   WorkItem* items1; int* prefix1; };   // items1 / prefix1 non-null: a second block builds the mode + 1 table
 int launch_build_work(const BuildArgs& b, cudaStream_t st);
 int trap_buffer_device_ptr(unsigned long long** out);
 // each translation unit with tensor kernels installs the buffer into its own g_trap_buf copy

@@ -20,6 +20,8 @@ struct FinArgs { FinTerm t[MSCS_MAX_TERMS]; int num_terms; float* term_loss; flo
 // grid = (row chunks, terms): per-row work is two dependent loads deep, so it is spread over many CTAs;
 // the per-term sums are reduced in fp64 (order-insensitive to far below fp32 resolution).
 __global__ void __launch_bounds__(256) k_finalize_rows(const __grid_constant__ FinArgs a, double* acc) {
+  pdl_trigger();
+  pdl_wait();
   const FinTerm& t = a.t[blockIdx.y];
   __shared__ double red[8];
   double part = 0.0;
@@ -52,6 +54,8 @@ __global__ void __launch_bounds__(256) k_finalize_rows(const __grid_constant__ F
 }
 
 __global__ void k_finalize_total(const __grid_constant__ FinArgs a, const double* acc) {
+  pdl_trigger();
+  pdl_wait();
   if (threadIdx.x != 0) return;
   double total = 0.0;
   bool bad = false;
@@ -67,8 +71,9 @@ __global__ void k_finalize_total(const __grid_constant__ FinArgs a, const double
   a.total_loss[1] = (bad || !isfinite((float)total)) ? 1.f : 0.f;
 }
 
-// job->work: the first 4096 bytes are reserved for these accumulators (zeroed by the forward launcher)
-int launch_finalize(const mscs_sim_job* job, cudaStream_t st) {
+// job->work: the first 4096 bytes are reserved for these accumulators (zeroed by k_row_ranges, the first kernel of
+// the forward sweeps: no memset between the kernels of the chain)
+int launch_finalize(const mscs_sim_job* job, cudaStream_t st, bool zero_acc) {
   FinArgs a{};
   a.num_terms = job->num_terms; a.term_loss = job->term_loss; a.total_loss = job->total_loss;
   int maxN = 0;
@@ -79,10 +84,10 @@ int launch_finalize(const mscs_sim_job* job, cudaStream_t st) {
     if (m.N1 > maxN) maxN = m.N1;
   }
   double* acc = (double*)job->work;
-  MSCS_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * MSCS_MAX_TERMS, st));
-  k_finalize_rows<<<dim3(ceil_div(maxN, 1024), job->num_terms), 256, 0, st>>>(a, acc);
+  if (zero_acc) MSCS_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * MSCS_MAX_TERMS, st));
+  MSCS_CUDA(launch_k(k_finalize_rows, dim3(ceil_div(maxN, 1024), job->num_terms), 256, 0, st, a, acc));
   MSCS_LAUNCH_CHECK();
-  k_finalize_total<<<1, 32, 0, st>>>(a, acc);
+  MSCS_CUDA(launch_k(k_finalize_total, 1, 32, 0, st, a, (const double*)acc));
   MSCS_LAUNCH_CHECK();
   return 0;
 }
@@ -281,7 +286,7 @@ extern "C" int mscs_debug_sim_forward_simt(const mscs_sim_job* job, const float*
       else k_simt_fwd<1><<<ceil_div(m.N1, 64), 256, 0, st>>>(t);
       MSCS_LAUNCH_CHECK();
     }
-  return launch_finalize(job, st);
+  return launch_finalize(job, st, true);
 }
 
 extern "C" int mscs_debug_sim_backward_simt(const mscs_sim_job* job, const float* const* f32_sets,

@@ -142,4 +142,4 @@ def test_step_plan_slab_layout():
     # a plane that is not a multiple of 8 pixels has no slot map (general scatter path)
     sp2 = _ops._StepPlan(torch.device("cpu"), (2, 60, 100), [(2, 32, 15, 25)], spec, True)
     assert sp2.slot_sizes == [0]
-    assert _ops.LAUNCHES_PER_STEP(4, False) == 16
+    assert _ops.LAUNCHES_PER_STEP(4, False) == 15
