@@ -893,27 +893,31 @@ def _run_forward_fast(sp, labels, feats32, needs):
         hp.wait_stream(cur)
         st_s = C.c_void_p(hp.cuda_stream)
     with _timed("sample"):
-        _lib.check(lib.mscs_sample_plan(C.byref(sp.cfg), labels.data_ptr(), e.ws, e.plan_dev, st_s), "mscs_sample_plan")
-        _lib.check(lib.mscs_fill_bytes(e.fill_ptrs, e.fill_vals, e.fill_bytes, 2, st_s), "mscs_fill_bytes")
-        _t = _seg("fwd: workspace + plan kernels", _t)
-        # dense gradients: pre-zeroed on a side stream, sampled sectors rewritten by the backward (MSCS_DENSE=1: the
-        # backward writes them in one streaming pass instead -- measured equal, see gather.cu).  Started here, next
-        # to the small sampling kernels: the fill (535 MB at cfg-2) costs ~70 us of step time WHEREVER it runs
-        # (measured next to the sampling kernels, under the forward, under the backward, and as a device-to-device
-        # copy from a persistent zero buffer) -- memset and D2D copies run on the SMs.
-        gradbufs = _GradBuffers(feats32, needs, sp.nhwc, sp.dF_n) \
-            if (any(needs) and (sp.nhwc or os.environ.get("MSCS_DENSE") != "1")) else None
-        if gradbufs is not None:
-            gradbufs.start_fill()
-        _t = _seg("fwd: grad buffers", _t)
+        # MT19937 output stream of this call (normally produced ahead of time during the previous step): looked up
+        # first, so that nothing but kernels sits between the launches of the sampling chain
         mt, pos = torch_mt_state()
         draws = _stream_cache(dev).acquire(mt, pos, sp.max_draws + _MT_N)
         if hp is not None:
             hp.wait_event(_stream_cache(dev).ready)
         _t = _seg("fwd: rng state + stream acquire", _t)
+        # dense gradients + gradient rows: pre-zeroed on a side stream, sampled sectors rewritten by the backward
+        # (MSCS_DENSE=1: the backward writes them in one streaming pass instead -- measured equal, see gather.cu).
+        # Started here, next to the small sampling kernels: the fill (535 MB at cfg-2) costs ~70 us of step time
+        # WHEREVER it runs (measured next to the sampling kernels, under the forward, under the backward, and as a
+        # device-to-device copy from a persistent zero buffer) -- memset and D2D copies run on the SMs.
+        gradbufs = _GradBuffers(feats32, needs, sp.nhwc, sp.dF_n) \
+            if (any(needs) and (sp.nhwc or os.environ.get("MSCS_DENSE") != "1")) else None
+        if gradbufs is not None:
+            gradbufs.start_fill()
+        _t = _seg("fwd: grad buffers", _t)
+        # workspace fills, then hist -> tile scan -> plan -> select back to back (programmatic dependent launches);
+        # the plan records travel to the host on a private stream (mscs_plan_fetch_begin)
+        _lib.check(lib.mscs_fill_bytes(e.fill_ptrs, e.fill_vals, e.fill_bytes, 2, st_s), "mscs_fill_bytes")
+        _lib.check(lib.mscs_sample_plan(C.byref(sp.cfg), labels.data_ptr(), e.ws, e.plan_dev, st_s), "mscs_sample_plan")
         _lib.check(lib.mscs_plan_fetch_begin(e.plan_dev, S, st_s), "mscs_plan_fetch_begin")
         _lib.check(lib.mscs_sample_select_async(C.byref(sp.cfg), e.plan_dev, sp.v_cap, e.ws, draws.data_ptr(), *e.arrs,
                                                 e.sarr, st_s), "mscs_sample_select_async")
+        _t = _seg("fwd: workspace + sampling kernels", _t)
         if hp is not None:
             cur.wait_stream(hp)
     with _timed("gather"):

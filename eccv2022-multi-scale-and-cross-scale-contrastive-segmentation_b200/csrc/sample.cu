@@ -359,6 +359,8 @@ struct SelectArgs {
 __global__ void __launch_bounds__(256)
 k_fy_select(const __grid_constant__ SampleLayout L, const __grid_constant__ SelectArgs a, char* ws,
             const uint32_t* __restrict__ draws) {
+  pdl_trigger();
+  pdl_wait();
   const int s = blockIdx.y, k = blockIdx.x;
   int T_s = a.T[s], V_s = a.V[s];
   long long base_s = a.draw_base[s];
@@ -599,24 +601,35 @@ extern "C" int mscs_sample_select_async(const mscs_sample_cfg* cfg, const mscs_s
   if (smem > 48 * 1024)
     MSCS_CUDA(cudaFuncSetAttribute(k_fy_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(t_cap, L.S);
-  k_fy_select<<<grid, 256, smem, st>>>(L, a, (char*)workspace, draws_dev);
+  MSCS_CUDA(launch_k(k_fy_select, grid, 256, smem, st, L, a, (char*)workspace, draws_dev));
   MSCS_LAUNCH_CHECK();
   return 0;
 }
 
 // Split plan fetch: begin = async D2H into a pinned staging buffer + event; end = wait for that event only
-// (work enqueued after begin keeps running) and hand the records out.
+// (work enqueued after begin keeps running) and hand the records out.  The copy runs on a private stream that
+// waits for the producer stream's position at the call: the producer stream itself (selection kernel next) does
+// not queue behind the copy.
 static thread_local mscs_scale_plan* t_plan_pinned = nullptr;
 static thread_local cudaEvent_t t_plan_event = nullptr;
+static thread_local cudaEvent_t t_plan_src_event = nullptr;
+static thread_local cudaStream_t t_plan_stream = nullptr;
 extern "C" int mscs_plan_fetch_begin(const mscs_scale_plan* plan_dev, int num_scales, void* stream_) {
   MSCS_CHECK_ARG(plan_dev && num_scales >= 1 && num_scales <= MSCS_MAX_SCALES, "bad arguments");
   cudaStream_t st = (cudaStream_t)stream_;
   if (!t_plan_pinned) {
     MSCS_CUDA(cudaHostAlloc((void**)&t_plan_pinned, sizeof(mscs_scale_plan) * MSCS_MAX_SCALES, cudaHostAllocDefault));
     MSCS_CUDA(cudaEventCreateWithFlags(&t_plan_event, cudaEventDisableTiming));
+    MSCS_CUDA(cudaEventCreateWithFlags(&t_plan_src_event, cudaEventDisableTiming));
+    int lo = 0, hi = 0;
+    MSCS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    MSCS_CUDA(cudaStreamCreateWithPriority(&t_plan_stream, cudaStreamNonBlocking, hi));
   }
-  MSCS_CUDA(cudaMemcpyAsync(t_plan_pinned, plan_dev, sizeof(mscs_scale_plan) * num_scales, cudaMemcpyDeviceToHost, st));
-  MSCS_CUDA(cudaEventRecord(t_plan_event, st));
+  MSCS_CUDA(cudaEventRecord(t_plan_src_event, st));
+  MSCS_CUDA(cudaStreamWaitEvent(t_plan_stream, t_plan_src_event, 0));
+  MSCS_CUDA(cudaMemcpyAsync(t_plan_pinned, plan_dev, sizeof(mscs_scale_plan) * num_scales, cudaMemcpyDeviceToHost,
+                            t_plan_stream));
+  MSCS_CUDA(cudaEventRecord(t_plan_event, t_plan_stream));
   return 0;
 }
 extern "C" int mscs_plan_fetch_end(mscs_scale_plan* plan_host, int num_scales) {

@@ -109,7 +109,8 @@ int mscs_sample_plan_from_counts(const mscs_sample_cfg* cfg, const int32_t* cons
 int mscs_plan_fetch(const mscs_scale_plan* plan_dev, mscs_scale_plan* plan_host, int num_scales,
                     void* stream);
 /* The same fetch split in two, so that work enqueued in between overlaps the host wait: begin = async copy into a
- * pinned staging buffer + event record on `stream`; end = wait for that event only, then hand the records out.
+ * pinned staging buffer, ordered after what `stream` holds at the call but executed on a private stream (work enqueued
+ * on `stream` afterwards does not queue behind the copy); end = wait for that copy only, then hand the records out.
  * (One outstanding fetch per host thread.) */
 int mscs_plan_fetch_begin(const mscs_scale_plan* plan_dev, int num_scales, void* stream);
 int mscs_plan_fetch_end(mscs_scale_plan* plan_host, int num_scales);
