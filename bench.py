@@ -13,6 +13,10 @@ sharded over the ranks, keys exchanged over NCCL): total work fixed -> strong sc
 
 Prints ONE JSON line (rank 0).  `--impl reference` times the CPU port of the reference
 (oracle/torch_port.py -- /root/reference is Python and cannot travel to the GPU box) on the host.
+Defaults: K=100 timed steps after W=20 warm-up steps (a step is ~1 ms; the short 20/5 default of the first
+versions made the timed region sensitive to the start-up of a fresh process); `--impl reference`: K=5, W=1 (a CPU
+step takes seconds) and never more than ~4 minutes in total, whatever K/W ask for (the JSON line says how many
+steps were timed).
 """
 import argparse
 import json
@@ -112,7 +116,7 @@ def cpu_port_step(labels, feats, ocfg, torch_port):
     return dt, [int(i.shape[0] * i.shape[1]) for i in idx], float(total)
 
 
-def cpu_sample(workload, steps, warmup):
+def cpu_sample(workload, steps, warmup, budget_s=None):
     """Reference-port timing on the host cores on a bounded sample of the workload."""
     from mscs_b200 import synth
     from oracle import torch_port
@@ -129,26 +133,33 @@ def cpu_sample(workload, steps, warmup):
     cores = os.cpu_count()
     torch.set_num_threads(cores)
     times, NS = [], None
+    if budget_s is not None:
+        warmup = min(warmup, 2)      # a CPU step is seconds long and warm after one pass (thread pool, allocator)
+    t_begin = time.perf_counter()
     for i in range(warmup + steps):
         torch.manual_seed(i)
         dt, NS, _ = cpu_port_step(labels, feats, ocfg, torch_port)
         if i >= warmup:
             times.append(dt)
+        # a CPU step takes seconds: stop early (and say so in `sample`) rather than run for longer than budget_s
+        if budget_s is not None and len(times) >= 3 and time.perf_counter() - t_begin + dt > budget_s:
+            break
     pairs = pairs_per_step(NS, ocfg["cross_scale"])
     sec = sum(times) / len(times)
     return dict(value=pairs / sec, unit=UNIT, cores=cores, kind="port",
                 sample=f"first {nimg} of {cfg['n']} images of the {workload} inputs "
-                       f"(N per scale {NS}, {pairs:.3e} anchor-pairs/step), {len(times)} timed steps after "
+                       f"(N per scale {NS}, {pairs:.3e} anchor-pairs/step), {len(times)} timed steps"
+                       f"{'' if len(times) == steps else f' (of {steps} requested: time budget {budget_s:.0f} s)'} after "
                        f"{warmup} warm-up, torch {torch.__version__} CPU fp32, {torch.get_num_threads()} threads",
-                seconds_per_step=sec, pairs_per_step=pairs)
+                seconds_per_step=sec, pairs_per_step=pairs, steps_timed=len(times))
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    cb = cpu_sample(args.workload, args.steps, args.warmup)
+    cb = cpu_sample(args.workload, args.steps, args.warmup, budget_s=240.0)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["seconds_per_step"] * 1e3,
+            "steps": cb["steps_timed"], "warmup": min(args.warmup, 2), "ms_per_step": cb["seconds_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "sample": cb["sample"]},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -160,8 +171,10 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    # a step is ~1 ms: the defaults keep the timed region (0.1 s) well above start-up effects of a fresh process
+    # (cold page cache, allocator growth); the whole default run still takes well under a minute
+    ap.add_argument("--steps", type=int, default=None, help="default: 100 (--impl reference: 5)")
+    ap.add_argument("--warmup", type=int, default=None, help="default: 20 (--impl reference: 1)")
     ap.add_argument("--impl", default="mscs", choices=["mscs", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -169,6 +182,9 @@ def main():
                     help="memory order of the feature maps: nchw = what the reference's projector emits (headline); "
                          "nhwc = torch.channels_last (row gather / scatter)")
     args = ap.parse_args()
+    ref = args.impl == "reference"       # a reference step is seconds of CPU work, one of ours a millisecond
+    args.steps = args.steps if args.steps is not None else (5 if ref else 100)
+    args.warmup = args.warmup if args.warmup is not None else (1 if ref else 20)
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
@@ -297,7 +313,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
-    n_e2e = max(3, args.steps // 2)
+    n_e2e = max(3, min(args.steps // 2, 40))
     for i in range(3):
         e2e_step(i)
     e2e_serial_ms = timed(lambda: [e2e_step(200 + i) for i in range(n_e2e)]) / n_e2e
