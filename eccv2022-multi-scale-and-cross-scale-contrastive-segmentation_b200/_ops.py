@@ -75,6 +75,10 @@ class LossSpec:
     detach_deepest: bool = False
     w_high_low: float = 1.0
     w_high_mid: float = 1.0
+    # not reference keys: "reference" = the torch CPU generator consumed exactly like the reference's randperm calls;
+    # "philox" = opt-in counter-based stream keyed by (sampler_seed, call index)
+    sampler: str = "reference"
+    seed: int = 0
 
 
 class ScaleSample:
@@ -834,6 +838,7 @@ class _Workspace:
             it.inv_norm = self.fbase + 4 * sp.foff[s][1]
         self.plan = (_lib.ScalePlan * S)()
         self.last_stream = None
+        self.philox = None          # stream buffer of the opt-in counter-based sampler (allocated on first use)
 
 
 class _StepState:
@@ -846,13 +851,17 @@ class _StepState:
             self.sp.ws_pool.append(e)
 
 
-def run_forward(sp, labels, feats32, needs, comm=None):
+def run_forward(sp, labels, feats32, needs, comm=None, philox=None):
+    """philox: None (reference stream: torch CPU generator) or (seed, call index) of the opt-in counter-based stream."""
     pooled = comm is not None and comm.world > 1
     # device-driven order (selection, gather and similarity forward enqueued before the host sees the plan): single
     # process, every plane a multiple of 8 pixels (slot maps), selection shared memory within limits
     if fast_path_ok(sp.spec, 1 if not pooled else comm.world) and (sp.nhwc or all(x != 0 for x in sp.slot_sizes)):
-        return _run_forward_fast(sp, labels, feats32, needs)
+        return _run_forward_fast(sp, labels, feats32, needs, philox)
     assert not sp.nhwc, "channels-last inputs are converted by the caller unless the fast path applies"
+    if philox is not None:
+        raise NotImplementedError("sampler='philox' is implemented for the single-process path with feature planes "
+                                  "that are a multiple of 8 pixels (or channels-last inputs)")
     return _run_forward_general(sp, labels, feats32, needs, comm, pooled)
 
 
@@ -869,7 +878,7 @@ def _finish_rng(sp, dev, mt, pos, total):
     _stream_cache(dev).release_and_prefetch(mt2, pos2, sp.max_draws + _MT_N)
 
 
-def _run_forward_fast(sp, labels, feats32, needs):
+def _run_forward_fast(sp, labels, feats32, needs, philox=None):
     """Single process.  Selection, gather AND the similarity forward are driven by the DEVICE plan records and enqueued
     before the host looks at the plan: the one host wait of the forward pass (needed to raise the reference's errors
     and to size the backward) overlaps ~0.5 ms of queued GPU work instead of draining the stream."""
@@ -895,10 +904,17 @@ def _run_forward_fast(sp, labels, feats32, needs):
     with _timed("sample"):
         # MT19937 output stream of this call (normally produced ahead of time during the previous step): looked up
         # first, so that nothing but kernels sits between the launches of the sampling chain
-        mt, pos = torch_mt_state()
-        draws = _stream_cache(dev).acquire(mt, pos, sp.max_draws + _MT_N)
-        if hp is not None:
-            hp.wait_event(_stream_cache(dev).ready)
+        if philox is None:
+            mt, pos = torch_mt_state()
+            draws_ptr = _stream_cache(dev).acquire(mt, pos, sp.max_draws + _MT_N).data_ptr()
+            if hp is not None:
+                hp.wait_event(_stream_cache(dev).ready)
+        else:       # counter-based stream of this call: one small kernel in front of the chain, no generator state
+            if e.philox is None:
+                e.philox = torch.empty((sp.max_draws + 3) // 4 * 4 + 4, dtype=torch.int32, device=dev)
+            draws_ptr = e.philox.data_ptr()
+            _lib.check(lib.mscs_philox_stream(int(philox[0]) & (2 ** 64 - 1), int(philox[1]), sp.max_draws, draws_ptr,
+                                              st_s), "mscs_philox_stream")
         _t = _seg("fwd: rng state + stream acquire", _t)
         # dense gradients + gradient rows: pre-zeroed on a side stream, sampled sectors rewritten by the backward
         # (MSCS_DENSE=1: the backward writes them in one streaming pass instead -- measured equal, see gather.cu).
@@ -915,7 +931,7 @@ def _run_forward_fast(sp, labels, feats32, needs):
         _lib.check(lib.mscs_fill_bytes(e.fill_ptrs, e.fill_vals, e.fill_bytes, 2, st_s), "mscs_fill_bytes")
         _lib.check(lib.mscs_sample_plan(C.byref(sp.cfg), labels.data_ptr(), e.ws, e.plan_dev, st_s), "mscs_sample_plan")
         _lib.check(lib.mscs_plan_fetch_begin(e.plan_dev, S, st_s), "mscs_plan_fetch_begin")
-        _lib.check(lib.mscs_sample_select_async(C.byref(sp.cfg), e.plan_dev, sp.v_cap, e.ws, draws.data_ptr(), *e.arrs,
+        _lib.check(lib.mscs_sample_select_async(C.byref(sp.cfg), e.plan_dev, sp.v_cap, e.ws, draws_ptr, *e.arrs,
                                                 e.sarr, st_s), "mscs_sample_select_async")
         _t = _seg("fwd: workspace + sampling kernels", _t)
         if hp is not None:
@@ -947,7 +963,8 @@ def _run_forward_fast(sp, labels, feats32, needs):
         t = e.job_bwd.terms[i]
         t.N1, t.N2 = samples[a].N, samples[k].N
     _t = _seg("fwd: after wait", _t)
-    _finish_rng(sp, dev, mt, pos, total)
+    if philox is None:
+        _finish_rng(sp, dev, mt, pos, total)
     _t = _seg("fwd: rng advance + prefetch", _t)
     state.job, state.samples, state.gradbufs, state.slots = e.job_bwd, samples, gradbufs, e.slots
     state.keep, state.stats, state.fslab = out, e.stats, e.fslab
@@ -1231,7 +1248,7 @@ class MsCsContrastiveFn(torch.autograd.Function):
             world, rank = (comm.world, comm.rank) if comm is not None else (1, 0)
             sp = _step_plan(feats32[0].device, labels.shape, [tuple(f.shape) for f in feats32], spec, single_scale,
                             world, rank, nhwc)
-            state = run_forward(sp, labels, feats32, needs, comm)
+            state = run_forward(sp, labels, feats32, needs, comm, holder.get("philox"))
         holder["samples"], holder["state"] = state.samples, state
         ctx.state, ctx.needs = state, needs
         ctx.shapes = [tuple(f.shape) for f in feats]

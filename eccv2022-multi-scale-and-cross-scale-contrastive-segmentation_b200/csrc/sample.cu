@@ -544,6 +544,51 @@ extern "C" int mscs_mt19937_stream(const uint32_t* mt_state_host, int mt_pos, ui
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// Opt-in counter-based permutation stream: Philox4x32-10 (Salmon et al., SC'11), word j of a
+// call = philox(counter = (j >> 2, 0, call lo, call hi), key = (seed lo, seed hi))[j & 3].  Random access: no
+// sequential generator state, no dependence on the torch CPU generator.  The stream-buffer convention of this
+// library is UNTEMPERED MT19937 words (k_fy_select applies the tempering), so the words are stored through the inverse
+// tempering: the consumer then sees exactly the Philox outputs (oracle/philox.py) and stays untouched.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mt_untemper(uint32_t y) {
+  y ^= y >> 18;
+  y ^= (y << 15) & 0xefc60000u;
+  uint32_t t = y;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) t = y ^ ((t << 7) & 0x9d2c5680u);
+  y = t;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) t = y ^ (t >> 11);
+  return t;
+}
+
+__global__ void __launch_bounds__(256)
+k_philox_stream(unsigned long long seed, unsigned long long call, unsigned long long n_quads, uint4* __restrict__ out) {
+  const unsigned long long q = (unsigned long long)blockIdx.x * 256ull + threadIdx.x;
+  if (q >= n_quads) return;
+  uint4 c = make_uint4((uint32_t)q, (uint32_t)(q >> 32), (uint32_t)call, (uint32_t)(call >> 32));
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[q] = make_uint4(mt_untemper(c.x), mt_untemper(c.y), mt_untemper(c.z), mt_untemper(c.w));
+}
+
+extern "C" int mscs_philox_stream(uint64_t seed, uint64_t call, uint64_t n_words, uint32_t* draws_dev, void* stream_) {
+  MSCS_CHECK_ARG(draws_dev && ((uintptr_t)draws_dev & 15) == 0, "draws_dev must be a 16-byte aligned device pointer");
+  if (n_words == 0) return 0;
+  const unsigned long long quads = (n_words + 3) / 4;       // the buffer holds n_words rounded up to 4 words
+  MSCS_CHECK_ARG(quads <= 0x7fffffffull * 256ull, "stream too long");
+  k_philox_stream<<<(unsigned)((quads + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(seed, call, quads, (uint4*)draws_dev);
+  MSCS_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int mscs_sample_select(const mscs_sample_cfg* cfg, const mscs_scale_plan* plan_host, void* workspace,
                                   const uint32_t* draws_dev, int32_t* const* idx_ref, int32_t* const* pair_ref,
                                   int32_t* const* pix, int32_t* const* cls, int32_t* const* seg,

@@ -37,7 +37,24 @@ def _spec_from_config(config, scales, weights, ms=False):
         weights=[float(w) for w in weights],
         cross_scale=bool(config.get("cross_scale_contrast", False)),                     # V2.py:23, _ms.py:27
         detach_deepest=bool(config.get("detach_deepest", False)),                        # _ms.py:29
-        w_high_low=float(config.get("w_high_low", 1.0)), w_high_mid=float(config.get("w_high_mid", 1.0)))
+        w_high_low=float(config.get("w_high_low", 1.0)), w_high_mid=float(config.get("w_high_mid", 1.0)),
+        sampler=_sampler_key(config), seed=int(config.get("sampler_seed", 0)))
+
+
+def _sampler_key(config):
+    """``sampler`` is NOT a reference key: "reference" (default) consumes the torch CPU generator exactly like the
+    reference's ``torch.randperm`` calls (V2.py:121); "philox" draws the permutations from a counter-based stream keyed
+    by (``sampler_seed``, call index of the module) and leaves the torch generator alone."""
+    s = str(config.get("sampler", "reference"))
+    if s not in ("reference", "philox"):
+        raise ValueError(f"sampler must be 'reference' or 'philox', got {s!r}")
+    return s
+
+
+def _philox_key(module, holder):
+    if module._spec.sampler == "philox":
+        holder["philox"] = (module._spec.seed, module._sampler_calls)
+        module._sampler_calls += 1
 
 
 class DenseContrastiveLossV2(nn.Module):
@@ -61,9 +78,11 @@ class DenseContrastiveLossV2(nn.Module):
         self.log_this_step = False
         self._scale = None
         self.last_samples = None
+        self._sampler_calls = 0
 
     def forward(self, label: torch.Tensor, features: torch.Tensor):
         holder = {}
+        _philox_key(self, holder)
         self._spec.num_classes = self.num_all_classes          # the reference lets callers override it (V2.py:238)
         total, _terms = MsCsContrastiveFn.apply(label, self._spec, True, holder, features)
         smp = holder["samples"][0]
@@ -112,6 +131,7 @@ class DenseContrastiveLossV2_ms(nn.Module):
         self.ms_losses, self.cs_losses = [], []
         self.log_this_step = False
         self.last_samples = None
+        self._sampler_calls = 0
 
     def forward(self, label: torch.Tensor, features: list, **kwargs):
         self.cs_losses, self.ms_losses = [], []
@@ -121,6 +141,7 @@ class DenseContrastiveLossV2_ms(nn.Module):
         if self.cross_scale_contrast:
             assert len(feats) > 1                            # _ms.py:63
         holder = {"comm": self.comm}
+        _philox_key(self, holder)
         total, terms = MsCsContrastiveFn.apply(label, self._spec, False, holder, *feats)
         state = holder["state"]
         self.last_samples, self.last_state = holder["samples"], state

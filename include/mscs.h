@@ -121,6 +121,11 @@ int mscs_plan_fetch_end(mscs_scale_plan* plan_host, int num_scales);
  * depends on the generator state, so the host side produces it ahead of time on a side stream. */
 int mscs_mt19937_stream(const uint32_t* mt_state_host, int mt_pos, uint64_t n_words, uint32_t* draws_dev,
                         void* stream);
+/* Opt-in counter-based stream (not a reference behaviour): `n_words` words of Philox4x32-10,
+ * word j = philox(counter = (j >> 2, 0, call lo, call hi), key = (seed lo, seed hi))[j & 3], stored in the same
+ * buffer convention as mscs_mt19937_stream (the selection kernel tempers what it reads, so the words are stored through
+ * the inverse tempering).  draws_dev: 16-byte aligned, n_words rounded up to a multiple of 4 words. */
+int mscs_philox_stream(uint64_t seed, uint64_t call, uint64_t n_words, uint32_t* draws_dev, void* stream);
 /* Phase 2 (async): per-pair Fisher-Yates prefix + rank->pixel selection from a precomputed stream.
  *   draws_dev : MT19937 stream starting at the generator position of this call;
  * outputs per scale s (arrays of N_s entries, N_s from the fetched plan):

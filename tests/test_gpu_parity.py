@@ -688,3 +688,57 @@ def test_channels_last_second_backward_half_and_no_grad(dev):
     with torch.no_grad():
         l2 = mod(labels, _nhwc(base))
     assert abs(float(l2) - float(loss)) <= 1e-6 * abs(float(loss))
+
+
+# ---- opt-in counter-based sampler ----------------------------------------------------
+@pytest.mark.gpu
+def test_philox_stream_kernel_matches_oracle(dev):
+    """mscs_philox_stream stores the words through the inverse MT19937 tempering (the selection kernel tempers what
+    it reads): tempering the buffer must give exactly the oracle's Philox4x32-10 stream."""
+    import mscs_b200
+    from oracle.mt19937 import temper
+    from oracle.philox import stream_words
+    lib = mscs_b200.load()
+    seed, call, n = 0xDEADBEEF12345678, 41, 100003
+    buf = torch.zeros((n + 3) // 4 * 4, dtype=torch.int32, device=dev)
+    rc = lib.mscs_philox_stream(seed, call, n, buf.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, lib.mscs_last_error()
+    got = temper(buf.cpu().numpy().view(np.uint32)[:n])
+    assert np.array_equal(got, stream_words(seed, call, 0, n))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_philox_sampler_matches_oracle_fed_the_same_stream(layout, dev):
+    """sampler='philox': the sampled indices equal the sampling oracle's when it consumes the same counter-based stream
+    (scale after scale, pair after pair, like the reference consumes its generator); the torch CPU generator is left
+    alone; consecutive calls use consecutive call indices."""
+    import mscs_b200
+    from mscs_b200 import synth
+    from oracle import sampling
+    from oracle.philox import PhiloxStream
+    cfg = dict(dataset="CITYSCAPES", experiment=1, temperature=0.1, scales=3, weights=[1.0, 0.7, 0.4],
+               cross_scale_contrast=True, min_views_per_class=5, max_views_per_class=40, max_features_total=600,
+               sampler="philox", sampler_seed=99)
+    labels = synth.synth_labels(2, 128, 256, 19, 6, 16, 0.05, 1)
+    feats = synth.synth_features(2, 128, 128, 256, [4, 8, 16], 2)
+    mod = mscs_b200.DenseContrastiveLossV2_ms(cfg)
+    torch.manual_seed(5)
+    rng0 = torch.get_rng_state().clone()
+    seen = []
+    for call in range(2):
+        fg = [(f.to(dev) if layout == "nchw" else _nhwc(f.to(dev))).requires_grad_(True) for f in feats]
+        loss = mod(labels.to(dev), fg)
+        loss.backward()
+        assert torch.isfinite(loss) and all(torch.isfinite(f.grad).all() for f in fg)
+        gen = PhiloxStream(99, call)
+        for s, smp in enumerate(mod.last_samples):
+            want = sampling.sample_indices(labels.numpy(), feats[s].shape[-1], 20, 5, 40, 600, gen)
+            assert (smp.T, smp.V) == (want["T"], want["V"])
+            assert np.array_equal(smp.idx_ref.cpu().numpy(), want["idx"]), (call, s)
+            assert np.array_equal(smp.pair_ref.cpu().numpy(), want["pairs"])
+        seen.append(mod.last_samples[0].idx_ref.clone())
+    assert not torch.equal(seen[0], seen[1])
+    assert torch.equal(torch.get_rng_state(), rng0), "the counter-based sampler must not touch the torch generator"
+    with pytest.raises(ValueError):
+        mscs_b200.DenseContrastiveLossV2(dict(dataset="CITYSCAPES", experiment=1, sampler="nope"))

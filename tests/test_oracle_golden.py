@@ -106,3 +106,32 @@ def test_big_sampling_hashes(name, golden):
                            ocfg["max_views"], ocfg["max_total"], gen)
         assert [o["T"], o["V"]] == meta["TV"][s]
         assert hashlib.sha256(np.ascontiguousarray(o["idx"].astype(np.int64)).tobytes()).hexdigest() == meta["idx_sha"][s]
+
+
+def test_philox_known_answers_and_stream():
+    """Philox4x32-10 restatement (oracle/philox.py) against the known-answer vectors of the Random123 distribution
+    (kat_vectors: zero, all-ones and pi-digit counters/keys), and the stream layout used by the opt-in sampler."""
+    from oracle.philox import PhiloxStream, philox4x32_10, stream_words
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = philox4x32_10([np.uint32(c) for c in ctr], [np.uint32(k) for k in key])
+        assert tuple(int(g) for g in got) == want
+    seed, call = 0x1234567887654321, 7
+    w = stream_words(seed, call, 0, 64)
+    blk3 = philox4x32_10([np.uint32(3), np.uint32(0), np.uint32(call), np.uint32(0)],
+                         [np.uint32(seed & 0xffffffff), np.uint32(seed >> 32)])
+    assert [int(x) for x in w[12:16]] == [int(x) for x in blk3]
+    assert np.array_equal(stream_words(seed, call, 5, 20), w[5:25])
+    g = PhiloxStream(seed, call)
+    assert np.array_equal(np.concatenate([g.draw(3), g.draw(10), g.draw(51)]), w)
+    assert not np.array_equal(stream_words(seed, call + 1, 0, 64), w)
+    # the sampling oracle runs unchanged on this generator (same draw(k) interface as MT19937)
+    from oracle import sampling
+    lab = np.random.default_rng(0).integers(0, 4, (2, 16, 32)).astype(np.int64)
+    a = sampling.sample_indices(lab, 16, 5, 2, 8, 1000, PhiloxStream(1, 0))
+    b = sampling.sample_indices(lab, 16, 5, 2, 8, 1000, PhiloxStream(1, 0))
+    c = sampling.sample_indices(lab, 16, 5, 2, 8, 1000, PhiloxStream(1, 1))
+    assert np.array_equal(a["idx"], b["idx"]) and not np.array_equal(a["idx"], c["idx"])
