@@ -154,6 +154,13 @@ def cpu_sample(workload, steps, warmup, budget_s=None):
                 seconds_per_step=sec, pairs_per_step=pairs, steps_timed=len(times))
 
 
+def workload_name(workload):
+    """`config.workload` of the JSON line -- the same string on both arms (the driver pairs the lines by it)."""
+    return f"{workload}: " + {
+        "cfg2": "HRNet-W48 Cityscapes ms+cs loss, 4 scales, 512x1024 crops, bs 12, 256-d projector",
+        "cfg5": "pooled cross-batch anchors, bs 64 in total, ms+cs, max_features_total 65536"}.get(workload, workload)
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -161,7 +168,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": cb["steps_timed"], "warmup": min(args.warmup, 2), "ms_per_step": cb["seconds_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "sample": cb["sample"]},
+            "config": {"workload": workload_name(args.workload), "sample": cb["sample"]},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -368,10 +375,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong" if pooled else "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: " + {
-                "cfg2": "HRNet-W48 Cityscapes ms+cs loss, 4 scales, 512x1024 crops, bs 12, 256-d projector",
-                "cfg5": "pooled cross-batch anchors, bs 64 in total, ms+cs, max_features_total 65536"}.get(
-                    args.workload, args.workload),
+            "config": {"workload": workload_name(args.workload),
                 "layout": args.layout, "anchors_per_scale": NS, "anchor_pairs_per_step": pairs, "per_gpu_batch": cfg["n"],
                 "l2": "inputs (535 MB of features per step) exceed the 126 MB L2; no explicit flush",
                 "parallelism": (f"pooled anchors, rows sharded x{world}, keys/statistics/gradient rows exchanged "
