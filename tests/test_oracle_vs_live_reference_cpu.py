@@ -21,6 +21,8 @@ import torch
 ROOT = sys.argv[1]
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import helpers                                # random_case(): the generator shared with the GPU parity test
 import make_golden as mg                      # import_reference(), ref_indices(): the shims of SURVEY.md 8c
 from mscs_b200 import synth
 from oracle import loss_fp64, torch_port
@@ -30,51 +32,16 @@ from oracle.mt19937 import MT19937
 DCV2, DCV2ms, INFO = mg.import_reference()
 torch.set_num_threads(4)
 rs = np.random.RandomState(20221017)
-DATASETS = [("CITYSCAPES", 1, 19), ("CADIS", 2, 17), ("CADIS", 1, 8), ("ADE20K", 1, 150)]   # (name, exp, real classes fed)
 n_cases = int(sys.argv[2])
 done = refused = 0
 for case in range(n_cases):
-    ds, exp, nreal = DATASETS[rs.randint(len(DATASETS))]
-    A = len(INFO[ds].CLASS_INFO[exp][1])
-    has_ignore = 255 in INFO[ds].CLASS_INFO[exp][1]
-    S = int(rs.randint(1, 5))
-    single = S == 1
-    n = int(rs.randint(1, 4))
-    cell = int(rs.choice([4, 8]))
-    base = [int(rs.choice([2, 4])) * (2 ** s if rs.rand() < 0.8 else max(1, 2 ** (s - 1))) for s in range(S)]
-    strides = sorted(base)
-    top = strides[-1]
-    unit = int(np.lcm(cell, top))
-    if rs.rand() < 0.2:       # a map so small that the deepest scale keeps no (image, class) pair: both sides must raise (Q8)
-        H, W = unit, int(rs.randint(1, 3)) * unit
-    else:
-        H, W = int(rs.randint(3, 7)) * unit, int(rs.randint(4, 9)) * unit
-    # a ragged label map: a few extra rows / columns that the integer stride division drops (V2.py:46 uses widths only)
-    ragged = rs.rand() < 0.3
-    k = int(rs.randint(2, min(5, A - 1) + 1))
-    ignore_id = A - 1                                   # without a 255 key this is the last REAL class: dropped all the same (Q2)
-    labels = synth.synth_labels(n, H, W, ignore_id, k, cell, 0.1, int(rs.randint(1 << 30)))
-    C = int(rs.choice([8, 24, 48]))
-    g = torch.Generator().manual_seed(int(rs.randint(1 << 30)))
-    feats = [torch.randn(n, C, H // s, W // s, generator=g) for s in strides]
-    if ragged:
-        pad = int(rs.randint(1, strides[0]))
-        labels = torch.nn.functional.pad(labels, (0, pad, 0, 0), value=int(labels[0, 0, 0]))
-        if any(labels.shape[-1] // f.shape[-1] != s for f, s in zip(feats, strides)):
-            continue
-    cfg = dict(dataset=ds, experiment=exp, temperature=float(rs.choice([0.07, 0.1, 0.5])),
-               min_views_per_class=int(rs.randint(2, 6)), max_views_per_class=int(rs.choice([1, 7, 30, 2500])),
-               max_features_total=int(rs.choice([60, 300, 10000])))
-    if not single:
-        cfg.update(scales=S, weights=[float(x) for x in rs.rand(S).round(2) + 0.1],
-                   cross_scale_contrast=bool(rs.rand() < 0.75), detach_deepest=bool(rs.rand() < 0.3),
-                   w_high_low=float(rs.choice([1.0, 0.5])), w_high_mid=float(rs.choice([1.0, 0.25])))
-        if rs.rand() < 0.3:
-            cfg["cross_scale_temperature"] = 0.3      # presence of the key -> 0.1 (Q5)
-    ocfg = oracle_cfg(cfg, A)
-    if single:
-        ocfg["cross_scale"], ocfg["weights"], ocfg["scales"] = False, [1.0], 1
-    seed = int(rs.randint(1 << 30))
+    rc = helpers.random_case(rs)
+    if rc is None:
+        continue
+    cfg, single, labels, feats, seed, S = rc["cfg"], rc["single"], rc["labels"], rc["feats"], rc["seed"], rc["S"]
+    A = len(INFO[cfg["dataset"]].CLASS_INFO[cfg["experiment"]][1])
+    assert A == helpers.CLASSES[(cfg["dataset"], cfg["experiment"])]
+    ocfg = helpers.oracle_cfg_for(dict(loss_cfg=cfg, single_scale=single))
     fg = [f.clone().requires_grad_(True) for f in feats]
     torch.manual_seed(seed)
     state0 = torch.get_rng_state()
