@@ -143,3 +143,42 @@ def test_step_plan_slab_layout():
     sp2 = _ops._StepPlan(torch.device("cpu"), (2, 60, 100), [(2, 32, 15, 25)], spec, True)
     assert sp2.slot_sizes == [0]
     assert _ops.LAUNCHES_PER_STEP(4, False) == 15
+
+
+def test_launch_count_claim_matches_committed_launch_list():
+    """`gpu_launches` of the bench line is LAUNCHES_PER_STEP x steps: the per-step figure must equal the number of
+    libmscs.so kernels between two `k_label_hist` launches of the committed ncu launch list (same command)."""
+    import csv
+    for name in ("r01_launches_cfg2.csv",):     # the channels-last list predates the merged work-table launch (16 then)
+        rows = [r for r in csv.reader(open(os.path.join(ROOT, "profiles", name))) if r and r[0].isdigit()]
+        names = [r[4] for r in rows]
+        first = [i for i, n in enumerate(names) if "k_label_hist" in n]
+        assert len(first) >= 2, name
+        step = names[first[0]:first[1]]
+        ours = [n for n in step if re.search(r"\bk_[a-z_0-9]+", n) and "at::" not in n]
+        assert len(ours) == _ops.LAUNCHES_PER_STEP(4, False), (name, ours)
+        assert any("k_sim_fwd" in n for n in ours) and any("k_sim_bwd" in n for n in ours)
+
+
+def test_plan_errors_map_to_the_reference_exceptions():
+    """Q8: no kept pair -> RuntimeError (torch.min of an empty tensor, V2.py:110); a kept class with one pixel ->
+    IndexError (0-d squeeze, V2.py:119-121); error codes come from the device plan records."""
+    spec = _ops.LossSpec(num_classes=20, temperature=0.1, cs_temperature=0.1, min_views=5)
+    plan = (_lib.ScalePlan * 2)()
+    _ops._raise_plan_errors(plan, 2, spec)            # both clean
+    plan[1].error = 1
+    with pytest.raises(RuntimeError, match="scale 1.*min_views_per_class=5"):
+        _ops._raise_plan_errors(plan, 2, spec)
+    plan[0].error = 2                                   # the first failing scale wins, like the reference's scale loop
+    with pytest.raises(IndexError, match="scale 0"):
+        _ops._raise_plan_errors(plan, 2, spec)
+
+
+def test_fast_path_gate():
+    """Device-driven order: single process and a selection table (12 B per view) within 200 KB of shared memory."""
+    mk = lambda **kw: _ops.LossSpec(num_classes=20, temperature=0.1, cs_temperature=0.1, **kw)
+    assert _ops.fast_path_ok(mk(), 1)                                   # reference defaults: V <= 2500
+    assert not _ops.fast_path_ok(mk(), 2)                               # pooled mode takes the host-driven order
+    assert _ops.fast_path_ok(mk(max_views=1, max_total=10000), 1)       # max_views == 1 means "no per-class cap" (Q3)
+    assert _ops.fast_path_ok(mk(max_views=1, max_total=65536), 1)       # V is capped at 16384 views: 192 KB, just inside
+    assert _ops.fast_path_ok(mk(max_views=1000, max_total=32768), 1)    # cfg-4 large
