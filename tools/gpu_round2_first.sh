@@ -1,0 +1,12 @@
+#!/bin/bash
+# First GPU call of the next round: the parity suite with the random-case test widened from the 10 cases that ran green
+# on a B200 to 80 (all pinned against the live reference on the CPU side), the default bench line, and the stale
+# channels-last launch list refreshed (it predates the merged work-table launch: 16 kernels per step instead of 15).
+mkdir -p gpurun_out
+MSCS_GPU_RANDOM=80 timeout -s KILL 400 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/pytest_gpu_random80.log 2>&1
+echo "pytest (80 random cases) exit $?"; tail -3 gpurun_out/pytest_gpu_random80.log
+timeout -s KILL 300 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
+echo "bench exit $?"; tail -c 3800 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
+timeout -s KILL 200 ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 40 --csv \
+  --log-file gpurun_out/launches_nhwc.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --layout nhwc > gpurun_out/ncu_bench_nhwc.log 2>&1
+echo "ncu launches (nhwc) exit $?"
