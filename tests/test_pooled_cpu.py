@@ -94,3 +94,67 @@ def test_pooled_partition_gloo_world2():
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     for r in range(world):
         assert out[r] == (True, True, True), (r, out[r])
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_backward_needs_only_row_statistics(world):
+    """The algebra behind the pooled backward, in numpy with the oracle as
+    the single-process answer: once the row statistics (neg, S, P) of ALL rows are known on every rank, a rank forms
+    both G_ij (its rows as anchors) and G_ji (its rows as keys) itself, so the gradient rows of its 128-aligned row
+    range need no reduce-scatter -- single-scale: dF_i = sum_j (G_ij + G_ji) f_j / tau; cross-scale: dA for its anchor
+    rows, dK for its key rows.  Concatenating the ranks' row blocks must give the oracle's full gradients."""
+    from mscs_b200 import shard_rows
+    from oracle import loss_fp64
+    rng = np.random.RandomState(world)
+
+    def unit(n, c):
+        f = rng.randn(n, c)
+        return f / np.linalg.norm(f, axis=1, keepdims=True)
+
+    def G_block(Fa, ya, Fk, yk, st, tau, self_mask, rows_a, N1):
+        """G[rows_a, :] from the row statistics of those anchor rows."""
+        E = np.exp(Fa[rows_a] @ Fk.T / tau)
+        pos = ya[rows_a, None] == yk[None, :]
+        negm = ~pos
+        if self_mask:
+            pos[np.arange(len(rows_a)), rows_a] = False
+        P = st["P"][rows_a]
+        div = P if self_mask else np.where(P > 0, P, 1.0)
+        inv = (1.0 / (div * N1))[:, None]
+        n_i = st["neg"][rows_a, None]
+        return np.where(pos, -inv * n_i / (E + n_i), 0.0) + np.where(negm, inv * st["S"][rows_a, None] * E, 0.0)
+
+    # single-scale term: 1000 rows, 7 classes, class-sorted like the kernel layout
+    N, C, tau = 1000, 24, 0.1
+    F, y = unit(N, C), np.sort(rng.randint(0, 7, N))
+    _, da, dk, st = loss_fp64.term(F, y, F, y, tau, True)
+    want = da + dk
+    got = np.zeros_like(want)
+    allrows = np.arange(N)
+    for r in range(world):
+        b, e = shard_rows(N, world, r)
+        rows = np.arange(b, e)
+        if len(rows) == 0:
+            continue
+        G_rows = G_block(F, y, F, y, st, tau, True, rows, N)                 # G_ij, i in my rows
+        G_cols = G_block(F, y, F, y, st, tau, True, allrows, N)[:, rows]     # G_ji, i in my rows (from j's statistics)
+        got[b:e] = (G_rows + G_cols.T) @ F / tau
+    assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+
+    # cross-scale term: 900 anchors x 300 keys, some anchors without any positive (class 6 absent from the keys)
+    N1, N2, tau = 900, 300, 0.07
+    Fa, ya = unit(N1, C), np.sort(rng.randint(0, 7, N1))
+    Fk, yk = unit(N2, C), np.sort(rng.randint(0, 6, N2))
+    _, da, dk, st = loss_fp64.term(Fa, ya, Fk, yk, tau, False)
+    assert (st["P"] == 0).any()
+    got_a, got_k = np.zeros_like(da), np.zeros_like(dk)
+    G_full = G_block(Fa, ya, Fk, yk, st, tau, False, np.arange(N1), N1)
+    for r in range(world):
+        b, e = shard_rows(N1, world, r)
+        if e > b:
+            got_a[b:e] = G_block(Fa, ya, Fk, yk, st, tau, False, np.arange(b, e), N1) @ Fk / tau
+        kb, ke = shard_rows(N2, world, r)
+        if ke > kb:
+            got_k[kb:ke] = G_full[:, kb:ke].T @ Fa / tau                     # columns of G from the exchanged statistics
+    assert np.abs(got_a - da).max() <= 1e-12 * max(1.0, np.abs(da).max())
+    assert np.abs(got_k - dk).max() <= 1e-12 * max(1.0, np.abs(dk).max())
