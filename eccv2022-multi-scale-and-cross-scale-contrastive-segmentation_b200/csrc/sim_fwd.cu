@@ -64,6 +64,30 @@ __device__ __forceinline__ void fast_chunk(const uint32_t (&cur)[32], float scal
   }
 }
 
+#ifdef MSCS_LEAN
+// `make lean` (libmscs_lean.so, loaded through MSCS_LIB): the sweep-0 epilogue without the MSCS_DEBUG_FLAGS experiment
+// branches and with the four 32-column chunks processed by a loop of two iterations (two chunks each, so the register
+// double buffer keeps compile-time indices) instead of a fully unrolled body -- a code-size experiment: the default
+// epilogue is ~3000 straight-line instructions and 11 % of its warp-stall samples are instruction-cache misses
+// (profiles/r01_stall_summary.md).  Same arithmetic in the same order as the default build.
+__device__ __forceinline__ void lean_chunk(const uint32_t (&cur)[32], int c0, int tN2, int wmin, int wmax, int p0,
+                                           unsigned plen, float scale, float& acc0, float& acc1, float& acc2,
+                                           float& acc3) {
+  const bool fast = (c0 + 32 <= wmin || c0 >= wmax) && (c0 + 32 <= tN2);
+  if (fast) {
+    fast_chunk<0x88>(cur, scale, acc0, acc1, acc2, acc3);
+  } else if (c0 < tN2) {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const int col = c0 + c;
+      const float e = ptx::ex2(__uint_as_float(cur[c]) * scale);
+      const bool isneg = ((unsigned)(col - p0) >= plen) && (col < tN2);
+      acc0 += isneg ? e : 0.f;
+    }
+  }
+}
+#endif
+
 template <int KB, int MODE>
 __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constant__ FwdArgs args) {
   extern __shared__ uint8_t smem_raw[];
@@ -146,7 +170,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
           ptx::mbar_wait(&a_full[stage], phase, 113);
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
+#ifdef MSCS_LEAN
+            {
+#else
             if (!(args.debug_flags & 2)) {
+#endif
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const uint64_t ad = ptx::umma_desc_sw128(a_addr + stage * kBlkBytes + k * 32, 16, 1024);
@@ -195,10 +223,31 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
         ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1, 121);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kFwdKeys + ch * CPT;
+#ifdef MSCS_LEAN
+        if (MODE == 0) {
+          if (cb < tN2) {
+            static_assert(NCH % 2 == 0, "two chunks per iteration");
+            uint32_t va[32], vb[32];
+            ptx::tmem_ld32(taddr, va);
+            ptx::tmem_ld_wait(va);
+#pragma unroll 1
+            for (int c4 = 0; c4 < NCH; c4 += 2) {
+              ptx::tmem_ld32(taddr + (c4 + 1) * 32, vb);
+              lean_chunk(va, cb + c4 * 32, tN2, wmin, wmax, p0, plen, scale, acc0, acc1, acc2, acc3);
+              ptx::tmem_ld_wait(vb);
+              if (c4 + 2 < NCH) ptx::tmem_ld32(taddr + (c4 + 2) * 32, va);
+              lean_chunk(vb, cb + (c4 + 1) * 32, tN2, wmin, wmax, p0, plen, scale, acc0, acc1, acc2, acc3);
+              if (c4 + 2 < NCH) ptx::tmem_ld_wait(va);
+            }
+          }
+        } else if (false) {      // the default epilogue below is dead code in this build
+          if (false) {
+#else
         if (args.debug_flags & 1) {
           // experiment: no TMEM reads / math
         } else if (MODE == 0) {
-          if (cb < tN2) {      // a quarter that lies entirely in the zero padding of the key block has no work
+          if (cb < tN2) {
+#endif      // a quarter that lies entirely in the zero padding of the key block has no work
             uint32_t va[32], vb[32];
             ptx::tmem_ld32(taddr, va);
             ptx::tmem_ld_wait(va);
