@@ -70,6 +70,9 @@ __device__ __forceinline__ void fast_chunk(const uint32_t (&cur)[32], float scal
 // double buffer keeps compile-time indices) instead of a fully unrolled body -- a code-size experiment: the default
 // epilogue is ~3000 straight-line instructions and 11 % of its warp-stall samples are instruction-cache misses
 // (profiles/r01_stall_summary.md).  Same arithmetic in the same order as the default build.
+// MSCS_LEAN=2 (libmscs_lean2.so) additionally releases the accumulator buffer as soon as its last chunk has been read
+// into registers, i.e. one chunk of math (a quarter of the epilogue) earlier: with two buffers the tile period is
+// (MMA + buffer hold time) / 2.
 __device__ __forceinline__ void lean_chunk(const uint32_t (&cur)[32], int c0, int tN2, int wmin, int wmax, int p0,
                                            unsigned plen, float scale, float& acc0, float& acc1, float& acc2,
                                            float& acc3) {
@@ -224,6 +227,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kFwdKeys + ch * CPT;
 #ifdef MSCS_LEAN
+        bool released = false;
         if (MODE == 0) {
           if (cb < tN2) {
             static_assert(NCH % 2 == 0, "two chunks per iteration");
@@ -236,6 +240,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
               lean_chunk(va, cb + c4 * 32, tN2, wmin, wmax, p0, plen, scale, acc0, acc1, acc2, acc3);
               ptx::tmem_ld_wait(vb);
               if (c4 + 2 < NCH) ptx::tmem_ld32(taddr + (c4 + 2) * 32, va);
+#if MSCS_LEAN >= 2
+              else {      // the whole accumulator row is in registers: hand the buffer back before the last chunk's math
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+                released = true;
+              }
+#endif
               lean_chunk(vb, cb + (c4 + 1) * 32, tN2, wmin, wmax, p0, plen, scale, acc0, acc1, acc2, acc3);
               if (c4 + 2 < NCH) ptx::tmem_ld_wait(va);
             }
@@ -304,9 +316,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
             }
           }
         }
+#ifdef MSCS_LEAN
+        if (!released) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+        }
+#else
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+#endif
         if (valid) {
           if (MODE == 0) atomicAdd(&t.neg[row], (acc0 + acc1) + (acc2 + acc3));
           else if (touches) { atomicAdd(&t.pos[row], acc0 * kLn2); atomicAdd(&t.ssum[row], acc1); }
