@@ -72,7 +72,8 @@ __device__ __forceinline__ void fast_chunk(const uint32_t (&cur)[32], float scal
 // (profiles/r01_stall_summary.md).  Same arithmetic in the same order as the default build.
 // MSCS_LEAN=2 (libmscs_lean2.so) additionally releases the accumulator buffer as soon as its last chunk has been read
 // into registers, i.e. one chunk of math (a quarter of the epilogue) earlier: with two buffers the tile period is
-// (MMA + buffer hold time) / 2.
+// (MMA + buffer hold time) / 2.  MSCS_LEAN=3 (libmscs_lean3.so) additionally lets the MMA warp poll its barriers with
+// test_wait instead of suspending in try_wait (the backward kernel does; the forward never got it).
 __device__ __forceinline__ void lean_chunk(const uint32_t (&cur)[32], int c0, int tN2, int wmin, int wmax, int p0,
                                            unsigned plen, float scale, float& acc0, float& acc1, float& acc2,
                                            float& acc3) {
@@ -167,10 +168,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
       ptx::tc_fence_after();
       for (int rt = sg.c_begin; rt < sg.c_end; ++rt, ++it) {
         const uint32_t buf = it & 1;
+#if defined(MSCS_LEAN) && MSCS_LEAN >= 3      // polling wait for the warp that feeds the tensor pipe, as in sim_bwd.cu: a thread
+        ptx::mbar_spin_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1, 112);     // suspended in try_wait resumes ~250 cycles late
+#else
         ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1, 112);
+#endif
         ptx::tc_fence_after();
         for (int kb = 0; kb < KB; ++kb) {
+#if defined(MSCS_LEAN) && MSCS_LEAN >= 3
+          ptx::mbar_spin_wait(&a_full[stage], phase, 113);
+#else
           ptx::mbar_wait(&a_full[stage], phase, 113);
+#endif
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
 #ifdef MSCS_LEAN

@@ -11,15 +11,15 @@ timeout -s KILL 200 ncu --metrics gpu__time_duration.sum --clock-control none -s
   --log-file gpurun_out/launches_nhwc.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --layout nhwc > gpurun_out/ncu_bench_nhwc.log 2>&1
 echo "ncu launches (nhwc) exit $?"
 # A/B of the forward-epilogue variants (csrc: `make lean` before the call; sim_fwd.cu MSCS_LEAN = 1: smaller code,
-# 2: + accumulator buffer released before the last chunk's math): parity under each, then 3 interleaved bench rounds
+# 2: + accumulator buffer released before the last chunk's math, 3: + polling waits in the MMA warp): parity under each, then 3 interleaved bench rounds
 PKG=eccv2022-multi-scale-and-cross-scale-contrastive-segmentation_b200
-for v in 1 2; do
+for v in 1 2 3; do
   [ -f $PKG/libmscs_lean$v.so ] || continue
   MSCS_LIB=$PWD/$PKG/libmscs_lean$v.so timeout -s KILL 300 python -m pytest tests -m gpu -q --timeout 200 > gpurun_out/pytest_gpu_lean$v.log 2>&1
   echo "pytest (lean$v library) exit $?"; tail -1 gpurun_out/pytest_gpu_lean$v.log
 done
 for i in 1 2 3; do
-  for v in default lean1 lean2; do
+  for v in default lean1 lean2 lean3; do
     lib=$PWD/$PKG/libmscs_$v.so; [ $v = default ] && lib=$PWD/$PKG/libmscs.so
     [ -f $lib ] || continue
     MSCS_LIB=$lib timeout -s KILL 200 python bench.py --steps 50 --warmup 10 --no-cpu-baseline > gpurun_out/bench_${v}_$i.json 2> /dev/null
