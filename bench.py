@@ -11,12 +11,13 @@ this path) -> weak scaling; value = anchor-pairs of all ranks / max-over-ranks d
 `--workload cfg5` is the POOLED cross-batch configuration instead (64 images in total, anchor rows
 sharded over the ranks, keys exchanged over NCCL): total work fixed -> strong scaling.
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU port of the reference
-(oracle/torch_port.py -- /root/reference is Python and cannot travel to the GPU box) on the host.
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's own implementation on the host cores: the
+unmodified loss files staged under oracle/_ref/ (oracle/make_ref.py; /root/reference does not exist on the GPU box),
+or, if those are absent, the fp32 torch port of the oracle (oracle/torch_port.py).
 Defaults: K=100 timed steps after W=20 warm-up steps (a step is ~1 ms; the short 20/5 default of the first
 versions made the timed region sensitive to the start-up of a fresh process); `--impl reference`: K=5, W=1 (a CPU
-step takes seconds) and never more than ~4 minutes in total, whatever K/W ask for (the JSON line says how many
-steps were timed).
+step takes seconds); exactly K steps after W are timed on a bounded SAMPLE of the workload (the first images of the same
+batch), sized from a calibration step so that the run ends within ~4 minutes (`cpu_baseline.sample` says which).
 """
 import argparse
 import json
@@ -107,17 +108,49 @@ class ClockSampler:
                 "reasons": sorted(k for k, v in names.items() if bits & v), "samples": len(sm)}
 
 
-def cpu_port_step(labels, feats, ocfg, torch_port):
+def _ref_modules():
+    """The reference's own loss classes (oracle/_ref or /root/reference, unmodified; `.cuda()` neutralised so that they
+    run on the host cores), or None when the staged files are absent -- then the torch port of the oracle is timed."""
+    try:
+        from oracle import ref_loader
+        return ref_loader.load(cpu=True)
+    except FileNotFoundError:
+        return None
+
+
+def cpu_step(ref, cfg, ocfg, labels, feats, torch_port):
+    """One forward + backward of the loss on the host: the reference classes themselves (kind "reference") or the
+    fp32 torch port of the oracle (kind "port")."""
     fg = [f.clone().requires_grad_(True) for f in feats]
     t0 = time.perf_counter()
-    total, _ms, _cs, idx = torch_port.ms_cs_loss(labels, fg, ocfg)
+    if ref is not None:
+        if cfg["single_scale"]:
+            total = ref.DenseContrastiveLossV2(dict(cfg["loss"]))(labels, fg[0])
+        else:
+            total = ref.DenseContrastiveLossV2_ms(dict(cfg["loss"]))(labels, fg)
+    else:
+        total = torch_port.ms_cs_loss(labels, fg, ocfg)[0]
     total.backward()
-    dt = time.perf_counter() - t0
-    return dt, [int(i.shape[0] * i.shape[1]) for i in idx], float(total)
+    return time.perf_counter() - t0, float(total.detach())
 
 
-def cpu_sample(workload, steps, warmup, budget_s=None):
-    """Reference-port timing on the host cores on a bounded sample of the workload."""
+def anchors_per_scale(labels, feats, ocfg):
+    """N per scale of a batch (a function of the labels and the caps only): from the sampling oracle."""
+    from oracle.sampling import sample_indices
+    from oracle.mt19937 import MT19937
+    gen = MT19937.from_torch_state(torch.get_rng_state().numpy().tobytes())
+    out = []
+    for f in feats:
+        o = sample_indices(labels.numpy(), f.shape[-1], ocfg["num_all_classes"], ocfg["min_views"], ocfg["max_views"],
+                           ocfg["max_total"], gen)
+        out.append(int(o["T"]) * int(o["V"]))
+    return out
+
+
+def cpu_sample(workload, steps, warmup, budget_s, images=None):
+    """The reference loss timed on the host cores on a bounded sample of the workload: the first `images` images of
+    the same inputs.  images=None: the largest of (all, half, quarter, ...) whose (warmup + steps) steps fit the
+    time budget, estimated from one calibration step on the smallest sample."""
     from mscs_b200 import synth
     from oracle import torch_port
     from oracle.config import oracle_cfg
@@ -127,30 +160,51 @@ def cpu_sample(workload, steps, warmup, budget_s=None):
     ocfg = oracle_cfg(lc, class_facts(lc["dataset"], lc["experiment"])[0])
     if cfg["single_scale"]:
         ocfg["cross_scale"], ocfg["weights"] = False, [1.0]
-    labels, feats = synth.make_inputs(workload)
-    nimg = min(CPU_SAMPLE_IMAGES, labels.shape[0])
-    labels, feats = labels[:nimg].contiguous(), [f[:nimg].contiguous() for f in feats]
+    ref = _ref_modules()
+    labels_all, feats_all = synth.make_inputs(workload)
     cores = os.cpu_count()
     torch.set_num_threads(cores)
-    times, NS = [], None
-    if budget_s is not None:
-        warmup = min(warmup, 2)      # a CPU step is seconds long and warm after one pass (thread pool, allocator)
+    n_all = labels_all.shape[0]
+
+    def subset(k):
+        return labels_all[:k].contiguous(), [f[:k].contiguous() for f in feats_all]
+
     t_begin = time.perf_counter()
+    calib = ""
+    if images is None:
+        small = min(CPU_SAMPLE_IMAGES, n_all)
+        lab, fts = subset(small)
+        torch.manual_seed(0)
+        cpu_step(ref, cfg, ocfg, lab, fts, torch_port)               # untimed: thread pool, allocator, imports
+        torch.manual_seed(1)
+        t_small, _ = cpu_step(ref, cfg, ocfg, lab, fts, torch_port)
+        images = small
+        k = n_all
+        while k > small:        # measured: the step time grows like images^1.3 (the per-pair dense scatter backward)
+            if (warmup + steps) * t_small * (k / small) ** 1.3 <= budget_s - (time.perf_counter() - t_begin):
+                images = k
+                break
+            k //= 2
+        calib = f"; sample sized by a calibration step ({t_small:.1f} s at {small} images) for a {budget_s:.0f} s budget"
+    labels, feats = subset(images)
+    torch.manual_seed(0)
+    NS = anchors_per_scale(labels, feats, ocfg)
+    times = []
     for i in range(warmup + steps):
         torch.manual_seed(i)
-        dt, NS, _ = cpu_port_step(labels, feats, ocfg, torch_port)
+        dt, _ = cpu_step(ref, cfg, ocfg, labels, feats, torch_port)
         if i >= warmup:
             times.append(dt)
-        # a CPU step takes seconds: stop early (and say so in `sample`) rather than run for longer than budget_s
-        if budget_s is not None and len(times) >= 3 and time.perf_counter() - t_begin + dt > budget_s:
-            break
     pairs = pairs_per_step(NS, ocfg["cross_scale"])
     sec = sum(times) / len(times)
-    return dict(value=pairs / sec, unit=UNIT, cores=cores, kind="port",
-                sample=f"first {nimg} of {cfg['n']} images of the {workload} inputs "
-                       f"(N per scale {NS}, {pairs:.3e} anchor-pairs/step), {len(times)} timed steps"
-                       f"{'' if len(times) == steps else f' (of {steps} requested: time budget {budget_s:.0f} s)'} after "
-                       f"{warmup} warm-up, torch {torch.__version__} CPU fp32, {torch.get_num_threads()} threads",
+    kind = "reference" if ref is not None else "port"
+    what = ("the reference's own losses/DenseContrastiveLossV2_ms.py + DenseContrastiveLossV2.py (unmodified, "
+            "oracle/_ref), fp32 ATen on the host") if ref is not None else "oracle/torch_port.py (fp32 torch port)"
+    return dict(value=pairs / sec, unit=UNIT, cores=cores, kind=kind,
+                sample=f"first {images} of {n_all} images of the {workload} inputs (N per scale {NS}, {pairs:.3e} "
+                       f"anchor-pairs/step; N is bound by max_features_total, so the work per step is that of the "
+                       f"full batch to within a few percent), {len(times)} timed steps after {warmup} warm-up; {what}, "
+                       f"torch {torch.__version__}, {torch.get_num_threads()} threads{calib}",
                 seconds_per_step=sec, pairs_per_step=pairs, steps_timed=len(times))
 
 
@@ -161,14 +215,31 @@ def workload_name(workload):
         "cfg5": "pooled cross-batch anchors, bs 64 in total, ms+cs, max_features_total 65536"}.get(workload, workload)
 
 
+def bench_config(workload, world, layout="nchw"):
+    """`config` of the JSON line: the same dict on both arms (the driver pairs the two lines by it)."""
+    from mscs_b200 import synth
+    cfg = synth.CONFIGS[workload]
+    feat_mb = sum(cfg["n"] * cfg["C"] * (cfg["H"] // s) * (cfg["W"] // s) * 4 for s in cfg["strides"]) / 1e6
+    pooled = workload == "cfg5"
+    return {"workload": workload_name(workload), "layout": layout,
+            "per_gpu_batch": cfg["n"] // world if pooled else cfg["n"],
+            "l2": f"inputs ({feat_mb:.0f} MB of features per step) exceed the 126 MB L2; no explicit flush",
+            "parallelism": (f"pooled anchors: rows sharded x{world}, keys / row statistics / gradient rows exchanged "
+                            f"over NCCL" if pooled else
+                            f"replicas x{world} (loss evaluated per rank on its local batch, as under DDP)")}
+
+
 def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path on the host cores (oracle/_ref = the unmodified files), on a
+    bounded sample of the same workload: exactly --steps timed steps after --warmup, the sample (number of images)
+    sized so that the run ends within ~4 minutes.  Rank 0 only."""
     if rank != 0:
         return
     cb = cpu_sample(args.workload, args.steps, args.warmup, budget_s=240.0)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": cb["steps_timed"], "warmup": min(args.warmup, 2), "ms_per_step": cb["seconds_per_step"] * 1e3,
+            "steps": cb["steps_timed"], "warmup": args.warmup, "ms_per_step": cb["seconds_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload), "sample": cb["sample"]},
+            "config": bench_config(args.workload, args.gpus),
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -375,13 +446,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong" if pooled else "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload),
-                "layout": args.layout, "anchors_per_scale": NS, "anchor_pairs_per_step": pairs, "per_gpu_batch": cfg["n"],
-                "l2": "inputs (535 MB of features per step) exceed the 126 MB L2; no explicit flush",
-                "parallelism": (f"pooled anchors, rows sharded x{world}, keys/statistics/gradient rows exchanged "
-                                f"with NCCL all-reduce" if pooled else
-                                f"replicas x{world} (loss evaluated per rank on its local batch, as under DDP)"),
-                "loss": float(loss.detach())},
+            "config": bench_config(args.workload, world, args.layout),
+            "detail": {"anchors_per_scale": NS, "anchor_pairs_per_step": pairs, "loss": float(loss.detach())},
             "roofline": roofline, "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": n_e2e,
@@ -390,7 +456,8 @@ def main():
                     "serial_ms_per_step": e2e_serial_ms},
             "gpu_launches": _ops.LAUNCHES_PER_STEP(len(feats_h), cfg["single_scale"]) * args.steps}
     if not args.no_cpu_baseline and world == 1:
-        cb = cpu_sample(args.workload, 3, 1)
+        # bounded sample (~20 s of CPU work): the reference's own files on the first 3 images, 1 warm-up + 2 timed steps
+        cb = cpu_sample(args.workload, 2, 1, budget_s=60.0, images=min(CPU_SAMPLE_IMAGES, cfg["n"]))
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
     if dist is not None:

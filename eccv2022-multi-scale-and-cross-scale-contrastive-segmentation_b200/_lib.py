@@ -51,7 +51,7 @@ class Term(C.Structure):
 class SimJob(C.Structure):
     _fields_ = [("num_terms", C.c_int32), ("C_pad", C.c_int32), ("num_classes", C.c_int32),
                 ("terms", Term * MAX_TERMS), ("term_loss", C.c_void_p), ("total_loss", C.c_void_p),
-                ("work", C.c_void_p)]
+                ("work", C.c_void_p), ("total_out", C.c_void_p)]
 
 
 _PTRS = C.POINTER(C.c_void_p)

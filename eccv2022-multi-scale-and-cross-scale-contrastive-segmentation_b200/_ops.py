@@ -420,9 +420,11 @@ def build_job(spec, samples, sets, single_scale):
         so += 3 * n1
         co += 2 * n1
     job.term_loss, job.total_loss = out.data_ptr(), out[len(terms):].data_ptr()
+    total = torch.empty((), dtype=torch.float32, device=dev)
+    job.total_out = total.data_ptr()
     work = torch.empty(_lib.load().mscs_sim_workspace_bytes(C.byref(job)), dtype=torch.uint8, device=dev)
     job.work = work.data_ptr()
-    return SimState(job=job, keep=[stats, coefs, out, work], term_loss=out[:len(terms)], total=out[len(terms)],
+    return SimState(job=job, keep=[stats, coefs, out, work], term_loss=out[:len(terms)], total=total,
                     num_ms=S, cs_logged=cs_logged)
 
 
@@ -764,6 +766,8 @@ def _raise_plan_errors(plan, S, spec):
                                f"{spec.min_views} pixels (the reference raises here too, V2.py:110)")
         if plan[s].error == 2:   # reference: 0-d squeeze then .shape[0] raises (V2.py:119-121)
             raise IndexError(f"scale {s}: a kept class has a single pixel (the reference raises here too)")
+        if plan[s].error == 3:
+            raise ValueError(f"scale {s}: {plan[s].V} views per class exceed the supported 16384")
 
 
 def _fill_job(job, sp, A, bbase, ibase, sbase, cbase, work_ptr):
@@ -893,8 +897,13 @@ def _run_forward_fast(sp, labels, feats32, needs, philox=None):
     e.last_stream = cur
     nt = len(sp.terms)
     out = torch.empty(nt + 2, dtype=torch.float32, device=dev)      # term losses, total, inf/NaN flag
+    # the 0-d loss handed to the caller: a tensor of its own (not a view of `out`) -- the reference's LossWrapper
+    # multiplies it IN PLACE (`loss *= weight`, LossWrapper.py:90), which autograd forbids on a view created inside
+    # a custom Function, and which must not change the logged (unweighted) scalars
+    total_t = torch.empty((), dtype=torch.float32, device=dev)
     for job in (e.job_fwd, e.job_bwd):
         job.term_loss, job.total_loss = out.data_ptr(), out.data_ptr() + 4 * nt
+        job.total_out = total_t.data_ptr()
     # the small, latency-bound sampling kernels run on a high-priority stream (see _hp_stream)
     hp = _hp_stream(dev) if os.environ.get("MSCS_HP", "1") != "0" else None
     st_s = st
@@ -968,7 +977,7 @@ def _run_forward_fast(sp, labels, feats32, needs, philox=None):
     _t = _seg("fwd: rng advance + prefetch", _t)
     state.job, state.samples, state.gradbufs, state.slots = e.job_bwd, samples, gradbufs, e.slots
     state.keep, state.stats, state.fslab = out, e.stats, e.fslab
-    state.term_loss, state.total, state.scalars = out[:nt], out[nt], out
+    state.term_loss, state.total, state.scalars = out[:nt], total_t, out
     state.num_ms, state.cs_logged, state.comm = S, sp.cs_logged, None
     return state
 
@@ -1026,6 +1035,8 @@ def _run_forward_general(sp, labels, feats32, needs, comm, pooled):
         nt = len(sp.terms)
         mbase = misc.data_ptr()
         job.term_loss, job.total_loss = mbase + 4 * sp.out_off, mbase + 4 * (sp.out_off + nt)
+        total_t = torch.empty((), dtype=f32, device=dev)      # own buffer, not a view (see _run_forward_fast)
+        job.total_out = total_t.data_ptr()
         _lib.check(lib.mscs_plan_fetch(plan_dev.data_ptr(), plan, S, st), "mscs_plan_fetch")     # the host sync
         _raise_plan_errors(plan, S, spec)
         total = sum(int(plan[s].draws) for s in range(S))
@@ -1075,7 +1086,7 @@ def _run_forward_general(sp, labels, feats32, needs, comm, pooled):
     state.keep = (ws, islab, fslab, bslab, stats, misc, work, slot_slab)
     state.stats = stats
     state.fslab, state.term_loss = fslab, misc[sp.out_off:sp.out_off + nt]
-    state.total = misc[sp.out_off + nt]
+    state.total = total_t
     state.scalars = misc[sp.out_off:sp.out_off + nt + 2]      # [term losses..., total, inf/NaN flag]: one copy for the logger
     state.num_ms, state.cs_logged, state.comm = S, sp.cs_logged, comm if pooled else None
     return state
@@ -1253,7 +1264,7 @@ class MsCsContrastiveFn(torch.autograd.Function):
         ctx.state, ctx.needs = state, needs
         ctx.shapes = [tuple(f.shape) for f in feats]
         ctx.dtypes = [f.dtype for f in feats]
-        total = state.total.reshape(())
+        total = state.total            # 0-d tensor with storage of its own: tolerates the caller's `loss *= w`
         terms = state.term_loss
         ctx.mark_non_differentiable(terms)
         ctx.set_materialize_grads(False)       # no zero tensor (a fill launch) for the unused gradient of `terms`

@@ -15,6 +15,7 @@ constexpr int kMaxV = 16384;     // views per pair the selection kernel supports
 
 struct ScaleGeo {
   int dl_h, dl_w, hw, tiles;
+  int fplane;                    // fh*fw: the flat index y*dl_w+x addresses the flattened FEATURE plane (V2.py:97,123)
   int tile_base;                 // first global tile id of this scale
   int ident_y, ident_x;
   float sy, sx;                  // float(in)/out, as ATen computes it
@@ -74,6 +75,7 @@ static int make_layout(const mscs_sample_cfg* cfg, SampleLayout* L) {
     g.dl_h = cfg->H / scale; g.dl_w = cfg->W / scale;      // V2.py:205
     MSCS_CHECK_ARG(g.dl_h >= 1 && g.dl_w >= 1, "empty down-sampled label at scale %d", s);
     g.hw = g.dl_h * g.dl_w;
+    g.fplane = cfg->fh[s] * cfg->fw[s];
     // the flat index y*dl_w+x addresses the flattened feature plane (V2.py:97,123): it must fit
     MSCS_CHECK_ARG((long long)g.hw <= (long long)cfg->fh[s] * cfg->fw[s],
                    "scale %d: down-sampled label %dx%d exceeds the feature plane %dx%d (the reference would "
@@ -260,9 +262,11 @@ k_plan(const __grid_constant__ SampleLayout L, PlanCfg pc, char* ws, mscs_scale_
     int run = 0;
     for (int c = 0; c <= A; ++c) { int v = npc[c]; npc[c] = run; run += v; }
     mscs_scale_plan h;
-    h.T = T; h.V = V; h.N = T * V; h.min_count = T > 0 ? min_count : 0; h.log_flag = logf;
+    h.error = (T == 0) ? 1 : (single_px ? 2 : (V > kMaxV ? 3 : 0));
+    // on an error the device-driven consumers (selection, gather, similarity forward: they read N from this record
+    // before the host has seen it) must find NOTHING to do -- the index arrays are not written then
+    h.T = T; h.V = V; h.N = h.error ? 0 : T * V; h.min_count = T > 0 ? min_count : 0; h.log_flag = logf;
     h.dl_h = g.dl_h; h.dl_w = g.dl_w;
-    h.error = (T == 0) ? 1 : (single_px ? 2 : 0);
     h.draw_base = 0; h.draws = carry_draws;
     plan[s] = h;
   }
@@ -450,9 +454,9 @@ k_fy_select(const __grid_constant__ SampleLayout L, const __grid_constant__ Sele
     }
     if (lane == 0) {
       a.idx_ref[s][(size_t)k * V + i] = p;
-      a.pix[s][dst + i] = b * g.hw + p;
+      a.pix[s][dst + i] = b * g.fplane + p;      // image base in FEATURE planes: what gather / scatter decode
       a.cls[s][dst + i] = c;
-      if (a.slot[s]) a.slot[s][b * g.hw + p] = dst + i;
+      if (a.slot[s]) a.slot[s][b * g.fplane + p] = dst + i;
     }
   }
 }
@@ -655,35 +659,43 @@ extern "C" int mscs_sample_select_async(const mscs_sample_cfg* cfg, const mscs_s
 // (work enqueued after begin keeps running) and hand the records out.  The copy runs on a private stream that
 // waits for the producer stream's position at the call: the producer stream itself (selection kernel next) does
 // not queue behind the copy.
-static thread_local mscs_scale_plan* t_plan_pinned = nullptr;
-static thread_local cudaEvent_t t_plan_event = nullptr;
-static thread_local cudaEvent_t t_plan_src_event = nullptr;
-static thread_local cudaStream_t t_plan_stream = nullptr;
+// One set of resources per (host thread, device): a process that drives several GPUs from one thread must not
+// record on a stream that belongs to another device.
+constexpr int kMaxDevices = 64;
+struct PlanFetch { mscs_scale_plan* pinned; cudaEvent_t done, src; cudaStream_t stream; };
+static thread_local PlanFetch t_fetch[kMaxDevices] = {};
+static thread_local int t_fetch_dev = -1;      // device of the outstanding fetch
 extern "C" int mscs_plan_fetch_begin(const mscs_scale_plan* plan_dev, int num_scales, void* stream_) {
   MSCS_CHECK_ARG(plan_dev && num_scales >= 1 && num_scales <= MSCS_MAX_SCALES, "bad arguments");
   cudaStream_t st = (cudaStream_t)stream_;
-  if (!t_plan_pinned) {
-    MSCS_CUDA(cudaHostAlloc((void**)&t_plan_pinned, sizeof(mscs_scale_plan) * MSCS_MAX_SCALES, cudaHostAllocDefault));
-    MSCS_CUDA(cudaEventCreateWithFlags(&t_plan_event, cudaEventDisableTiming));
-    MSCS_CUDA(cudaEventCreateWithFlags(&t_plan_src_event, cudaEventDisableTiming));
+  int dev = 0;
+  MSCS_CUDA(cudaGetDevice(&dev));
+  MSCS_CHECK_ARG(dev >= 0 && dev < kMaxDevices, "device ordinal %d out of range", dev);
+  PlanFetch& f = t_fetch[dev];
+  if (!f.pinned) {
+    MSCS_CUDA(cudaHostAlloc((void**)&f.pinned, sizeof(mscs_scale_plan) * MSCS_MAX_SCALES, cudaHostAllocDefault));
+    MSCS_CUDA(cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
+    MSCS_CUDA(cudaEventCreateWithFlags(&f.src, cudaEventDisableTiming));
     int lo = 0, hi = 0;
     MSCS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    MSCS_CUDA(cudaStreamCreateWithPriority(&t_plan_stream, cudaStreamNonBlocking, hi));
+    MSCS_CUDA(cudaStreamCreateWithPriority(&f.stream, cudaStreamNonBlocking, hi));
   }
-  MSCS_CUDA(cudaEventRecord(t_plan_src_event, st));
-  MSCS_CUDA(cudaStreamWaitEvent(t_plan_stream, t_plan_src_event, 0));
-  MSCS_CUDA(cudaMemcpyAsync(t_plan_pinned, plan_dev, sizeof(mscs_scale_plan) * num_scales, cudaMemcpyDeviceToHost,
-                            t_plan_stream));
-  MSCS_CUDA(cudaEventRecord(t_plan_event, t_plan_stream));
+  MSCS_CUDA(cudaEventRecord(f.src, st));
+  MSCS_CUDA(cudaStreamWaitEvent(f.stream, f.src, 0));
+  MSCS_CUDA(cudaMemcpyAsync(f.pinned, plan_dev, sizeof(mscs_scale_plan) * num_scales, cudaMemcpyDeviceToHost,
+                            f.stream));
+  MSCS_CUDA(cudaEventRecord(f.done, f.stream));
+  t_fetch_dev = dev;
   return 0;
 }
 extern "C" int mscs_plan_fetch_end(mscs_scale_plan* plan_host, int num_scales) {
   MSCS_CHECK_ARG(plan_host && num_scales >= 1 && num_scales <= MSCS_MAX_SCALES, "bad arguments");
-  MSCS_CHECK_ARG(t_plan_pinned != nullptr, "mscs_plan_fetch_end without mscs_plan_fetch_begin on this thread");
-  MSCS_CUDA(cudaEventSynchronize(t_plan_event));
+  MSCS_CHECK_ARG(t_fetch_dev >= 0, "mscs_plan_fetch_end without mscs_plan_fetch_begin on this thread");
+  PlanFetch& f = t_fetch[t_fetch_dev];
+  MSCS_CUDA(cudaEventSynchronize(f.done));
   long long base = 0;
   for (int s = 0; s < num_scales; ++s) {
-    plan_host[s] = t_plan_pinned[s];
+    plan_host[s] = f.pinned[s];
     plan_host[s].draw_base = base; base += plan_host[s].draws;
   }
   return 0;

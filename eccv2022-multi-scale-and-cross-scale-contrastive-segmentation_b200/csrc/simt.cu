@@ -14,7 +14,7 @@ struct FinTerm {
   int N1, self_mask; float weight;
   const int* n1_dev;      // optional device-resident row count
 };
-struct FinArgs { FinTerm t[MSCS_MAX_TERMS]; int num_terms; float* term_loss; float* total_loss; };
+struct FinArgs { FinTerm t[MSCS_MAX_TERMS]; int num_terms; float* term_loss; float* total_loss; float* total_out; };
 
 // loss = mean_i(-pos_i / div_i)  (V2.py:187-188, _ms.py:148-156); coefficients for K4.
 // grid = (row chunks, terms): per-row work is two dependent loads deep, so it is spread over many CTAs;
@@ -66,6 +66,7 @@ __global__ void k_finalize_total(const __grid_constant__ FinArgs a, const double
     total += (double)a.t[ti].weight * (double)l;
   }
   a.total_loss[0] = (float)total;
+  if (a.total_out) *a.total_out = (float)total;
   // device-side replacement of the logger's has_inf_or_nan(loss) host check (utils.py / LoggingManager.py:190):
   // one flag next to the scalars, fetched together with them in a single copy
   a.total_loss[1] = (bad || !isfinite((float)total)) ? 1.f : 0.f;
@@ -76,6 +77,7 @@ __global__ void k_finalize_total(const __grid_constant__ FinArgs a, const double
 int launch_finalize(const mscs_sim_job* job, cudaStream_t st, bool zero_acc) {
   FinArgs a{};
   a.num_terms = job->num_terms; a.term_loss = job->term_loss; a.total_loss = job->total_loss;
+  a.total_out = job->total_out;
   int maxN = 0;
   for (int t = 0; t < job->num_terms; ++t) {
     const mscs_term& m = job->terms[t];

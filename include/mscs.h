@@ -82,7 +82,7 @@ typedef struct {
   int32_t min_count;  /* min pixel count over kept pairs                 (V2.py:110) */
   int32_t log_flag;   /* log_this_step as the reference sets it          (V2.py:75,83) */
   int32_t dl_h, dl_w; /* down-sampled label size (H//s, W//s), s = W//fw (V2.py:46,205) */
-  int32_t error;      /* 0 ok, 1 = no pair kept, 2 = a kept pair has a single pixel  */
+  int32_t error;      /* 0 ok, 1 = no pair kept, 2 = a kept pair has a single pixel, 3 = V > 16384 (N is 0 then) */
   int64_t draw_base;  /* offset of this scale's first draw in the MT19937 stream     */
   int64_t draws;      /* sum over kept pairs of (count-1)                            */
 } mscs_scale_plan;
@@ -131,10 +131,10 @@ int mscs_philox_stream(uint64_t seed, uint64_t call, uint64_t n_words, uint32_t*
  * outputs per scale s (arrays of N_s entries, N_s from the fetched plan):
  *   idx_ref[s]  : flat pixel index y*w+x in REFERENCE order k*V+v            (V2.py:122)
  *   pair_ref[s] : (T,2) int32 (image, class) in reference order              (V2.py:106-107)
- *   pix[s]      : image*dl_h*dl_w + y*w+x, rows sorted by class (kernel order)
+ *   pix[s]      : image*fh*fw + y*dl_w+x (global pixel id in FEATURE planes, V2.py:97,123), rows sorted by class
  *   cls[s]      : class id of each sorted row
  *   seg[s]      : A+1 int32, seg[c] = first sorted row of class c, seg[A] = N
- *   slot[s]     : optional (array or entries may be NULL): int32 n*dl_h*dl_w pixel -> sorted row map,
+ *   slot[s]     : optional (array or entries may be NULL): int32 n*fh*fw pixel -> sorted row map,
  *                 PRE-FILLED with -1 by the caller; the sampled pixels receive their row
  */
 int mscs_sample_select(const mscs_sample_cfg* cfg, const mscs_scale_plan* plan_host, void* workspace,
@@ -218,6 +218,9 @@ typedef struct {
   float* total_loss;  /* out: 2 floats: [0] = sum_t weight_t * term_loss_t; [1] = 1.0 if any term or the
                          total is inf/NaN else 0.0 (device-side has_inf_or_nan, LoggingManager.py:190) */
   void* work;         /* scratch, mscs_sim_workspace_bytes() */
+  float* total_out;   /* optional out (NULL = unused): a second copy of total_loss[0] in a buffer of its own -- the
+                         0-d tensor handed to the caller, which LossWrapper.py:90 multiplies IN PLACE (`loss *= w`):
+                         it must not alias the logged scalars above (nor be a view of them for autograd) */
 } mscs_sim_job;
 
 size_t mscs_sim_workspace_bytes(const mscs_sim_job* job);

@@ -104,13 +104,15 @@ def scatter_dense(dx, pairs, idx, shape):
     return out.reshape(shape)
 
 
-def ms_cs_loss(label, feats, cfg, gen, need_grad=True, chunk=1024, samples=None):
+def ms_cs_loss(label, feats, cfg, gen, need_grad=True, chunk=1024, samples=None, dense=True):
     """The whole path: DenseContrastiveLossV2_ms.forward (or the single-scale class when
     ``cfg['single_scale']``) + gradient w.r.t. every feature map.
 
     cfg keys: num_all_classes, temperature, cs_temperature, min_views, max_views, max_total,
     weights, cross_scale, detach_deepest, w_high_low, w_high_mid.
-    Returns dict(total, ms, cs, samples, grads).
+    Returns dict(total, ms, cs, samples, grads, grad_rows); ``dense=False`` skips the dense scatter (grads = None)
+    and only returns ``grad_rows``: per scale the (T*V, C) gradient rows at the sampled pixels in reference order
+    k*V+v -- the only non-zero part of the dense gradient (sizes where a dense fp64 map is too large to hold).
     """
     A = cfg["num_all_classes"]
     S = len(feats)
@@ -146,8 +148,9 @@ def ms_cs_loss(label, feats, cfg, gen, need_grad=True, chunk=1024, samples=None)
                 dFs[0] += w * da
                 if not cfg.get("detach_deepest"):
                     dFs[ks] += w * dk
-    grads = None
+    grads = rows = None
     if need_grad:
-        grads = [scatter_dense(normalize_backward(dFs[s], Fs[s], norms[s]), samples[s]["pairs"],
-                               samples[s]["idx"], feats[s].shape) for s in range(S)]
-    return dict(total=total, ms=ms, cs=cs, samples=samples, grads=grads)
+        rows = [normalize_backward(dFs[s], Fs[s], norms[s]) for s in range(S)]
+        if dense:
+            grads = [scatter_dense(rows[s], samples[s]["pairs"], samples[s]["idx"], feats[s].shape) for s in range(S)]
+    return dict(total=total, ms=ms, cs=cs, samples=samples, grads=grads, grad_rows=rows)

@@ -175,6 +175,49 @@ def run_case(name, loss_cfg, single_scale, labels, feats, seed, DCV2, DCV2ms, IN
     out[name] = meta
 
 
+def oracle_case(name, INFO, out):
+    """Sizes the reference cannot hold on this machine (cfg-4-large: ~12 N x N fp32 tensors of 4.3 GB; cfg-5: 16.6 GB
+    each): loss + gradient rows from the chunked fp64 oracle, which the cases above pin against the reference.
+    The sampled indices are the reference's (asserted by sampling_only_case on the same inputs)."""
+    from mscs_b200 import synth
+    from oracle.config import oracle_cfg
+    from oracle.mt19937 import MT19937
+    from oracle import loss_fp64
+    cfg = synth.CONFIGS[name]
+    lc = cfg["loss"]
+    A = len(INFO[lc["dataset"]].CLASS_INFO[lc["experiment"]][1])
+    ocfg = oracle_cfg(lc, A)
+    if cfg["single_scale"]:
+        ocfg["cross_scale"], ocfg["weights"] = False, [1.0]
+    labels, feats = synth.make_inputs(name)
+    torch.manual_seed(0)
+    state0 = torch.get_rng_state()
+    gen = MT19937.from_torch_state(state0.numpy().tobytes())
+    t0 = time.time()
+    res = loss_fp64.ms_cs_loss(labels.numpy(), [f.numpy() for f in feats], ocfg, gen, need_grad=True, chunk=2048,
+                               dense=False)
+    dt = time.time() - t0
+    arrays = {"rng_state0": state0.numpy()}
+    meta = dict(loss_cfg=lc, single_scale=cfg["single_scale"], seed=0, source="oracle_fp64 (reference infeasible at "
+                "this size on the build machine)", total=res["total"], ms=res["ms"], cs=res["cs"],
+                TV=[[int(sm["T"]), int(sm["V"])] for sm in res["samples"]],
+                idx_sha=[sha(sm["idx"].astype(np.int64)) for sm in res["samples"]],
+                grad_l2=[float(np.sqrt((r ** 2).sum())) for r in res["grad_rows"]], oracle_cpu_seconds=dt)
+    for s, rows in enumerate(res["grad_rows"]):
+        sm = res["samples"][s]
+        arrays[f"idx{s}"] = sm["idx"].astype(np.int32)
+        arrays[f"pairs{s}"] = sm["pairs"].astype(np.int32)
+        sel = np.random.RandomState(1234 + s).choice(rows.shape[0], size=min(256, rows.shape[0]), replace=False)
+        sel.sort()
+        arrays[f"grad_rows{s}"] = rows[sel].astype(np.float32)
+        arrays[f"grad_row_ids{s}"] = sel.astype(np.int32)
+        arrays[f"grad_row_l2_{s}"] = np.sqrt((rows ** 2).sum(1)).astype(np.float32)
+    print(f"[{name}] fp64 oracle total {res['total']:.9f} ms {res['ms']} cs {res['cs']} T,V {meta['TV']} "
+          f"({dt:.0f} s)", flush=True)
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **arrays)
+    out[name] = meta
+
+
 def sampling_only_case(name, DCV2, INFO, out):
     """(T,V) + index hashes for the big configurations (cheap: no features needed)."""
     from mscs_b200 import synth
@@ -277,6 +320,16 @@ def main():
     for name in ("cfg3", "cfg4", "cfg4_large", "cfg5"):
         if want(name):
             sampling_only_case(name, DCV2, INFO, out)
+    # loss + gradient rows of the remaining BASELINE configurations: the reference itself where it fits this machine
+    # (cfg-3: like cfg-2; cfg-4: one N ~ 10k scale), the fp64 oracle where it does not
+    for name in ("cfg3", "cfg4"):
+        if want(name + "_loss"):
+            labels, feats = synth.make_inputs(name)
+            run_case(name, synth.CONFIGS[name]["loss"], synth.CONFIGS[name]["single_scale"], labels, feats, 0,
+                     DCV2, DCV2ms, INFO, False, out)
+    for name in ("cfg4_large", "cfg5"):
+        if want(name + "_loss"):
+            oracle_case(name, INFO, out)
 
     path = os.path.join(HERE, "golden.json")
     old = json.load(open(path)) if os.path.exists(path) else {}

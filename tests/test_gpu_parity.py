@@ -247,7 +247,6 @@ def test_end_to_end_small(name, golden, dev):
     torch.set_rng_state(torch.from_numpy(z["rng_state0"]))
     loss = mod(labels.to(dev), fg[0] if meta["single_scale"] else fg)
     assert loss.dim() == 0 and loss.requires_grad
-    loss = loss * 1.0
     loss *= 0.1                       # LossWrapper multiplies in place (LossWrapper.py:90)
     loss.backward()
     assert abs(float(loss) / 0.1 - meta["total"]) < 1e-3 * abs(meta["total"])
@@ -264,8 +263,11 @@ def test_end_to_end_small(name, golden, dev):
     assert torch.equal(torch.get_rng_state(), torch.from_numpy(z["rng_state1"]))
 
 
-@pytest.mark.parametrize("name", ["cfg1", "cfg2"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg4", "cfg4_large", "cfg5"])
 def test_end_to_end_bench_configs(name, golden, dev):
+    """Every BASELINE configuration against recorded loss / gradient rows: cfg-1..4 from the REFERENCE run on the build
+    machine, cfg-4-large and cfg-5 (64 images on one GPU) from the chunked fp64 oracle, which the other cases pin
+    (tests/golden/make_golden.py; golden.json says which under `source`)."""
     from mscs_b200 import synth
     meta = golden[name]
     z = load_npz(name)
@@ -742,3 +744,37 @@ def test_philox_sampler_matches_oracle_fed_the_same_stream(layout, dev):
     assert torch.equal(torch.get_rng_state(), rng0), "the counter-based sampler must not touch the torch generator"
     with pytest.raises(ValueError):
         mscs_b200.DenseContrastiveLossV2(dict(dataset="CITYSCAPES", experiment=1, sampler="nope"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_feature_plane_larger_than_downsampled_label(layout, dev):
+    """n > 1 and dl_h*dl_w < fh*fw (the reference only looks at widths, V2.py:46: a 256x512 label with 33x64 feature
+    maps gives a 32x64 down-sampled label): the flat index y*dl_w + x addresses the flattened FEATURE plane of image b
+    (features.view(n, c, -1)[b, :, idx], V2.py:97,123), so the image base is b*fh*fw, not b*dl_h*dl_w."""
+    import mscs_b200
+    from mscs_b200 import synth
+    from oracle import loss_fp64
+    from oracle.config import oracle_cfg
+    from oracle.mt19937 import MT19937
+    cfg = dict(dataset="CITYSCAPES", experiment=1, temperature=0.1, scales=2, weights=[1.0, 0.5],
+               cross_scale_contrast=True, min_views_per_class=5, max_views_per_class=25, max_features_total=2000)
+    labels = synth.synth_labels(3, 256, 512, 19, 6, 16, 0.05, 21)
+    g = torch.Generator().manual_seed(22)
+    feats = [torch.randn(3, 32, 33, 64, generator=g), torch.randn(3, 32, 17, 32, generator=g)]
+    torch.manual_seed(5)
+    gen = MT19937.from_torch_state(torch.get_rng_state().numpy().tobytes())
+    want = loss_fp64.ms_cs_loss(labels.numpy(), [f.numpy() for f in feats], oracle_cfg(cfg, 20), gen)
+    mod = mscs_b200.DenseContrastiveLossV2_ms(cfg)
+    fg = [(_nhwc(f.to(dev)) if layout == "nhwc" else f.to(dev)).requires_grad_(True) for f in feats]
+    loss = mod(labels.to(dev), fg)
+    loss.backward()
+    assert mod.last_state.sp.nhwc == (layout == "nhwc")
+    for s, smp in enumerate(mod.last_samples):
+        assert (smp.dl_h * smp.dl_w) < feats[s].shape[2] * feats[s].shape[3]
+        assert np.array_equal(smp.idx_ref.cpu().numpy(), want["samples"][s]["idx"])
+    assert abs(float(loss) - want["total"]) < 1e-3 * abs(want["total"])
+    for s, f in enumerate(fg):
+        got = f.grad.cpu().numpy().astype(np.float64)
+        assert np.array_equal(np.abs(got).sum(1) != 0, np.abs(want["grads"][s]).sum(1) != 0), "different pixels touched"
+        assert cosine(got, want["grads"][s]) >= 0.999
