@@ -1264,7 +1264,10 @@ class MsCsContrastiveFn(torch.autograd.Function):
         ctx.state, ctx.needs = state, needs
         ctx.shapes = [tuple(f.shape) for f in feats]
         ctx.dtypes = [f.dtype for f in feats]
-        total = state.total            # 0-d tensor with storage of its own: tolerates the caller's `loss *= w`
+        # 0-d tensor with storage of its own: tolerates the caller's `loss *= w`.  The state must NOT keep it: an output
+        # of this Function references its grad_fn, which owns ctx.state -- a cycle through C++ that Python's collector
+        # cannot see (the state, its workspace and the dense-gradient slab would never be returned)
+        total, state.total = state.total, None
         terms = state.term_loss
         ctx.mark_non_differentiable(terms)
         ctx.set_materialize_grads(False)       # no zero tensor (a fill launch) for the unused gradient of `terms`

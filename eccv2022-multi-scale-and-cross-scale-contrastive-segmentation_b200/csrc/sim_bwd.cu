@@ -456,7 +456,8 @@ extern "C" int mscs_sim_backward_sets(const mscs_sim_job* job, const float* grad
             2 * (align_up(sizeof(WorkItem) * fwd_items, 64) + align_up(sizeof(int) * (fwd_items + 1), 64));
   BwdArgs args{};
   args.grad_out = grad_out;
-  if (const char* e = getenv("MSCS_DEBUG_FLAGS")) args.flags = atoi(e);
+  static const int dbg_flags = [] { const char* e = getenv("MSCS_DEBUG_FLAGS"); return e ? atoi(e) : 0; }();
+  args.flags = dbg_flags;      // experiments only, read once per process
   const void* bases[MSCS_MAX_SCALES]; int nmaps = 0;
   auto map_of = [&](const void* base, int rows) -> int {
     for (int i = 0; i < nmaps; ++i) if (bases[i] == base) return i;
@@ -482,7 +483,8 @@ extern "C" int mscs_sim_backward_sets(const mscs_sim_job* job, const float* grad
   }
   b.num_terms = np; b.nitems = nitems; b.rows_per_item = 128; b.mode = 0;
   b.pad = 6;      // a run start costs about as much as 6 units (X load, pipeline fill, dX flush: ~15k cycles)
-  if (const char* e = getenv("MSCS_BWD_PAD")) b.pad = atoi(e);
+  static const int pad_env = [] { const char* e = getenv("MSCS_BWD_PAD"); return e ? atoi(e) : -1; }();
+  if (pad_env >= 0) b.pad = pad_env;
   b.items = (WorkItem*)w; w += align_up(sizeof(WorkItem) * (size_t)nitems, 64);
   b.prefix = (int*)w;
   rc = launch_build_work(b, st);

@@ -43,56 +43,58 @@ struct FwdArgs {
   alignas(64) CUtensorMap maps[MSCS_MAX_SCALES];
   FwdTerm t[MSCS_MAX_TERMS];
   WorkTable work;
-  int debug_flags;     // experiments only (MSCS_DEBUG_FLAGS): 1 = epilogue skips the math
 };
 
 __host__ __device__ constexpr size_t fwd_smem_bytes(int KB) {
   return 1024 /*alignment slack*/ + (size_t)(2 * KB + kFwdStages) * kBlkBytes + 256 /*barriers*/;
 }
 
-// 32 unmasked logits -> 4 partial sums of exp2(v * scale).  Bit (c & 7) of POLY selects the elements
-// whose exponential is evaluated as a polynomial on the FMA pipe instead of MUFU.EX2 (the MUFU unit,
-// 16 results/clk/SM, is the forward pass's second bottleneck next to the tensor pipe).
+// 32 unmasked logits -> partial sums of exp2(v * scale), TWO elements per instruction wherever the pipe allows it
+// (packed fp32x2 multiply / add / polynomial; MUFU.EX2 itself is scalar).  Bit ((c >> 1) & 7) of POLY selects the
+// element PAIRS whose exponential is evaluated as a degree-4 polynomial on the FMA pipe instead of MUFU.EX2: the MUFU
+// unit (16 results/clk/SM) is the epilogue's bottleneck next to the issue slots.  Per pair: MUFU path = FMUL2 + 2 MUFU
+// + FADD2 (2 issue slots per element), polynomial path = 7 FFMA2 + 2 (shift, add) per element + FADD2.
 template <int POLY>
-__device__ __forceinline__ void fast_chunk(const uint32_t (&cur)[32], float scale, float& acc0, float& acc1,
-                                           float& acc2, float& acc3) {
+__device__ __forceinline__ void fast_chunk(const uint32_t (&cur)[16], uint64_t scale2, uint64_t& acc_a, uint64_t& acc_b) {
 #pragma unroll
-  for (int c = 0; c < 32; ++c) {
-    const float v = __uint_as_float(cur[c]);
-    const float e = ((POLY >> (c & 7)) & 1) ? ptx::ex2_poly(v, scale) : ptx::ex2(v * scale);
-    if ((c & 3) == 0) acc0 += e; else if ((c & 3) == 1) acc1 += e; else if ((c & 3) == 2) acc2 += e; else acc3 += e;
+  for (int c = 0; c < 16; c += 2) {
+    const uint64_t v2 = ptx::pack2u(cur[c], cur[c + 1]);
+    uint64_t e2;
+    if ((POLY >> ((c >> 1) & 7)) & 1) {
+      e2 = ptx::ex2_poly2(v2, scale2);
+    } else {
+      float x0, x1;
+      ptx::unpack2(ptx::mul2(v2, scale2), x0, x1);
+      e2 = ptx::pack2(ptx::ex2(x0), ptx::ex2(x1));
+    }
+    if (c & 2) acc_b = ptx::add2(acc_b, e2); else acc_a = ptx::add2(acc_a, e2);
   }
 }
 
-#ifdef MSCS_LEAN
-// `make lean` (libmscs_lean.so, loaded through MSCS_LIB): the sweep-0 epilogue without the MSCS_DEBUG_FLAGS experiment
-// branches and with the four 32-column chunks processed by a loop of two iterations (two chunks each, so the register
-// double buffer keeps compile-time indices) instead of a fully unrolled body -- a code-size experiment: the default
-// epilogue is ~3000 straight-line instructions and 11 % of its warp-stall samples are instruction-cache misses
-// (profiles/r01_stall_summary.md).  Same arithmetic in the same order as the default build.
-// MSCS_LEAN=2 (libmscs_lean2.so) additionally releases the accumulator buffer as soon as its last chunk has been read
-// into registers, i.e. one chunk of math (a quarter of the epilogue) earlier: with two buffers the tile period is
-// (MMA + buffer hold time) / 2.  MSCS_LEAN=3 (libmscs_lean3.so) additionally lets the MMA warp poll its barriers with
-// test_wait instead of suspending in try_wait (the backward kernel does; the forward never got it).
-__device__ __forceinline__ void lean_chunk(const uint32_t (&cur)[32], int c0, int tN2, int wmin, int wmax, int p0,
-                                           unsigned plen, float scale, float& acc0, float& acc1, float& acc2,
-                                           float& acc3) {
-  const bool fast = (c0 + 32 <= wmin || c0 >= wmax) && (c0 + 32 <= tN2);
+// one 16-column chunk of the negative sweep: unmasked when no row of this warp has a positive in it (and it lies
+// inside the key set), otherwise per-element masks.  (16 columns: two chunks in flight cost 32 registers, which
+// leaves the compiler room to overlap the MUFU latencies of neighbouring pairs; with 32-column chunks every pair
+// went through the same register pair.)
+template <int POLY>
+__device__ __forceinline__ void neg_chunk(const uint32_t (&cur)[16], int c0, int tN2, int wmin, int wmax, int p0,
+                                          unsigned plen, float scale, uint64_t scale2, uint64_t& acc_a, uint64_t& acc_b,
+                                          float& acc_m) {
+  const bool fast = (c0 + 16 <= wmin || c0 >= wmax) && (c0 + 16 <= tN2);
   if (fast) {
-    fast_chunk<0x88>(cur, scale, acc0, acc1, acc2, acc3);
+    fast_chunk<POLY>(cur, scale2, acc_a, acc_b);
   } else if (c0 < tN2) {
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
+    for (int c = 0; c < 16; ++c) {
       const int col = c0 + c;
       const float e = ptx::ex2(__uint_as_float(cur[c]) * scale);
       const bool isneg = ((unsigned)(col - p0) >= plen) && (col < tN2);
-      acc0 += isneg ? e : 0.f;
+      acc_m += isneg ? e : 0.f;
     }
   }
 }
-#endif
 
-template <int KB, int MODE>
+// POLY: pair mask of fast_chunk (sweep 0 only): 0x88 = a quarter of the exponentials on the FMA pipe
+template <int KB, int MODE, int POLY>
 __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constant__ FwdArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -168,32 +170,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
       ptx::tc_fence_after();
       for (int rt = sg.c_begin; rt < sg.c_end; ++rt, ++it) {
         const uint32_t buf = it & 1;
-#if defined(MSCS_LEAN) && MSCS_LEAN >= 3      // polling wait for the warp that feeds the tensor pipe, as in sim_bwd.cu: a thread
-        ptx::mbar_spin_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1, 112);     // suspended in try_wait resumes ~250 cycles late
-#else
         ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1, 112);
-#endif
         ptx::tc_fence_after();
         for (int kb = 0; kb < KB; ++kb) {
-#if defined(MSCS_LEAN) && MSCS_LEAN >= 3
-          ptx::mbar_spin_wait(&a_full[stage], phase, 113);
-#else
           ptx::mbar_wait(&a_full[stage], phase, 113);
-#endif
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
-#ifdef MSCS_LEAN
-            {
-#else
-            if (!(args.debug_flags & 2)) {
-#endif
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t ad = ptx::umma_desc_sw128(a_addr + stage * kBlkBytes + k * 32, 16, 1024);
-                const uint64_t bd = ptx::umma_desc_sw128(k_addr + kb * 2 * kBlkBytes + k * 32, 16, 1024);
-                ptx::umma_ss(tmem_base + buf * kFwdKeys, ad, bd, idesc, (kb | k) != 0);
-              }
-            }      // experiment 2: no MMAs, the stage is released at once (pure TMA streaming rate)
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = ptx::umma_desc_sw128(a_addr + stage * kBlkBytes + k * 32, 16, 1024);
+              const uint64_t bd = ptx::umma_desc_sw128(k_addr + kb * 2 * kBlkBytes + k * 32, 16, 1024);
+              ptx::umma_ss(tmem_base + buf * kFwdKeys, ad, bd, idesc, (kb | k) != 0);
+            }
             ptx::umma_commit(&a_empty[stage]);
           }
           __syncwarp();
@@ -231,79 +219,29 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
         const unsigned plen = (unsigned)(p1 - p0);
         const int self_col = t.self_mask ? row : -1;
         const bool touches = !(cb + CPT <= wmin || cb >= wmax);
-        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;   // MODE 1: acc0 = pos (log2 units), acc1 = S
+        float acc0 = 0.f, acc1 = 0.f;   // MODE 0: acc0 = masked-chunk sum; MODE 1: acc0 = pos (log2 units), acc1 = S
+        uint64_t acc_a = 0ull, acc_b = 0ull;      // MODE 0: packed partial sums of the unmasked chunks
         ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1, 121);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kFwdKeys + ch * CPT;
-#ifdef MSCS_LEAN
-        bool released = false;
         if (MODE == 0) {
-          if (cb < tN2) {
-            static_assert(NCH % 2 == 0, "two chunks per iteration");
-            uint32_t va[32], vb[32];
-            ptx::tmem_ld32(taddr, va);
-            ptx::tmem_ld_wait(va);
+          if (cb < tN2) {      // a half that lies entirely in the zero padding of the key block has no work
+            // two chunks per iteration (the register double buffer keeps compile-time indices); rolled: the fully
+            // unrolled body missed the instruction cache at the head of every chunk (11 % of the stall samples)
+            constexpr int NC16 = CPT / 16;
+            static_assert(NC16 % 2 == 0, "two chunks per iteration");
+            const uint64_t scale2 = ptx::pack2(scale, scale);
+            uint32_t va[16], vb[16];
+            ptx::tmem_ld16(taddr, va);
+            ptx::tmem_ld_wait16(va);
 #pragma unroll 1
-            for (int c4 = 0; c4 < NCH; c4 += 2) {
-              ptx::tmem_ld32(taddr + (c4 + 1) * 32, vb);
-              lean_chunk(va, cb + c4 * 32, tN2, wmin, wmax, p0, plen, scale, acc0, acc1, acc2, acc3);
-              ptx::tmem_ld_wait(vb);
-              if (c4 + 2 < NCH) ptx::tmem_ld32(taddr + (c4 + 2) * 32, va);
-#if MSCS_LEAN >= 2
-              else {      // the whole accumulator row is in registers: hand the buffer back before the last chunk's math
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
-                released = true;
-              }
-#endif
-              lean_chunk(vb, cb + (c4 + 1) * 32, tN2, wmin, wmax, p0, plen, scale, acc0, acc1, acc2, acc3);
-              if (c4 + 2 < NCH) ptx::tmem_ld_wait(va);
-            }
-          }
-        } else if (false) {      // the default epilogue below is dead code in this build
-          if (false) {
-#else
-        if (args.debug_flags & 1) {
-          // experiment: no TMEM reads / math
-        } else if (MODE == 0) {
-          if (cb < tN2) {
-#endif      // a quarter that lies entirely in the zero padding of the key block has no work
-            uint32_t va[32], vb[32];
-            ptx::tmem_ld32(taddr, va);
-            ptx::tmem_ld_wait(va);
-#pragma unroll
-            for (int c4 = 0; c4 < NCH; ++c4) {
-              uint32_t (&cur)[32] = (c4 & 1) ? vb : va;
-              uint32_t (&nxt)[32] = (c4 & 1) ? va : vb;
-              if (c4 < NCH - 1) ptx::tmem_ld32(taddr + (c4 + 1) * 32, nxt);
-              const int c0 = cb + c4 * 32;
-              // 32-column chunk without positives of any row of this warp and inside the key set: no masks
-              const bool fast = (c0 + 32 <= wmin || c0 >= wmax) && (c0 + 32 <= tN2);
-              if (args.debug_flags & 8) {               // experiment: TMEM loads only, no math (wrong results)
-              } else if (fast && (args.debug_flags & 4)) {      // experiment: no MUFU (wrong results)
-#pragma unroll
-                for (int c = 0; c < 32; c += 4) {
-                  acc0 += __uint_as_float(cur[c]) * scale;
-                  acc1 += __uint_as_float(cur[c + 1]) * scale;
-                  acc2 += __uint_as_float(cur[c + 2]) * scale;
-                  acc3 += __uint_as_float(cur[c + 3]) * scale;
-                }
-              } else if (fast) {
-                // a quarter of the exponentials on the FMA pipe (degree-4 polynomial, 2.7e-6 relative): measured
-                // best of {0, 1/4, 3/8, 1/2}; MSCS_DEBUG_FLAGS=16 selects the MUFU-only variant for comparison
-                if (args.debug_flags & 16) fast_chunk<0x00>(cur, scale, acc0, acc1, acc2, acc3);
-                else fast_chunk<0x88>(cur, scale, acc0, acc1, acc2, acc3);
-              } else if (c0 < tN2) {
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                  const int col = c0 + c;
-                  const float e = ptx::ex2(__uint_as_float(cur[c]) * scale);
-                  const bool isneg = ((unsigned)(col - p0) >= plen) && (col < tN2);
-                  acc0 += isneg ? e : 0.f;
-                }
-              }
-              if (c4 < NCH - 1) ptx::tmem_ld_wait(nxt);
+            for (int c4 = 0; c4 < NC16; c4 += 2) {
+              ptx::tmem_ld16(taddr + (c4 + 1) * 16, vb);
+              neg_chunk<POLY>(va, cb + c4 * 16, tN2, wmin, wmax, p0, plen, scale, scale2, acc_a, acc_b, acc0);
+              ptx::tmem_ld_wait16(vb);
+              if (c4 + 2 < NC16) ptx::tmem_ld16(taddr + (c4 + 2) * 16, va);
+              neg_chunk<POLY>(vb, cb + (c4 + 1) * 16, tN2, wmin, wmax, p0, plen, scale, scale2, acc_a, acc_b, acc0);
+              if (c4 + 2 < NC16) ptx::tmem_ld_wait16(va);
             }
           }
         } else if (touches) {
@@ -325,19 +263,15 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
             }
           }
         }
-#ifdef MSCS_LEAN
-        if (!released) {
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
-        }
-#else
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
-#endif
         if (valid) {
-          if (MODE == 0) atomicAdd(&t.neg[row], (acc0 + acc1) + (acc2 + acc3));
+          if (MODE == 0) {
+            float a0, a1, b0, b1;
+            ptx::unpack2(acc_a, a0, a1); ptx::unpack2(acc_b, b0, b1);
+            atomicAdd(&t.neg[row], ((a0 + a1) + (b0 + b1)) + acc0);
+          }
           else if (touches) { atomicAdd(&t.pos[row], acc0 * kLn2); atomicAdd(&t.ssum[row], acc1); }
         }
       }
@@ -474,19 +408,45 @@ int sm_count() {
   return n > 0 ? n : 148;
 }
 
-template <int KB>
-static int launch_fwd(const FwdArgs& args, int mode, cudaStream_t st) {
+// environment switches of the tuning experiments, read ONCE per process (no getenv on the per-step path)
+struct FwdTuning { int poly, pad; bool timeline; };
+static const FwdTuning& fwd_tuning() {
+  static const FwdTuning t = [] {
+    FwdTuning v{1, 0, false};
+    if (const char* e = getenv("MSCS_FWD_POLY")) v.poly = atoi(e);      // 0: MUFU only, 1: 1/4, 2: 3/8, 3: 1/2 polynomial
+    if (const char* e = getenv("MSCS_FWD_PAD")) v.pad = atoi(e);
+    v.timeline = getenv("MSCS_FWD_TIMELINE") != nullptr;
+    return v;
+  }();
+  return t;
+}
+
+template <int KB, int MODE, int POLY>
+static int launch_fwd_k(const FwdArgs& args, cudaStream_t st) {
   const size_t smem = fwd_smem_bytes(KB);
-  if (int rc = ensure_trap_buffer()) return rc;
-  if (mode == 0) {
-    MSCS_CUDA(cudaFuncSetAttribute(k_sim_fwd<KB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MSCS_CUDA(launch_k(k_sim_fwd<KB, 0>, sm_count(), kFwdThreads, smem, st, args));
-  } else {
-    MSCS_CUDA(cudaFuncSetAttribute(k_sim_fwd<KB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MSCS_CUDA(launch_k(k_sim_fwd<KB, 1>, sm_count(), kFwdThreads, smem, st, args));
+  static bool attr_done = false;      // per instantiation
+  if (!attr_done) {
+    MSCS_CUDA(cudaFuncSetAttribute(k_sim_fwd<KB, MODE, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
   }
+  MSCS_CUDA(launch_k(k_sim_fwd<KB, MODE, POLY>, sm_count(), kFwdThreads, smem, st, args));
   MSCS_LAUNCH_CHECK();
   return 0;
+}
+
+template <int KB>
+static int launch_fwd(const FwdArgs& args, int mode, cudaStream_t st) {
+  if (int rc = ensure_trap_buffer()) return rc;
+  if (mode == 1) return launch_fwd_k<KB, 1, 0>(args, st);
+  if (KB == 4) {      // the polynomial share is a tuning switch for the 256-channel kernels only
+    switch (fwd_tuning().poly) {
+      case 0: return launch_fwd_k<KB, 0, 0x00>(args, st);
+      case 2: return launch_fwd_k<KB, 0, 0x92>(args, st);
+      case 3: return launch_fwd_k<KB, 0, 0xAA>(args, st);
+      default: break;
+    }
+  }
+  return launch_fwd_k<KB, 0, 0x88>(args, st);
 }
 
 }  // namespace mscs
@@ -527,8 +487,7 @@ extern "C" int mscs_sim_forward_sweeps(const mscs_sim_job* job, void* stream_) {
   MSCS_CHECK_ARG(job->work, "work buffer is null");
   cudaStream_t st = (cudaStream_t)stream_;
   FwdArgs args{};
-  if (const char* e = getenv("MSCS_DEBUG_FLAGS")) args.debug_flags = atoi(e);
-  g_tl_on = getenv("MSCS_FWD_TIMELINE") != nullptr;
+  g_tl_on = fwd_tuning().timeline;
   g_tl_n = 0;
   tl_mark(st);
   // one tensor map per distinct operand matrix
@@ -567,8 +526,7 @@ extern "C" int mscs_sim_forward_sweeps(const mscs_sim_job* job, void* stream_) {
   MSCS_LAUNCH_CHECK();
   tl_mark(st);
   b.num_terms = job->num_terms; b.nitems = nitems; b.rows_per_item = kFwdKeys;
-  b.pad = 0;      // start-up charge of a key block (128 KB load + pipeline fill), in anchor tiles
-  if (const char* e = getenv("MSCS_FWD_PAD")) b.pad = atoi(e);
+  b.pad = fwd_tuning().pad;      // start-up charge of a key block (128 KB load + pipeline fill), in anchor tiles
   // both work tables (sweep 0: every tile; sweep 1: class-diagonal tiles) depend only on the class arrays: one launch
   b.mode = 0;
   b.items = (WorkItem*)w;  w += align_up(sizeof(WorkItem) * (size_t)nitems, 64);

@@ -158,8 +158,8 @@ def test_live_reference_on_gpu_same_wrapper_same_inputs(name, ref, dev):
     assert abs(float(total_o) - float(total_r)) < 1e-3 * abs(float(total_r))
     for s, (go, fr) in enumerate(zip(grads_o, fg_r)):
         gr = fr.grad
-        assert torch.equal(go != 0, gr != 0) or float(go[(go != 0) != (gr != 0)].abs().max()) < 1e-12, \
-            "different pixels carry a gradient"
+        # the same PIXELS carry a gradient (single channels of a sampled pixel may be exactly 0 on one side only)
+        assert torch.equal((go != 0).any(dim=1), (gr != 0).any(dim=1)), "different pixels carry a gradient"
         a, b = go.double().flatten(), gr.double().flatten()
         cs = float((a @ b) / (a.norm() * b.norm()))
         err, mx = float((a - b).abs().max()), float(b.abs().max())

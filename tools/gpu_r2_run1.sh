@@ -2,7 +2,7 @@
 # Round 2, first GPU call: parity suite (80 random cases, LossWrapper + live-reference tests), default bench line,
 # A/B of the MSCS_LEAN forward-epilogue variants.
 mkdir -p gpurun_out
-MSCS_GPU_RANDOM=80 timeout -s KILL 900 python -m pytest tests -m gpu -q --timeout 600 -k "not cfg5" -x > gpurun_out/pytest_gpu_r2a.log 2>&1
+MSCS_GPU_RANDOM=80 timeout -s KILL 900 python -m pytest tests -m gpu -q --timeout 600 -k "not cfg5" > gpurun_out/pytest_gpu_r2a.log 2>&1
 echo "pytest exit $?"; tail -15 gpurun_out/pytest_gpu_r2a.log
 timeout -s KILL 300 python bench.py > gpurun_out/bench_r2a.json 2> gpurun_out/bench_r2a.err
 echo "bench exit $?"; tail -c 3000 gpurun_out/bench_r2a.json; tail -3 gpurun_out/bench_r2a.err
