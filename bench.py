@@ -246,6 +246,84 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def measure_pooled(dev, rank, world, dist, steps=10, warmup=3):
+    """The sharded configuration north_star names (cfg5: 64 images pooled over the ranks, anchor rows sharded, keys /
+    row statistics / gradient rows exchanged): ms per step at this world size and -- measured in the same run by rank 0
+    alone on the full batch -- the single-GPU time it is compared with (strong scaling).  Labels are the cfg5 labels
+    (same (T, V) as the parity fixtures); features are drawn on the device per (scale, image), identical for every
+    world size."""
+    import mscs_b200
+    from mscs_b200 import synth
+    cfg = synth.CONFIGS["cfg5"]
+    labels_all = synth.make_labels(cfg)
+    n = cfg["n"]
+
+    def inputs(i0, i1):
+        fts = []
+        for si, st in enumerate(cfg["strides"]):
+            f = torch.empty((i1 - i0, cfg["C"], cfg["H"] // st, cfg["W"] // st), device=dev)
+            for b in range(i0, i1):
+                g = torch.Generator(device=dev)
+                g.manual_seed(100003 * (si + 1) + b)
+                f[b - i0].normal_(generator=g)
+            fts.append(f.requires_grad_(True))
+        return labels_all[i0:i1].contiguous().to(dev), fts
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(comm, lab, fts, sync):
+        mod = mscs_b200.DenseContrastiveLossV2_ms(dict(cfg["loss"]), comm=comm) if comm is not None else \
+            mscs_b200.DenseContrastiveLossV2_ms(dict(cfg["loss"]))
+        torch.manual_seed(0)                 # every rank: same CPU generator state (the pooled plan consumes it)
+
+        def one():
+            for f in fts:
+                f.grad = None
+            loss = mod(lab, fts)
+            loss.backward()
+            return loss
+        for _ in range(warmup):
+            one()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync()
+        e0.record()
+        for _ in range(steps):
+            loss = one()
+        e1.record()
+        sync()
+        NS = [s_.N for s_ in mod.last_samples]
+        return e0.elapsed_time(e1) / steps, float(loss.detach()), NS, mod
+
+    out = {"workload": workload_name("cfg5"), "n_gpus": world, "steps": steps, "warmup": warmup, "scaling": "strong"}
+    single_ms = None
+    if rank == 0:        # the single-GPU reference time of the same batch (the other ranks wait at the barrier below)
+        lab, fts = inputs(0, n)
+        single_ms, loss1, NS, _m = run(None, lab, fts, torch.cuda.synchronize)
+        out.update(single_gpu_ms_per_step=single_ms, single_gpu_loss=loss1, anchors_per_scale=NS)
+        del lab, fts, _m
+        torch.cuda.empty_cache()
+    if world > 1:
+        barrier()
+        nl = n // world
+        lab, fts = inputs(rank * nl, (rank + 1) * nl)
+        ms, loss, NS, mod = run(mscs_b200.TorchDistComm(), lab, fts, barrier)
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+        if rank == 0:
+            pairs = pairs_per_step(NS, True)
+            out.update(ms_per_step=ms, value=pairs / (ms * 1e-3), unit=UNIT, loss=loss,
+                       speedup_vs_single_gpu=single_ms / ms, efficiency=single_ms / ms / world,
+                       exchange=mod.last_state.exchange_info if hasattr(mod.last_state, "exchange_info") else None)
+    elif rank == 0:
+        pairs = pairs_per_step(out["anchors_per_scale"], True)
+        out.update(ms_per_step=single_ms, value=pairs / (single_ms * 1e-3), unit=UNIT)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -256,6 +334,7 @@ def main():
     ap.add_argument("--impl", default="mscs", choices=["mscs", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pooled", action="store_true", help="skip the cfg5 (pooled, sharded) record")
     ap.add_argument("--layout", default="nchw", choices=["nchw", "nhwc"],
                     help="memory order of the feature maps: nchw = what the reference's projector emits (headline); "
                          "nhwc = torch.channels_last (row gather / scatter)")
@@ -407,27 +486,50 @@ def main():
     fwd_flops = 2.0 * Cdim * per_gpu
     t_bwd = stage_ms.get("sim_bwd", float("nan")) * 1e-3
     achieved = bwd_flops / t_bwd / 1e12
-    # DRAM traffic of one k_sim_bwd launch at cfg-2 from the ncu --set full capture summarised in
-    # profiles/r01_ncu_kernels.md (dram__bytes_read.sum + dram__bytes_write.sum); other workloads: not captured
-    traffic = 51.0e6 + 0.02e6 if (args.workload == "cfg2" and not pooled) else None
-    roofline = {"bound": "tensor", "kernel": "k_sim_bwd", "achieved": achieved, "peak": pk["tflops_sustained"],
-                "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"], "traffic": traffic,
-                "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
-                "peak_source": pk["source"] + ": sustained cuBLAS bf16 (the kernel is timed inside the sustained "
-                               "step loop; burst figure %.1f)" % pk["tflops"],
-                "frac_of_burst_peak": achieved / pk["tflops"],
+    # DRAM traffic of one k_sim_bwd launch at cfg-2: a CONSTANT copied from the ncu --set full capture summarised in
+    # profiles/ (dram__bytes_read.sum + dram__bytes_write.sum), not measured by this run; other workloads: not captured
+    traffic = 51.0e6 + 0.06e6 if (args.workload == "cfg2" and not pooled) else None
+    # Denominator: the BURST cuBLAS bf16 figure of MEASURED_PEAKS.json.  The timed region of the default run is a
+    # fraction of a second at full SM clock, so the sustained (power-limited, 4 s) figure would flatter the kernel.
+    roofline = {"bound": "tensor", "kernel": "k_sim_bwd", "achieved": achieved, "peak": pk["tflops"],
+                "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": traffic,
+                "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum; constant from the "
+                                "committed capture in profiles/, not re-measured here)",
+                "peak_source": pk["source"] + ": burst cuBLAS bf16 (sustained figure %.1f)" % pk["tflops_sustained"],
+                "frac_of_sustained_peak": achieved / pk["tflops_sustained"],
                 "algorithmic_flops_per_launch": bwd_flops,
                 "launch_ms": t_bwd * 1e3,
-                "fwd": {"kernel": "k_sim_fwd (2 sweeps)", "achieved": fwd_flops / (stage_ms["sim_fwd"] * 1e-3) / 1e12,
+                "fwd": {"kernel": "k_sim_fwd (2 sweeps + row ranges, work tables, finalise)",
+                        "achieved": fwd_flops / (stage_ms["sim_fwd"] * 1e-3) / 1e12,
+                        "frac": fwd_flops / (stage_ms["sim_fwd"] * 1e-3) / 1e12 / pk["tflops"],
                         "launch_ms": stage_ms["sim_fwd"]},
+                "similarity_kernels": {"achieved": (fwd_flops + bwd_flops) / ((stage_ms["sim_fwd"] + stage_ms["sim_bwd"])
+                                                                               * 1e-3) / 1e12,
+                                       "frac": (fwd_flops + bwd_flops) / ((stage_ms["sim_fwd"] + stage_ms["sim_bwd"])
+                                                                          * 1e-3) / 1e12 / pk["tflops"]},
                 "stage_ms": stage_ms}
     dense_bytes = sum(f.numel() * 4 for f in feats_h)
     row_bytes = sum(NS) * Cdim * 4
+    if "zero_fill" in stage_ms:
+        # the zero fill of the dense gradients + gradient rows: a library memset on a side stream, timed on that stream
+        fill_bytes = dense_bytes + 4 * mod.last_state.sp.dF_n
+        roofline["zero_fill_hbm"] = {"kernel": "cudaMemsetAsync (side stream, overlaps the sampling / gather stages)",
+                                     "bytes": fill_bytes, "launch_ms": stage_ms["zero_fill"],
+                                     "achieved_gbs": fill_bytes / (stage_ms["zero_fill"] * 1e-3) / 1e9,
+                                     "peak_gbs": pk["hbm"]}
     if args.layout == "nchw":
-        # the stage waits for the zero fill of the dense gradients (side stream) and rewrites the sampled sectors
-        roofline["scatter_hbm"] = {"kernel": "memset + k_scatter_sectors", "bytes": dense_bytes,
-                                   "achieved_gbs": dense_bytes / (stage_ms["scatter"] * 1e-3) / 1e9,
+        # the scatter kernel's OWN algorithmic bytes: gradient rows + unit rows read, slot maps read, and one 32-byte
+        # sector written per sampled pixel and channel (the dense zero fill is the separate entry above)
+        sc_bytes = 2 * row_bytes + 4 * sum(f.shape[0] * f.shape[2] * f.shape[3] for f in feats_h) + sum(NS) * Cdim * 32
+        roofline["scatter_hbm"] = {"kernel": "k_scatter_sectors_batch", "bytes": sc_bytes,
+                                   "achieved_gbs": sc_bytes / (stage_ms["scatter"] * 1e-3) / 1e9,
                                    "peak_gbs": pk["hbm"], "launch_ms": stage_ms["scatter"]}
+        # gather: useful bytes (N*C*4 read + rows written) and the sector traffic NCHW forces (one 32 B sector per value)
+        roofline["gather_hbm"] = {"kernel": "k_gather_sectors_batch", "bytes": row_bytes + sum(NS) * (Cdim * 6 + 4),
+                                  "sector_bytes": sum(NS) * Cdim * 32 + sum(NS) * (Cdim * 6 + 4),
+                                  "achieved_gbs": (sum(NS) * Cdim * 32 + sum(NS) * (Cdim * 6 + 4))
+                                  / (stage_ms["gather"] * 1e-3) / 1e9,
+                                  "peak_gbs": pk["hbm"], "launch_ms": stage_ms["gather"]}
     else:
         # row kernels: the stage times hold the row traffic only (the zero fill of the dense gradients runs on the side
         # stream under the other stages); latency-bound at this size, reported for completeness
@@ -438,6 +540,12 @@ def main():
                                    "achieved_gbs": 3 * row_bytes / (stage_ms["scatter"] * 1e-3) / 1e9,
                                    "peak_gbs": pk["hbm"], "launch_ms": stage_ms["scatter"]}
 
+    # ---- the sharded (pooled cross-batch) configuration next to the replica numbers ---------------
+    pooled_rec = None
+    if not pooled and not args.no_pooled:
+        del feats, labels
+        torch.cuda.empty_cache()
+        pooled_rec = measure_pooled(dev, rank, world, dist)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -452,9 +560,13 @@ def main():
             "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": n_e2e,
                     "pipeline": "the copy of step i+1's inputs (copy stream) overlaps step i's kernels; every step "
-                                "copies its own inputs and reads its loss back",
+                                "copies its own inputs and reads its loss back; the dense feature gradients (the "
+                                "backward's result, 535 MB at cfg2) STAY on the device, where the projector's backward "
+                                "consumes them in training",
                     "serial_ms_per_step": e2e_serial_ms},
             "gpu_launches": _ops.LAUNCHES_PER_STEP(len(feats_h), cfg["single_scale"]) * args.steps}
+    if pooled_rec is not None:
+        line["pooled"] = pooled_rec
     if not args.no_cpu_baseline and world == 1:
         # bounded sample (~20 s of CPU work): the reference's own files on the first 3 images, 1 warm-up + 2 timed steps
         cb = cpu_sample(args.workload, 2, 1, budget_s=60.0, images=min(CPU_SAMPLE_IMAGES, cfg["n"]))

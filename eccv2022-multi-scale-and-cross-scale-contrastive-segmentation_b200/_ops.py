@@ -500,8 +500,15 @@ class _GradBuffers:
         side.wait_stream(_cur_stream())
         if self.slab.numel():
             ptrs = _lib.ptr_array([self.slab.data_ptr()])
+            if TIMING is not None:      # bench.py: the fill's own duration, on the stream it runs on
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record(side)
             _lib.check(_lib.load().mscs_fill_bytes(ptrs, (C.c_int32 * 1)(0), (C.c_size_t * 1)(4 * self.slab.numel()), 1,
                                                    C.c_void_p(side.cuda_stream)), "mscs_fill_bytes")
+            if TIMING is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record(side)
+                TIMING.setdefault("zero_fill", []).append((e0, e1))
             self.slab.record_stream(side)
         self.ready = torch.cuda.Event()
         self.ready.record(side)

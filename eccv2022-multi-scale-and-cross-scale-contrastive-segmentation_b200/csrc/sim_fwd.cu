@@ -13,21 +13,30 @@
 // shared-memory operand traffic per FLOP is 25% lower than with 128x128 MMAs (which measured at
 // ~45% of the tensor peak here, shared-memory bound) and the accumulate dependency is hidden.
 // Accumulators (128 lanes x 256 columns) are double-buffered in TMEM.
-// Warp roles: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..11 / 12..19 epilogue groups 0 / 1
-// (even / odd tiles): thread = (anchor row of the tile, 128-key half); partial row sums go out with
-// one atomicAdd per row, half and tile.
+// Warp roles: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4..19 epilogue: thread = (anchor row of the tile,
+// 64-key quarter).  In the negative sweep a thread first copies ITS WHOLE 64-logit share of the accumulator into
+// registers and hands the buffer back to the MMA warp at once, then evaluates the exponentials from registers while
+// the MMAs of the next two tiles run: the accumulator is held for ~800 cycles instead of for the ~3400 cycles of the
+// math (event trace of the two-group ping-pong version, profiles/r02_fwd_trace.md: tile period 2900 cycles against
+// 2048 of MMA time, the MMA warp waiting for a buffer a third of the time).  Partial row sums go out with one
+// atomicAdd per row, quarter and tile.
 #include "sim_tc.cuh"
 #include <stdlib.h>
+#ifdef MSCS_TRACE      // the forward trace records sweep 0 only (sweep 1 would overwrite it)
+#undef MSCS_TRACE_EV
+#define MSCS_TRACE_EV(slot, k, tile)                                                                 \
+  do {                                                                                               \
+    if (MODE == 0 && blockIdx.x == 5 && (threadIdx.x & 31) == 0 && (tile) < 256u)                    \
+      mscs::ptx::g_trace[(slot) * 2048 + (tile) * 8 + (k)] = (unsigned long long)clock64();          \
+  } while (0)
+#endif
 
 namespace mscs {
 
 constexpr int kFwdKeys = 256;       // resident key block = N of the MMA
-// Two epilogue groups of 8 warps: group g owns accumulator buffer g, i.e. every second tile, so the TMEM-load
-// latency and barrier hand-over of one tile overlap the exponentials of the other (with one group the
-// MUFU unit idled half of the time although it is the busiest unit of the pass).
 constexpr int kFwdEpiWarps = 16;
 constexpr int kFwdThreads = 128 + 32 * kFwdEpiWarps;
-constexpr int kFwdColsPerThread = kFwdKeys / 2;      // thread = (anchor row, 128-key half) of its group's tiles
+constexpr int kFwdColsPerThread = kFwdKeys / 4;      // thread = (anchor row, 64-key quarter) of every tile
 constexpr int kFwdStages = 5;
 
 struct FwdTerm {
@@ -115,7 +124,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < kFwdStages; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
     ptx::mbar_init(k_full, 1); ptx::mbar_init(k_empty, 1);
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], kFwdEpiWarps / 2); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], kFwdEpiWarps); }
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc(tmem_slot, 512);
@@ -170,8 +179,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
       ptx::tc_fence_after();
       for (int rt = sg.c_begin; rt < sg.c_end; ++rt, ++it) {
         const uint32_t buf = it & 1;
+        MSCS_TRACE_EV(0, 0, it);
         ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1, 112);
         ptx::tc_fence_after();
+        MSCS_TRACE_EV(0, 1, it);
         for (int kb = 0; kb < KB; ++kb) {
           ptx::mbar_wait(&a_full[stage], phase, 113);
           ptx::tc_fence_after();
@@ -189,6 +200,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
         }
         if (ptx::elect_one()) ptx::umma_commit(&acc_full[buf]);
         __syncwarp();
+        MSCS_TRACE_EV(0, 2, it);
       }
       if (ptx::elect_one()) ptx::umma_commit(k_empty);
       __syncwarp();
@@ -196,7 +208,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
   } else if (warp >= 4) {
     // ================= epilogue: thread = (anchor row of the tile, 128-key half) =================
     constexpr int CPT = kFwdColsPerThread, NCH = CPT / 32;
-    const int grp = (warp - 4) >> 3, ch = ((warp - 4) >> 2) & 1, quad = warp & 3;
+    const int ch = (warp - 4) >> 2, quad = warp & 3;
     Walker wk(args.work);
     Segment sg;
     uint32_t it = 0;
@@ -209,7 +221,6 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
       // loads are issued before the accumulator wait (the other group keeps the SM busy meanwhile)
       for (int rt = sg.c_begin; rt < sg.c_end; ++rt, ++it) {
         const uint32_t buf = it & 1;
-        if (buf != (uint32_t)grp) continue;
         const int row = rt * 128 + quad * 32 + lane;
         const bool valid = row < tN1;
         const int2 n_gr = t.grp_range[rt * 4 + quad];
@@ -221,51 +232,71 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
         const bool touches = !(cb + CPT <= wmin || cb >= wmax);
         float acc0 = 0.f, acc1 = 0.f;   // MODE 0: acc0 = masked-chunk sum; MODE 1: acc0 = pos (log2 units), acc1 = S
         uint64_t acc_a = 0ull, acc_b = 0ull;      // MODE 0: packed partial sums of the unmasked chunks
+#ifdef MSCS_TRACE
+        const int tslot = warp == 4 ? 1 : (warp == 11 ? 2 : (warp == 19 ? 3 : -1));
+        if (tslot > 0) MSCS_TRACE_EV(tslot, 0, it);
+#endif
         ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1, 121);
         ptx::tc_fence_after();
+#ifdef MSCS_TRACE
+        if (tslot > 0) MSCS_TRACE_EV(tslot, 1, it);
+#endif
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + buf * kFwdKeys + ch * CPT;
         if (MODE == 0) {
-          if (cb < tN2) {      // a half that lies entirely in the zero padding of the key block has no work
-            // two chunks per iteration (the register double buffer keeps compile-time indices); rolled: the fully
-            // unrolled body missed the instruction cache at the head of every chunk (11 % of the stall samples)
-            constexpr int NC16 = CPT / 16;
-            static_assert(NC16 % 2 == 0, "two chunks per iteration");
+          // the thread's whole share (64 logits) -> registers, then the buffer goes back to the MMA warp
+          static_assert(CPT == 64, "two 32-column loads per thread");
+          uint32_t va[32], vb[32];
+          const bool work = cb < tN2;      // a quarter that lies entirely in the zero padding of the key block has none
+          if (work) {
+            ptx::tmem_ld32(taddr, va);
+            ptx::tmem_ld32(taddr + 32, vb);
+            ptx::tmem_ld_wait(va);
+            ptx::tmem_ld_wait(vb);
+          }
+#ifdef MSCS_TRACE
+          if (tslot > 0) MSCS_TRACE_EV(tslot, 3, it);
+#endif
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+          if (work) {
             const uint64_t scale2 = ptx::pack2(scale, scale);
-            uint32_t va[16], vb[16];
-            ptx::tmem_ld16(taddr, va);
-            ptx::tmem_ld_wait16(va);
-#pragma unroll 1
-            for (int c4 = 0; c4 < NC16; c4 += 2) {
-              ptx::tmem_ld16(taddr + (c4 + 1) * 16, vb);
-              neg_chunk<POLY>(va, cb + c4 * 16, tN2, wmin, wmax, p0, plen, scale, scale2, acc_a, acc_b, acc0);
-              ptx::tmem_ld_wait16(vb);
-              if (c4 + 2 < NC16) ptx::tmem_ld16(taddr + (c4 + 2) * 16, va);
-              neg_chunk<POLY>(vb, cb + (c4 + 1) * 16, tN2, wmin, wmax, p0, plen, scale, scale2, acc_a, acc_b, acc0);
-              if (c4 + 2 < NC16) ptx::tmem_ld_wait16(va);
-            }
+            neg_chunk<POLY>(*reinterpret_cast<const uint32_t(*)[16]>(&va[0]), cb, tN2, wmin, wmax, p0, plen, scale,
+                            scale2, acc_a, acc_b, acc0);
+            neg_chunk<POLY>(*reinterpret_cast<const uint32_t(*)[16]>(&va[16]), cb + 16, tN2, wmin, wmax, p0, plen, scale,
+                            scale2, acc_a, acc_b, acc0);
+            neg_chunk<POLY>(*reinterpret_cast<const uint32_t(*)[16]>(&vb[0]), cb + 32, tN2, wmin, wmax, p0, plen, scale,
+                            scale2, acc_a, acc_b, acc0);
+            neg_chunk<POLY>(*reinterpret_cast<const uint32_t(*)[16]>(&vb[16]), cb + 48, tN2, wmin, wmax, p0, plen, scale,
+                            scale2, acc_a, acc_b, acc0);
           }
-        } else if (touches) {
+        } else {
+          if (touches) {
 #pragma unroll 1
-          for (int c4 = 0; c4 < NCH; ++c4) {
-            const int c0 = cb + c4 * 32;
-            if (c0 + 32 <= wmin || c0 >= wmax) continue;      // warp-uniform
-            uint32_t v[32];
-            ptx::tmem_ld32(taddr + c4 * 32, v);
-            ptx::tmem_ld_wait(v);
+            for (int c4 = 0; c4 < NCH; ++c4) {
+              const int c0 = cb + c4 * 32;
+              if (c0 + 32 <= wmin || c0 >= wmax) continue;      // warp-uniform
+              uint32_t v[32];
+              ptx::tmem_ld32(taddr + c4 * 32, v);
+              ptx::tmem_ld_wait(v);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const int col = c0 + c;
-              const bool ispos = ((unsigned)(col - p0) < plen) && (col != self_col);
-              const float x = __uint_as_float(v[c]) * scale;      // logit in log2 units
-              const float den = ptx::ex2(x) + negi;
-              acc0 += ispos ? (x - ptx::lg2(den)) : 0.f;
-              acc1 += ispos ? ptx::rcp(den) : 0.f;
+              for (int c = 0; c < 32; ++c) {
+                const int col = c0 + c;
+                const bool ispos = ((unsigned)(col - p0) < plen) && (col != self_col);
+                const float x = __uint_as_float(v[c]) * scale;      // logit in log2 units
+                const float den = ptx::ex2(x) + negi;
+                acc0 += ispos ? (x - ptx::lg2(den)) : 0.f;
+                acc1 += ispos ? ptx::rcp(den) : 0.f;
+              }
             }
           }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
         }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+#ifdef MSCS_TRACE
+        if (tslot > 0) MSCS_TRACE_EV(tslot, 2, it);
+#endif
         if (valid) {
           if (MODE == 0) {
             float a0, a1, b0, b1;
@@ -563,6 +594,23 @@ extern "C" int mscs_sim_forward(const mscs_sim_job* job, void* stream_) {
   rc = launch_finalize(job, (cudaStream_t)stream_);
   tl_mark((cudaStream_t)stream_);
   return rc;
+}
+
+// debug (trace build only): copy out and reset the event trace of sweep 0 of the forward kernel (CTA 5):
+// [slot][tile][event] clock64 values; slot 0 = MMA warp (0 before / 1 after the acc_empty wait, 2 tile issued),
+// slots 1..3 = epilogue warps 4, 11 (group 0) and 12 (group 1): 0 before / 1 after the acc_full wait, 2 math done
+extern "C" int mscs_debug_trace_fwd(unsigned long long* out, int max_events) {
+#ifdef MSCS_TRACE
+  MSCS_CUDA(cudaDeviceSynchronize());
+  const int n = max_events < 8192 ? max_events : 8192;
+  MSCS_CUDA(cudaMemcpyFromSymbol(out, ptx::g_trace, sizeof(unsigned long long) * n));
+  static unsigned long long zeros[8192];
+  MSCS_CUDA(cudaMemcpyToSymbol(ptx::g_trace, zeros, sizeof(zeros)));
+  return n;
+#else
+  (void)out; (void)max_events;
+  return 0;
+#endif
 }
 
 // debug: read and reset the barrier wait profile of this translation unit (ns and count per tag % 32)

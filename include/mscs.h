@@ -43,6 +43,8 @@ int mscs_debug_wait_profile_bwd(unsigned long long* ns_out, unsigned long long* 
 /* debug (library built with -DMSCS_TRACE only, otherwise returns 0): copy out and reset the event trace of
    the backward tensor kernel -- clock64 values of one CTA, indexed [4 slots][256 tiles][8 events]. */
 int mscs_debug_trace_bwd(unsigned long long* out, int max_events);
+/* the same for sweep 0 of the forward tensor kernel (slot 0 = MMA warp, slots 1..3 = three epilogue warps) */
+int mscs_debug_trace_fwd(unsigned long long* out, int max_events);
 /* debug (MSCS_FWD_TIMELINE set in the environment): milliseconds between the launches of the last forward call
    (row ranges, work table 0, sweep 0, work table 1, sweep 1); returns the number of intervals */
 int mscs_debug_fwd_timeline(float* ms_out, int max_n);
