@@ -4,6 +4,7 @@ import ctypes as C
 import os
 
 MAX_SCALES, MAX_TERMS = 8, 16
+MAX_RANKS, IPC_HANDLE_BYTES = 8, 64      # MSCS_MAX_RANKS, MSCS_IPC_HANDLE_BYTES
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MSCS_LIB") or os.path.join(_HERE, "libmscs.so")   # MSCS_LIB: profiling build
@@ -109,6 +110,17 @@ _SIGNATURES = {
                                        C.c_int, C.c_void_p, C.c_void_p]),
     "mscs_scatter_grad": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "mscs_xchg_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
+    "mscs_xchg_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "mscs_xchg_close": (C.c_int, [C.c_void_p]),
+    "mscs_xchg_free": (C.c_int, [C.c_void_p]),
+    "mscs_xchg_barrier": (C.c_int, [_PTRS, C.c_int, C.c_int, C.c_uint32, C.c_double, C.c_void_p]),
+    "mscs_xchg_push": (C.c_int, [_PTRS, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_int,
+                                 C.c_void_p]),
+    "mscs_gather_normalize_p2p": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, _PTRS, C.c_int,
+                                            C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mscs_scatter_sectors_pull": (C.c_int, [_PTRS, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

@@ -494,22 +494,27 @@ class _GradBuffers:
             off += n_
         self.side, self.ready = side, None
 
-    def start_fill(self):
-        """Zero-fill on the side stream, ordered after what the main stream has enqueued so far."""
+    def start_fill(self, extra=None):
+        """Zero-fill on the side stream, ordered after what the main stream has enqueued so far.  `extra`: one more
+        (address, bytes) region cleared by the same call (pooled mode: the gradient rows in the exchange slab)."""
         side = self.side
         side.wait_stream(_cur_stream())
-        if self.slab.numel():
-            ptrs = _lib.ptr_array([self.slab.data_ptr()])
+        if self.slab.numel() or extra:
+            regions = ([(self.slab.data_ptr(), 4 * self.slab.numel())] if self.slab.numel() else []) + \
+                ([extra] if extra else [])
+            ptrs = _lib.ptr_array([r[0] for r in regions])
             if TIMING is not None:      # bench.py: the fill's own duration, on the stream it runs on
                 e0 = torch.cuda.Event(enable_timing=True)
                 e0.record(side)
-            _lib.check(_lib.load().mscs_fill_bytes(ptrs, (C.c_int32 * 1)(0), (C.c_size_t * 1)(4 * self.slab.numel()), 1,
+            _lib.check(_lib.load().mscs_fill_bytes(ptrs, (C.c_int32 * len(regions))(*([0] * len(regions))),
+                                                   (C.c_size_t * len(regions))(*[r[1] for r in regions]), len(regions),
                                                    C.c_void_p(side.cuda_stream)), "mscs_fill_bytes")
             if TIMING is not None:
                 e1 = torch.cuda.Event(enable_timing=True)
                 e1.record(side)
                 TIMING.setdefault("zero_fill", []).append((e0, e1))
-            self.slab.record_stream(side)
+            if self.slab.numel():
+                self.slab.record_stream(side)
         self.ready = torch.cuda.Event()
         self.ready.record(side)
 
@@ -524,38 +529,65 @@ class _GradBuffers:
         return d
 
 
-# ---- pooled cross-batch mode: collectives -----------------------------------------------------
-class TorchDistComm:
-    """torch.distributed (NCCL over NVLink) collectives of the pooled mode: one process per GPU."""
+# ---- pooled cross-batch mode: exchange over NVLink peer memory ---------------------------------
+class _SymSlab:
+    """One rank's view of the exchange slabs of all ranks (csrc/xchg.cu): `local` = address of the own slab, `peers` =
+    ctypes array of every rank's slab as mapped here (peers[rank] == local), `epoch` = barrier counter (identical
+    sequence on every rank), `parity` = which half the next step uses."""
 
-    def __init__(self, group=None):
+    def __init__(self, local, peer_ptrs, keep=None):
+        self.local, self.peers, self.keep = local, _lib.ptr_array(peer_ptrs), keep
+        self.epoch, self.parity = 0, 0
+
+
+class TorchDistComm:
+    """Pooled mode over the GPUs of one box, one process per GPU.  torch.distributed (NCCL) carries only the two
+    tiny control-plane exchanges (class histograms, IPC handles); the data plane -- normalised key rows, row
+    statistics, gradient rows -- is written / read by the library's own kernels over NVLink peer memory, ordered by a
+    device-side flag barrier (mscs_xchg_*)."""
+
+    def __init__(self, group=None, barrier_timeout_s=20.0):
         import torch.distributed as dist
         self.dist, self.group = dist, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.owns_rng = True
-
-    def all_reduce(self, t):
-        self.dist.all_reduce(t, group=self.group)
+        self.timeout = barrier_timeout_s
+        if self.world > _lib.MAX_RANKS:
+            raise ValueError(f"pooled mode supports up to {_lib.MAX_RANKS} ranks (one box), got {self.world}")
 
     def all_gather(self, t):
         out = torch.empty(self.world * t.numel(), dtype=t.dtype, device=t.device)
         self.dist.all_gather_into_tensor(out, t.reshape(-1), group=self.group)
         return out
 
-    def all_reduce_async(self, t):
-        """Returns a handle whose wait() orders the current stream after the collective."""
-        return self.dist.all_reduce(t, group=self.group, async_op=True)
+    def symmetric(self, nbytes, dev):
+        """Collective: every rank allocates its exchange slab (cudaMalloc, zeroed) and maps everybody else's."""
+        lib = _lib.load()
+        ptr, handle = C.c_void_p(), C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        _lib.check(lib.mscs_xchg_alloc(nbytes, C.byref(ptr), handle), "mscs_xchg_alloc")
+        mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=dev)
+        handles = self.all_gather(mine).cpu().numpy().reshape(self.world, _lib.IPC_HANDLE_BYTES)
+        peers = []
+        for r in range(self.world):
+            if r == self.rank:
+                peers.append(ptr.value)
+                continue
+            q = C.c_void_p()
+            _lib.check(lib.mscs_xchg_open(handles[r].tobytes(), C.byref(q)), "mscs_xchg_open")
+            peers.append(q.value)
+        return _SymSlab(ptr.value, peers)
 
-    def all_gather_blocks_async(self, buf, per):
-        """In place: block r (buf[r*per:(r+1)*per]) is valid on rank r; afterwards all `world` blocks are valid
-        everywhere.  Half the volume of the all-reduce that would do the same job on zero-initialised buffers."""
-        return self.dist.all_gather_into_tensor(buf[:self.world * per], buf[self.rank * per:(self.rank + 1) * per],
-                                                group=self.group, async_op=True)
+    def barrier(self, slab):
+        """Device-side barrier on the current stream (no host wait)."""
+        slab.epoch += 1
+        _lib.check(_lib.load().mscs_xchg_barrier(slab.peers, self.world, self.rank, slab.epoch, self.timeout, _stream()),
+                   "mscs_xchg_barrier")
 
 
 class ThreadComm:
-    """In-process emulation of `world` ranks on ONE device (one Python thread per rank, lock-step
-    collectives).  Test infrastructure for the pooled mode's host logic and row-range kernels."""
+    """In-process emulation of `world` ranks on ONE device (one Python thread per rank): the slabs of all "ranks" live
+    in one address space (the peer stores of the kernels are plain local stores) and the barrier is a host barrier
+    around a device synchronisation.  Test infrastructure for the pooled mode's host logic and row-range kernels."""
 
     class _Shared:
         def __init__(self, world):
@@ -580,26 +612,18 @@ class ThreadComm:
         sh.barrier.wait()
         return res
 
-    def all_reduce(self, t):
-        res = self._exchange(t, lambda ts: torch.stack([x.clone() for x in ts]).sum(0).to(ts[0].dtype))
-        t.copy_(res)
-
     def all_gather(self, t):
         return self._exchange(t, lambda ts: torch.cat([x.reshape(-1) for x in ts])).clone()
 
-    class _Done:
-        def wait(self):
-            pass
+    def symmetric(self, nbytes, dev):
+        mine = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        ptrs = self._exchange(mine.data_ptr(), lambda xs: list(xs))
+        return _SymSlab(mine.data_ptr(), list(ptrs), keep=mine)
 
-    def all_reduce_async(self, t):
-        self.all_reduce(t)
-        return ThreadComm._Done()
-
-    def all_gather_blocks_async(self, buf, per):
-        mine = buf[self.rank * per:(self.rank + 1) * per]
-        res = self._exchange(mine, lambda ts: torch.cat([x.reshape(-1).clone() for x in ts]))
-        buf[:self.world * per].copy_(res)
-        return ThreadComm._Done()
+    def barrier(self, slab):
+        slab.epoch += 1
+        torch.cuda.synchronize()
+        self.sh.barrier.wait()
 
 
 def shard_rows(N, world, rank):
@@ -720,6 +744,18 @@ class _StepPlan:
             self.dF_off.append(off)
             off += (self.Ncap[s] + 128 * world) * self.C_pad      # slack: `world` 128-aligned row blocks (pooled mode)
         self.dF_n = off
+        # pooled mode: layout of the exchange slab (identical on every rank): barrier flags, then per step parity the
+        # operand matrices (bf16), the row statistics and the gradient rows.  Two parities: a rank that runs ahead
+        # writes the next step's rows while a slower rank still reads this step's.
+        self.x_off, off = [], 256
+        for _par in range(2):
+            d = {}
+            for name, nbytes in (("b", 2 * self.bslab_n), ("stats", 4 * self.stats_n), ("dF", 4 * self.dF_n)):
+                d[name] = off
+                off += (nbytes + 255) // 256 * 256
+            self.x_off.append(d)
+        self.x_bytes = off
+        self.xslab = None            # _SymSlab, created by the first pooled call (collective)
 
 
 _step_plans = {}
@@ -873,7 +909,9 @@ def run_forward(sp, labels, feats32, needs, comm=None, philox=None):
     if philox is not None:
         raise NotImplementedError("sampler='philox' is implemented for the single-process path with feature planes "
                                   "that are a multiple of 8 pixels (or channels-last inputs)")
-    return _run_forward_general(sp, labels, feats32, needs, comm, pooled)
+    if pooled:
+        return _run_forward_pooled(sp, labels, feats32, needs, comm)
+    return _run_forward_general(sp, labels, feats32, needs)
 
 
 def _finish_rng(sp, dev, mt, pos, total):
@@ -989,9 +1027,9 @@ def _run_forward_fast(sp, labels, feats32, needs, philox=None):
     return state
 
 
-def _run_forward_general(sp, labels, feats32, needs, comm, pooled):
-    """Host-driven order on one stream: plan, fetch (host sync), select, gather, forward.  Used by the pooled
-    multi-rank mode (collectives in between) and by planes that are not a multiple of 8 pixels."""
+def _run_forward_general(sp, labels, feats32, needs):
+    """Host-driven order on one stream: plan, fetch (host sync), select, gather, forward.  Single process, planes that
+    are not a multiple of 8 pixels (no slot maps) or selection shared memory beyond the fast path's limit."""
     lib = _lib.load()
     dev, S, A, spec = sp.dev, sp.S, sp.A, sp.spec
     st = _stream()
@@ -999,24 +1037,12 @@ def _run_forward_general(sp, labels, feats32, needs, comm, pooled):
     ws = torch.empty(sp.ws_bytes, dtype=u8, device=dev)
     plan_dev = torch.empty(S * C.sizeof(_lib.ScalePlan), dtype=u8, device=dev)
     with _timed("sample"):
-        if not pooled:
-            _lib.check(lib.mscs_sample_plan(C.byref(sp.cfg), labels.data_ptr(), ws.data_ptr(), plan_dev.data_ptr(),
-                                            st), "mscs_sample_plan")
-        else:
-            # local histograms -> all-gather of the (image, class) counts -> identical global plan on every rank
-            _lib.check(lib.mscs_sample_hist(C.byref(sp.cfg), labels.data_ptr(), ws.data_ptr(), st), "mscs_sample_hist")
-            nA = sp.n_local * A
-            local = torch.cat([ws[sp.counts_off[s]:sp.counts_off[s] + 4 * nA].view(i32) for s in range(S)])
-            gathered = comm.all_gather(local).view(comm.world, S, nA)
-            counts_g = gathered.permute(1, 0, 2).contiguous()          # [S][n_global][A]
-            cptr = _lib.ptr_array([counts_g[s].data_ptr() for s in range(S)])
-            _lib.check(lib.mscs_sample_plan_from_counts(C.byref(sp.cfg), cptr, ws.data_ptr(), plan_dev.data_ptr(),
-                                                        st), "mscs_sample_plan_from_counts")
+        _lib.check(lib.mscs_sample_plan(C.byref(sp.cfg), labels.data_ptr(), ws.data_ptr(), plan_dev.data_ptr(), st),
+                   "mscs_sample_plan")
         sizes = sp.slot_sizes
-        islab = (torch.zeros if pooled else torch.empty)(sp.islab_n, dtype=i32, device=dev)
+        islab = torch.empty(sp.islab_n, dtype=i32, device=dev)
         fslab = torch.empty(sp.fslab_n, dtype=f32, device=dev)
-        # pooled: rows of other ranks must be zero for the all-reduce
-        bslab = (torch.zeros if pooled else torch.empty)(sp.bslab_n, dtype=torch.bfloat16, device=dev)
+        bslab = torch.empty(sp.bslab_n, dtype=torch.bfloat16, device=dev)
         stats = torch.zeros(sp.stats_n, dtype=f32, device=dev)
         misc = torch.empty(sp.misc_n, dtype=f32, device=dev)
         work = torch.empty(sp.work_bytes, dtype=u8, device=dev)
@@ -1047,15 +1073,10 @@ def _run_forward_general(sp, labels, feats32, needs, comm, pooled):
         _lib.check(lib.mscs_plan_fetch(plan_dev.data_ptr(), plan, S, st), "mscs_plan_fetch")     # the host sync
         _raise_plan_errors(plan, S, spec)
         total = sum(int(plan[s].draws) for s in range(S))
-        if pooled:       # rows of other ranks keep pix = -1 (not gathered / scattered here)
-            for s in range(S):
-                islab[sp.ioff[s][2]:sp.ioff[s][2] + sp.Ncap[s]].fill_(-1)
         _lib.check(lib.mscs_sample_select(C.byref(sp.cfg), plan, ws.data_ptr(), draws.data_ptr(), *arrs, sarr, st),
                    "mscs_sample_select")
     samples = [ScaleSample(plan[s].T, plan[s].V, plan[s].N, bool(plan[s].log_flag), plan[s].dl_h, plan[s].dl_w,
                            islab, sp.ioff[s], A) for s in range(S)]
-    if pooled:           # class of every row on every rank (disjoint supports: the sum is the union)
-        comm.all_reduce(islab[sp.cls_begin:])
     with _timed("gather"):
         for s in range(S):
             n, Cc, h, w = sp.feat_shapes[s]
@@ -1068,26 +1089,12 @@ def _run_forward_general(sp, labels, feats32, needs, comm, pooled):
                 _lib.check(lib.mscs_gather_normalize(feats32[s].data_ptr(), n, Cc, h * w, samples[s].ptr(2),
                                                      samples[s].N, bbase + 2 * sp.boff[s], fbase + 4 * sp.foff[s][0],
                                                      fbase + 4 * sp.foff[s][1], st), "mscs_gather_normalize")
-    if pooled:
-        # normalised rows of all ranks: all-gather expressed as a sum of disjoint supports (the slab is
-        # zero-initialised).  One collective: per-scale asynchronous pieces overlapping the gather measured much
-        # slower at 2 GPUs (17.1 vs 13.2 ms per step).
-        comm.all_reduce(bslab)
     for i, (a, k, *_rest) in enumerate(sp.terms):      # the plan-dependent fields of the job
         t = job.terms[i]
         t.N1, t.N2 = samples[a].N, samples[k].N
-        if pooled:       # anchor (and key) rows are sharded over the ranks in 128-row granules
-            t.row_begin, t.row_end = shard_rows(samples[a].N, comm.world, comm.rank)
-            t.krow_begin, t.krow_end = shard_rows(samples[k].N, comm.world, comm.rank)
     with _timed("sim_fwd"):
-        if not pooled:
-            _lib.check(lib.mscs_sim_forward(C.byref(job), st), "mscs_sim_forward")
-        else:
-            _lib.check(lib.mscs_sim_forward_sweeps(C.byref(job), st), "mscs_sim_forward_sweeps")
-            comm.all_reduce(stats)       # row statistics of all ranks' rows
-            _lib.check(lib.mscs_sim_finalize(C.byref(job), st), "mscs_sim_finalize")
-    if comm is None or comm.owns_rng:
-        _finish_rng(sp, dev, mt, pos, total)
+        _lib.check(lib.mscs_sim_forward(C.byref(job), st), "mscs_sim_forward")
+    _finish_rng(sp, dev, mt, pos, total)
     state = _StepState()
     state.sp, state.job, state.samples, state.gradbufs, state.slots = sp, job, samples, gradbufs, slots
     state.keep = (ws, islab, fslab, bslab, stats, misc, work, slot_slab)
@@ -1095,8 +1102,181 @@ def _run_forward_general(sp, labels, feats32, needs, comm, pooled):
     state.fslab, state.term_loss = fslab, misc[sp.out_off:sp.out_off + nt]
     state.total = total_t
     state.scalars = misc[sp.out_off:sp.out_off + nt + 2]      # [term losses..., total, inf/NaN flag]: one copy for the logger
-    state.num_ms, state.cs_logged, state.comm = S, sp.cs_logged, comm if pooled else None
+    state.num_ms, state.cs_logged, state.comm = S, sp.cs_logged, None
     return state
+
+
+def _run_forward_pooled(sp, labels, feats32, needs, comm):
+    """POOLED cross-batch mode (one process per GPU, each with its own images): the reference loss of the concatenated
+    batch of all ranks.  Control plane over NCCL (class histograms: a few KB); data plane by the library's own kernels
+    over NVLink peer memory (csrc/xchg.cu), ordered by three device-side barriers per step:
+
+      K1 histograms -> all-gather of the (image, class) counts -> the SAME global plan on every rank -> selection of the
+      local pixels (class ids of every row come from the plan: no exchange) -> K2 fused with the all-gather: each
+      normalised bf16 row is stored into the same sorted row of EVERY rank's operand matrix -> barrier A ->
+      K3 sweeps over this rank's anchor-row range against all keys -> its row statistics pushed to every peer ->
+      barrier B -> finalise on all rows (every rank then holds the global loss and the coefficients of every row, so
+      the backward needs no reduce-scatter) -> [backward: K4 over the rank's row range -> barrier C -> the scatter
+      PULLS each gradient row of a local pixel from the rank that computed it]."""
+    lib = _lib.load()
+    dev, S, A, spec = sp.dev, sp.S, sp.A, sp.spec
+    st = _stream()
+    i32, f32, u8 = torch.int32, torch.float32, torch.uint8
+    if not all(sp.slot_sizes):
+        raise NotImplementedError("pooled mode needs feature planes that are a multiple of 8 pixels")
+    if sp.xslab is None:
+        sp.xslab = comm.symmetric(sp.x_bytes, dev)           # collective, first call only
+    xs = sp.xslab
+    par = xs.parity
+    xs.parity ^= 1
+    xo = sp.x_off[par]
+    world, rank = comm.world, comm.rank
+    ws = torch.empty(sp.ws_bytes, dtype=u8, device=dev)
+    plan_dev = torch.empty(S * C.sizeof(_lib.ScalePlan), dtype=u8, device=dev)
+    with _timed("sample"):
+        # local histograms -> all-gather of the (image, class) counts -> identical global plan on every rank
+        _lib.check(lib.mscs_sample_hist(C.byref(sp.cfg), labels.data_ptr(), ws.data_ptr(), st), "mscs_sample_hist")
+        nA = sp.n_local * A
+        local = torch.cat([ws[sp.counts_off[s]:sp.counts_off[s] + 4 * nA].view(i32) for s in range(S)])
+        gathered = comm.all_gather(local).view(world, S, nA)
+        counts_g = gathered.permute(1, 0, 2).contiguous()          # [S][n_global][A]
+        cptr = _lib.ptr_array([counts_g[s].data_ptr() for s in range(S)])
+        _lib.check(lib.mscs_sample_plan_from_counts(C.byref(sp.cfg), cptr, ws.data_ptr(), plan_dev.data_ptr(), st),
+                   "mscs_sample_plan_from_counts")
+        sizes = sp.slot_sizes
+        islab = torch.empty(sp.islab_n, dtype=i32, device=dev)
+        fslab = torch.empty(sp.fslab_n, dtype=f32, device=dev)
+        misc = torch.empty(sp.misc_n, dtype=f32, device=dev)
+        work = torch.empty(sp.work_bytes, dtype=u8, device=dev)
+        slot_slab = torch.full((sum(sizes),), -1, dtype=i32, device=dev)
+        slots, off = [], 0
+        for x in sizes:
+            slots.append(slot_slab[off:off + x])
+            off += x
+        # dense gradients (local) and this parity's gradient rows in the slab: zero-filled on the side stream;
+        # this parity's row statistics: zeroed here, i.e. before this rank's barrier A, hence before any peer's push
+        gradbufs = _GradBuffers(feats32, needs, False, 0) if any(needs) else None
+        if gradbufs is not None:
+            gradbufs.start_fill(extra=(xs.local + xo["dF"], 4 * sp.dF_n))
+        _lib.check(lib.mscs_fill_bytes(_lib.ptr_array([xs.local + xo["stats"]]), (C.c_int32 * 1)(0),
+                                       (C.c_size_t * 1)(4 * sp.stats_n), 1, st), "mscs_fill_bytes")
+        mt, pos = torch_mt_state()
+        draws = _stream_cache(dev).acquire(mt, pos, sp.max_draws + _MT_N)
+        plan = (_lib.ScalePlan * S)()
+        ibase = islab.data_ptr()
+        arrs = [_lib.ptr_array([ibase + 4 * sp.ioff[s][k] for s in range(S)]) for k in range(5)]
+        sarr = _lib.ptr_array([x.data_ptr() for x in slots])
+        fbase, bbase = fslab.data_ptr(), xs.local + xo["b"]
+        job = _lib.SimJob()
+        _fill_job(job, sp, A, bbase, ibase, xs.local + xo["stats"], misc.data_ptr(), work.data_ptr())
+        nt = len(sp.terms)
+        mbase = misc.data_ptr()
+        job.term_loss, job.total_loss = mbase + 4 * sp.out_off, mbase + 4 * (sp.out_off + nt)
+        total_t = torch.empty((), dtype=f32, device=dev)      # own buffer, not a view (see _run_forward_fast)
+        job.total_out = total_t.data_ptr()
+        _lib.check(lib.mscs_plan_fetch(plan_dev.data_ptr(), plan, S, st), "mscs_plan_fetch")     # the host sync
+        _raise_plan_errors(plan, S, spec)
+        total = sum(int(plan[s].draws) for s in range(S))
+        _lib.check(lib.mscs_sample_select(C.byref(sp.cfg), plan, ws.data_ptr(), draws.data_ptr(), *arrs, sarr, st),
+                   "mscs_sample_select")
+    samples = [ScaleSample(plan[s].T, plan[s].V, plan[s].N, bool(plan[s].log_flag), plan[s].dl_h, plan[s].dl_w,
+                           islab, sp.ioff[s], A) for s in range(S)]
+    sent = 0
+    with _timed("gather"):
+        for s in range(S):
+            n, Cc, h, w = sp.feat_shapes[s]
+            _lib.check(lib.mscs_gather_normalize_p2p(feats32[s].data_ptr(), n, Cc, h * w, slots[s].data_ptr(),
+                                                     samples[s].N, xs.peers, world, rank, xo["b"] + 2 * sp.boff[s],
+                                                     fbase + 4 * sp.foff[s][0], fbase + 4 * sp.foff[s][1], st),
+                       "mscs_gather_normalize_p2p")
+        comm.barrier(xs)                                   # A: every rank's key rows have landed here
+    push_off, push_len = [], []
+    for i, (a, k, *_rest) in enumerate(sp.terms):      # the plan-dependent fields of the job
+        t = job.terms[i]
+        t.N1, t.N2 = samples[a].N, samples[k].N
+        # anchor (and key) rows are sharded over the ranks in 128-row granules
+        t.row_begin, t.row_end = shard_rows(samples[a].N, world, rank)
+        t.krow_begin, t.krow_end = shard_rows(samples[k].N, world, rank)
+        n1 = (sp.Ncap[a] + 15) // 16 * 16
+        for q in range(3):      # neg, pos, S of this rank's rows
+            push_off.append(xo["stats"] // 4 + sp.soff[i] + q * n1 + t.row_begin)
+            push_len.append(t.row_end - t.row_begin)
+    with _timed("sim_fwd"):
+        _lib.check(lib.mscs_sim_forward_sweeps(C.byref(job), st), "mscs_sim_forward_sweeps")
+        _lib.check(lib.mscs_xchg_push(xs.peers, world, rank, (C.c_int64 * len(push_off))(*push_off),
+                                      (C.c_int32 * len(push_len))(*push_len), len(push_off), st), "mscs_xchg_push")
+        comm.barrier(xs)                                   # B: the statistics of every row are complete here
+        _lib.check(lib.mscs_sim_finalize(C.byref(job), st), "mscs_sim_finalize")
+    if comm.owns_rng:
+        _finish_rng(sp, dev, mt, pos, total)
+    state = _StepState()
+    state.sp, state.job, state.samples, state.gradbufs, state.slots = sp, job, samples, gradbufs, slots
+    state.keep = (ws, islab, fslab, misc, work, slot_slab)
+    state.stats = None
+    state.fslab, state.term_loss = fslab, misc[sp.out_off:sp.out_off + nt]
+    state.total = total_t
+    state.scalars = misc[sp.out_off:sp.out_off + nt + 2]      # [term losses..., total, inf/NaN flag]: one copy for the logger
+    state.num_ms, state.cs_logged, state.comm = S, sp.cs_logged, comm
+    state.xs, state.par = xs, par
+    n_local = sum(int(samples[s].N) for s in range(S)) / world        # rows this rank owns, on average
+    state.exchange_info = {
+        "transport": "NVLink peer stores / loads by the library's kernels (CUDA IPC slabs) + device-side flag barriers; "
+                     "NCCL only for the class histograms",
+        "barriers_per_step": 3,
+        "nccl_all_gather_bytes": int(local.numel() * 4 * world),
+        "key_rows_stored_to_peers_bytes": int(n_local * sp.C_pad * 2 * (world - 1)),
+        "row_statistics_pushed_bytes": int(sum(push_len) * 4 * (world - 1)),
+        "gradient_rows_pulled_bytes": int(n_local * sp.C_pad * 4 * (world - 1) / world)}
+    return state
+
+
+def _run_backward_pooled(state, grad_out, needs, shapes, dtypes):
+    """Pooled mode: every rank computes the COMPLETE gradient rows of its 128-aligned row block of every anchor set
+    (one launch for all passes) into its exchange slab; after the barrier the scatter pulls the row of every LOCAL
+    pixel from the rank that computed it -- an eighth of the rows travels, once, to where it is needed."""
+    lib = _lib.load()
+    sp, comm, xs = state.sp, state.comm, state.xs
+    dev, S = sp.dev, sp.S
+    st = _stream()
+    xo = sp.x_off[state.par]
+    gb = state.gradbufs
+    first = gb is not None and gb.ready is not None and not getattr(state, "bwd_done", False)
+    if first:
+        _cur_stream().wait_event(gb.ready)          # the side-stream zero fill (dense gradients + the slab's row region)
+    else:                                           # second backward through the same graph: clear the row region again
+        _lib.check(lib.mscs_fill_bytes(_lib.ptr_array([xs.local + xo["dF"]]), (C.c_int32 * 1)(0),
+                                       (C.c_size_t * 1)(4 * sp.dF_n), 1, st), "mscs_fill_bytes")
+        comm.barrier(xs)                            # nobody still pulls the previous rows
+    state.bwd_done = True
+    base = xs.local + xo["dF"]
+    ptrs = [0] * _lib.MAX_SCALES
+    lds = (C.c_int32 * _lib.MAX_SCALES)()
+    for s in range(S):
+        ptrs[s], lds[s] = base + 4 * sp.dF_off[s], sp.C_pad
+    g = grad_out.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+    with _timed("sim_bwd"):
+        _lib.check(lib.mscs_sim_backward(C.byref(state.job), g.data_ptr(), _lib.ptr_array(ptrs), lds, st),
+                   "mscs_sim_backward")
+        comm.barrier(xs)                            # C: every rank's gradient rows are complete
+    grads = []
+    fbase = state.fslab.data_ptr()
+    with _timed("scatter"):
+        for s in range(S):
+            if not needs[s]:
+                grads.append(None)
+                continue
+            n, Cc, h, w = shapes[s]
+            pre = gb.take(s) if gb is not None else None
+            if pre is None:
+                pre = torch.zeros(shapes[s], dtype=torch.float32, device=dev)
+            N = state.samples[s].N
+            per = ((N + 127) // 128 + comm.world - 1) // comm.world * 128
+            _lib.check(lib.mscs_scatter_sectors_pull(xs.peers, comm.world, xo["dF"] + 4 * sp.dF_off[s], per, sp.C_pad,
+                                                     fbase + 4 * sp.foff[s][0], fbase + 4 * sp.foff[s][1],
+                                                     state.slots[s].data_ptr(), n, Cc, h * w, pre.data_ptr(), st),
+                       "mscs_scatter_sectors_pull")
+            grads.append(pre if dtypes[s] == torch.float32 else pre.to(dtypes[s]))
+    return grads
 
 
 def run_backward(state, grad_out, needs, shapes, dtypes):
@@ -1104,6 +1284,8 @@ def run_backward(state, grad_out, needs, shapes, dtypes):
     sp = state.sp
     dev, S = sp.dev, sp.S
     st = _stream()
+    if state.comm is not None:
+        return _run_backward_pooled(state, grad_out, needs, shapes, dtypes)
     # gradient rows: zeroed ahead of time together with the dense gradients (side stream, during the forward)
     dF = None
     if state.gradbufs is not None:
@@ -1118,26 +1300,9 @@ def run_backward(state, grad_out, needs, shapes, dtypes):
     for s in range(S):
         ptrs[s], lds[s] = base + 4 * sp.dF_off[s], sp.C_pad
     g = grad_out.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
-    handles = [None] * S
     with _timed("sim_bwd"):
-        if state.comm is None:
-            _lib.check(lib.mscs_sim_backward(C.byref(state.job), g.data_ptr(), _lib.ptr_array(ptrs), lds, st),
-                       "mscs_sim_backward")
-        else:
-            # Pooled mode.  Every rank computes the COMPLETE gradient rows of its 128-aligned row block of every set;
-            # the owners of the pixels need them: all-gather of the blocks (in place).  The backward is launched set
-            # by set (largest first) and each set's exchange starts as soon as its launch is enqueued, so it overlaps
-            # the tensor work of the following sets; the scatter of a set waits for its own exchange only.
-            comm = state.comm
-            order = sorted(range(S), key=lambda s_: -state.samples[s_].N)
-            pa = _lib.ptr_array(ptrs)
-            for s in order:
-                _lib.check(lib.mscs_sim_backward_sets(C.byref(state.job), g.data_ptr(), pa, lds, 1 << s, st),
-                           "mscs_sim_backward_sets")
-                N = state.samples[s].N
-                per = ((N + 127) // 128 + comm.world - 1) // comm.world * 128
-                rows = dF[sp.dF_off[s]:sp.dF_off[s] + comm.world * per * sp.C_pad]
-                handles[s] = comm.all_gather_blocks_async(rows, per * sp.C_pad)
+        _lib.check(lib.mscs_sim_backward(C.byref(state.job), g.data_ptr(), _lib.ptr_array(ptrs), lds, st),
+                   "mscs_sim_backward")
     grads = []
     fbase = state.fslab.data_ptr()
     if sp.nhwc:
@@ -1162,7 +1327,7 @@ def run_backward(state, grad_out, needs, shapes, dtypes):
                 _lib.check(lib.mscs_scatter_rows_nhwc_batch(items, len(idx), st), "mscs_scatter_rows_nhwc_batch")
             return [None if not needs[s] else (outs[s] if dtypes[s] == torch.float32 else outs[s].to(dtypes[s]))
                     for s in range(S)]
-    dense = state.comm is None and state.gradbufs is None and \
+    dense = state.gradbufs is None and \
         all((not needs[s]) or (state.slots[s] is not None) for s in range(S))
     if dense:
         with _timed("scatter"):
@@ -1199,18 +1364,12 @@ def run_backward(state, grad_out, needs, shapes, dtypes):
                 continue
             n, Cc, h, w = shapes[s]
             smp = state.samples[s]
-            if handles[s] is not None:
-                handles[s].wait()
             pre, slot = (gb.take(s) if gb is not None else None), state.slots[s]
             if pre is not None and slot is not None:
                 out = pre
-                if state.comm is None:      # single process: every scale in one launch (below)
-                    batch.append((ptrs[s], fbase + 4 * sp.foff[s][0], fbase + 4 * sp.foff[s][1], slot.data_ptr(),
-                                  n, Cc, h * w, out.data_ptr()))
-                else:
-                    _lib.check(lib.mscs_scatter_sectors(ptrs[s], sp.C_pad, fbase + 4 * sp.foff[s][0],
-                                                        fbase + 4 * sp.foff[s][1], slot.data_ptr(), n, Cc, h * w,
-                                                        out.data_ptr(), st), "mscs_scatter_sectors")
+                # every scale in one launch (below)
+                batch.append((ptrs[s], fbase + 4 * sp.foff[s][0], fbase + 4 * sp.foff[s][1], slot.data_ptr(),
+                              n, Cc, h * w, out.data_ptr()))
             else:
                 out = torch.empty(shapes[s], dtype=torch.float32, device=dev)
                 _lib.check(lib.mscs_scatter_grad(ptrs[s], sp.C_pad, fbase + 4 * sp.foff[s][0],

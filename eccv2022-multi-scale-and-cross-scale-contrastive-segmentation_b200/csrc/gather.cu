@@ -171,10 +171,14 @@ __global__ void k_slot_map(const int* __restrict__ pix, int N, int* __restrict__
 // Sector writer: the dense gradient is already zero; one warp per 8-pixel octet (= one 32-byte
 // sector per channel plane) rewrites every sector that holds at least one sampled pixel with
 // full-sector stores (values + explicit zeros), so no partial-sector read-modify-write reaches HBM.
+// pooled mode: gradient row i was computed by rank i / rows_per_rank and is READ FROM THAT RANK'S slab over NVLink
+// (n == 0: every row is local, `dF` is used)
+struct PullRows { const float* p[MSCS_MAX_RANKS]; int n, rows_per_rank; };
+
 __device__ __forceinline__ void
 scatter_sectors_body(const float* __restrict__ dF, int ldF, const float* __restrict__ anc_f32,
                   const float* __restrict__ inv_norm, const int* __restrict__ slot, int n_octets, int C,
-                  int plane, float* __restrict__ dfeat, int block_base) {
+                  int plane, float* __restrict__ dfeat, int block_base, const PullRows* pull = nullptr) {
   const int lane = threadIdx.x & 31;
   const int oct = ((int)blockIdx.x - block_base) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (oct >= n_octets) return;
@@ -187,7 +191,7 @@ scatter_sectors_body(const float* __restrict__ dF, int ldF, const float* __restr
   for (int j = 0; j < 8; ++j) {
     const int row = __shfl_sync(0xffffffffu, s_mine, j);
     if (row >= 0) {                                   // warp-uniform
-      const float* g = dF + (size_t)row * ldF;
+      const float* g = (pull ? pull->p[row / pull->rows_per_rank] : dF) + (size_t)row * ldF;
       const float* f = anc_f32 + (size_t)row * C;
       float gv[kMaxC / 32], fv[kMaxC / 32], dot = 0.f;
 #pragma unroll
@@ -223,6 +227,12 @@ k_scatter_sectors(const float* __restrict__ dF, int ldF, const float* __restrict
                   const float* __restrict__ inv_norm, const int* __restrict__ slot, int n_octets, int C,
                   int plane, float* __restrict__ dfeat, int block_base) {
   scatter_sectors_body(dF, ldF, anc_f32, inv_norm, slot, n_octets, C, plane, dfeat, block_base);
+}
+__global__ void __launch_bounds__(256)
+k_scatter_sectors_pull(const __grid_constant__ PullRows pull, int ldF, const float* __restrict__ anc_f32,
+                       const float* __restrict__ inv_norm, const int* __restrict__ slot, int n_octets, int C,
+                       int plane, float* __restrict__ dfeat) {
+  scatter_sectors_body(nullptr, ldF, anc_f32, inv_norm, slot, n_octets, C, plane, dfeat, 0, &pull);
 }
 
 
@@ -468,6 +478,28 @@ extern "C" int mscs_scatter_sectors(const float* dF, int ldF, const float* anc_f
   const int n_oct = n * (plane / 8);
   k_scatter_sectors<<<ceil_div(n_oct, 8), 256, 0, (cudaStream_t)stream_>>>(dF, ldF, anc_f32, inv_norm, slot, n_oct,
                                                                            C, plane, dfeat, 0);
+  MSCS_LAUNCH_CHECK();
+  return 0;
+}
+
+// pooled mode: the same scatter with every gradient row read from the rank that computed it (row / rows_per_rank)
+extern "C" int mscs_scatter_sectors_pull(void* const* slabs, int world, size_t dF_byte_off, int rows_per_rank, int ldF,
+                                         const float* anc_f32, const float* inv_norm, const int32_t* slot, int n, int C,
+                                         int plane, float* dfeat, void* stream_) {
+  MSCS_CHECK_ARG(slabs && anc_f32 && inv_norm && slot && dfeat, "null pointer argument");
+  MSCS_CHECK_ARG(world >= 1 && world <= MSCS_MAX_RANKS && rows_per_rank >= 1, "bad world %d / rows per rank %d", world,
+                 rows_per_rank);
+  MSCS_CHECK_ARG(C >= 1 && C <= kMaxC && ldF >= C, "C=%d / ldF=%d unsupported", C, ldF);
+  MSCS_CHECK_ARG(plane % 8 == 0, "plane %d is not a multiple of 8 pixels", plane);
+  PullRows pull{};
+  pull.n = world; pull.rows_per_rank = rows_per_rank;
+  for (int r = 0; r < world; ++r) {
+    MSCS_CHECK_ARG(slabs[r] != nullptr, "peer %d: null slab pointer", r);
+    pull.p[r] = reinterpret_cast<const float*>((const char*)slabs[r] + dF_byte_off);
+  }
+  const int n_oct = n * (plane / 8);
+  k_scatter_sectors_pull<<<ceil_div(n_oct, 8), 256, 0, (cudaStream_t)stream_>>>(pull, ldF, anc_f32, inv_norm, slot,
+                                                                                n_oct, C, plane, dfeat);
   MSCS_LAUNCH_CHECK();
   return 0;
 }

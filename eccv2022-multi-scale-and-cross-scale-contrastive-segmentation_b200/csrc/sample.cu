@@ -381,8 +381,14 @@ k_fy_select(const __grid_constant__ SampleLayout L, const __grid_constant__ Sele
   if (k == 0)                                   // class segments: identical on every rank
     for (int i = threadIdx.x; i <= A; i += blockDim.x) a.seg[s][i] = reinterpret_cast<const int*>(ws + g.off_seg)[i];
   const int bg = pa.b[k], c = pa.c[k], cnt = pa.cnt[k], dst = pa.dst[k];
-  const int b = bg - L.b0;                      // local image index; other ranks' pairs are skipped
-  if (b < 0 || b >= L.n) return;
+  const int b = bg - L.b0;                      // local image index
+  if (b < 0 || b >= L.n) {
+    // another rank's pair (pooled mode): its pixels are not selected here, but the plan is global, so the class id of
+    // its sorted rows is known on every rank -- no exchange of the class arrays; pix = -1 marks the rows "not local"
+    for (int i = threadIdx.x; i < V; i += blockDim.x) { a.cls[s][dst + i] = c; a.pix[s][dst + i] = -1; }
+    if (threadIdx.x == 0) { a.pair_ref[s][2 * k] = bg; a.pair_ref[s][2 * k + 1] = c; }
+    return;
+  }
   const uint32_t* u = draws + base_s + pa.off[k];
   extern __shared__ int sm[];
   int* t_arr = sm;            // t_i = i + z_i : position swapped with i at step i

@@ -29,6 +29,8 @@ extern "C" {
 #define MSCS_MAX_SCALES 8
 #define MSCS_MAX_TERMS 16   /* single-scale terms + cross-scale terms */
 #define MSCS_MAX_PASSES 32  /* backward passes: 1 per ms term, up to 2 per cs term */
+#define MSCS_MAX_RANKS 8    /* pooled mode: GPUs of one box */
+#define MSCS_IPC_HANDLE_BYTES 64
 
 /* library info ------------------------------------------------------------------------- */
 const char* mscs_version(void);
@@ -287,6 +289,40 @@ int mscs_scatter_rows_nhwc_batch(const mscs_rows_item* items, int count, void* s
  * (one bit per pixel: sampled or not, built inside the call). */
 int mscs_scatter_dense_batch(const mscs_scatter_item* items, const int32_t* rows, int count, uint32_t* mask_scratch,
                              void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Pooled cross-batch mode -- the exchange between the GPUs of one box over NVLink peer memory.  (Not a reference
+ * behaviour: the reference evaluates the loss per rank, utils/distributed.py:63-73 `concat_all_gather` is imported by
+ * DenseContrastiveLossV2_ms.py:3 and never called; BASELINE.json's north_star adds this configuration.)
+ * Every rank owns one exchange slab with the SAME layout; `slabs[r]` is rank r's slab as mapped into this process
+ * (slabs[rank] = the local allocation).  Word r of the first 32 bytes of a slab is the barrier epoch of rank r.
+ * ------------------------------------------------------------------------------------- */
+/* cudaMalloc + zero fill + CUDA IPC export (handle_out: MSCS_IPC_HANDLE_BYTES bytes, to be sent to the peers) */
+int mscs_xchg_alloc(size_t bytes, void** dev_ptr, unsigned char* handle_out);
+/* map a peer's slab from its IPC handle (peer access is enabled on first use) / unmap it */
+int mscs_xchg_open(const unsigned char* handle, void** dev_ptr);
+int mscs_xchg_close(void* dev_ptr);
+int mscs_xchg_free(void* dev_ptr);
+/* Device-side barrier across the ranks (async, one tiny kernel): everything this rank enqueued on `stream` before the
+ * call -- peer stores included -- is visible to every rank after ITS barrier call with the same epoch has completed.
+ * `epoch`: strictly increasing per slab (1, 2, 3, ...), the same sequence on every rank.  A rank that waits longer than
+ * timeout_s seconds (<= 0: 20 s) traps, i.e. the stream reports a launch failure instead of hanging. */
+int mscs_xchg_barrier(void* const* slabs, int world, int rank, uint32_t epoch, double timeout_s, void* stream);
+/* copy `count` (<= 48) float ranges [float_off[j], float_off[j] + len[j]) of the local slab to the same offsets of
+ * every peer's slab (row statistics of this rank's anchor rows) */
+int mscs_xchg_push(void* const* slabs, int world, int rank, const int64_t* float_off, const int32_t* len, int count,
+                   void* stream);
+/* K2 fused with the all-gather of the normalised key set: as mscs_gather_normalize_sectors, but every bf16 anchor row
+ * is stored into the operand matrix at byte offset bf16_byte_off of EVERY rank's slab (same sorted row everywhere: the
+ * plan is global); fp32 rows and inverse norms stay local.  Also zeroes the local padding rows [N, N_pad). */
+int mscs_gather_normalize_p2p(const float* feat, int n, int C, int plane, const int32_t* slot, int N,
+                              void* const* slabs, int world, int rank, size_t bf16_byte_off, float* anc_f32,
+                              float* inv_norm, void* stream);
+/* as mscs_scatter_sectors, with gradient row i read from rank (i / rows_per_rank)'s slab at dF_byte_off (the rank
+ * that computed it: anchor rows are sharded in 128-aligned blocks of rows_per_rank rows) */
+int mscs_scatter_sectors_pull(void* const* slabs, int world, size_t dF_byte_off, int rows_per_rank, int ldF,
+                              const float* anc_f32, const float* inv_norm, const int32_t* slot, int n, int C, int plane,
+                              float* dfeat, void* stream);
 
 #ifdef __cplusplus
 }

@@ -332,7 +332,7 @@ def test_properties_full_size(dev):
 
 
 # ---- pooled cross-batch mode: `world` ranks emulated on one GPU (ThreadComm) ------------------
-def _pooled_emulated(cfg, labels, feats, world, seed, dev):
+def _pooled_emulated(cfg, labels, feats, world, seed, dev, keep_on_device=False):
     import threading
     import mscs_b200
     from mscs_b200 import _ops
@@ -351,7 +351,7 @@ def _pooled_emulated(cfg, labels, feats, world, seed, dev):
             grads = _ops.run_backward(mod.last_state, torch.ones((), device=dev), [True] * len(fts),
                                       [tuple(f.shape) for f in fts], [f.dtype for f in fts])
             torch.cuda.synchronize()
-            results[r] = (float(loss.detach()), [g.cpu() for g in grads],
+            results[r] = (float(loss.detach()), [g if keep_on_device else g.cpu() for g in grads],
                           [float(x) for x in mod.ms_losses] + [float(x) for x in mod.cs_losses])
         except Exception as e:      # noqa: BLE001
             errors.append(e)
@@ -403,6 +403,42 @@ def test_pooled_mode_matches_single_process(world, dev):
             err = float((g - want).abs().max())
             print(f"world {world} rank {r} scale {s}: grad cosine {cs:.8f} max-abs {err:.3e}")
             assert cs > 0.99999
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_pooled_cfg5_vs_fp64_oracle_fixture(world, golden, dev):
+    """BASELINE config 5 (64 images pooled over the ranks) through the POOLED code path -- `world` ranks emulated on
+    this GPU (ThreadComm: same kernels, row ranges, peer-store gather, statistics push and pull scatter as under
+    torchrun; only the transport is local) -- against the chunked fp64 oracle's loss and gradient rows
+    (tests/golden/cfg5.npz).  tools/pooled_check.py repeats the comparison over real NVLink ranks."""
+    from mscs_b200 import synth
+    meta, z = golden["cfg5"], load_npz("cfg5")
+    labels, feats = synth.make_inputs("cfg5")
+    res = _pooled_emulated(dict(meta["loss_cfg"]), labels, feats, world, 0, dev, keep_on_device=True)
+    nl = labels.shape[0] // world
+    for r, (l, grads, terms) in enumerate(res):
+        rel = abs(l - meta["total"]) / abs(meta["total"])
+        assert rel < 1e-3, (r, l, meta["total"])
+        for a, b in zip(terms, meta["ms"] + meta["cs"]):
+            assert abs(a - b) < 1e-3 * abs(b), (r, a, b)
+    print(f"pooled cfg5 x{world}: loss {res[0][0]:.6f} oracle {meta['total']:.6f}")
+    for s in range(len(feats)):
+        idx, pairs, ids = z[f"idx{s}"], z[f"pairs{s}"], z[f"grad_row_ids{s}"]
+        T, V = idx.shape
+        k, v = ids // V, ids % V
+        rows = np.empty((len(ids), feats[s].shape[1]), dtype=np.float32)
+        for j in range(len(ids)):
+            b, p = int(pairs[k[j], 0]), int(idx[k[j], v[j]])
+            g = res[b // nl][1][s]
+            rows[j] = g[b % nl].reshape(g.shape[1], -1)[:, p].cpu().numpy()
+        cs, err = cosine(rows, z[f"grad_rows{s}"]), np.abs(rows - z[f"grad_rows{s}"]).max()
+        tot = float(np.sqrt(sum(float(res[r][1][s].double().pow(2).sum()) for r in range(world))))
+        touched = sum(int((res[r][1][s] != 0).any(dim=1).sum()) for r in range(world))
+        print(f"pooled cfg5 x{world} scale {s}: grad rows cosine {cs:.7f} max-abs {err:.3e}; |grad| {tot:.6e} vs "
+              f"{meta['grad_l2'][s]:.6e}; {touched} pixels touched")
+        assert cs >= 0.999
+        assert abs(tot - meta["grad_l2"][s]) < 1e-2 * meta["grad_l2"][s]
+        assert touched == T * V
 
 
 # ---- API behaviours of the reference classes ----------------------------------------------------

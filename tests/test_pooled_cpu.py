@@ -2,8 +2,8 @@
 
 The kernels need a GPU, so what runs here is the partition itself with the oracle standing in for
 the kernels: every rank computes the row statistics / gradient rows of ITS row range against all keys,
-the ranks exchange them with the same collectives the product uses (sum of disjoint supports), and
-the result must equal the single-process oracle."""
+the ranks exchange them (here with gloo collectives; the product moves the same row ranges with its own kernels over
+NVLink peer memory, csrc/xchg.cu), and the result must equal the single-process oracle."""
 import os
 import socket
 
@@ -58,17 +58,20 @@ def _worker(rank, world, port, out):
     allc = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(allc, mine)
     ok_gather = all(int(allc[r][0, 0]) == r for r in range(world))
-    # gradient rows: every rank holds the complete rows of its 128-aligned block; the product exchanges them with an
-    # in-place block all-gather (TorchDistComm.all_gather_blocks_async) instead of an all-reduce of a zero-filled buffer
+    # gradient rows: every rank holds the complete rows of its 128-aligned block; in the product the scatter of a rank
+    # PULLS row i of a local pixel from rank i // per (mscs_scatter_sectors_pull).  Emulated with an all-gather of
+    # the blocks: the rule "row i lives on rank i // per" must reproduce every row, for every owner of pixels
     from mscs_b200 import TorchDistComm
     comm = TorchDistComm()
+    assert comm.world == world and comm.rank == rank
     Cp = 8
     per = ((N + 127) // 128 + world - 1) // world * 128
     rows_full = torch.from_numpy(rng.randn(world * per, Cp)).float()          # same on every rank (same seed)
-    buf = torch.zeros(world * per * Cp + 3 * Cp)                               # slack like the dF slab
-    buf[rank * per * Cp:(rank + 1) * per * Cp] = rows_full[rank * per:(rank + 1) * per].reshape(-1)
-    comm.all_gather_blocks_async(buf[:world * per * Cp], per * Cp).wait()
-    ok_blocks = torch.equal(buf[:world * per * Cp], rows_full.reshape(-1)) and float(buf[world * per * Cp:].abs().max()) == 0.0
+    mine_blk = rows_full[rank * per:(rank + 1) * per].contiguous()
+    blocks = comm.all_gather(mine_blk).view(world, per, Cp)
+    rows_i = torch.arange(N)
+    pulled = blocks[rows_i // per, rows_i % per]
+    ok_blocks = torch.equal(pulled, rows_full[:N]) and shard_rows(N, world, rank) == (min(N, rank * per), min(N, (rank + 1) * per))
     out[rank] = (ok_stats, ok_cover, ok_gather and ok_blocks)
     dist.destroy_process_group()
 
