@@ -122,6 +122,14 @@ gather_sectors_body(int block, int nblocks, const float* __restrict__ feat, int 
     }
 #pragma unroll
     for (int q = 0; q < kMaxC / 32; ++q) ss = fmaf(v[q], v[q], ss);
+    if (anc_bf16 == nullptr) {      // raw mode (projector-tail path): the sampled rows as they are, no normalisation
+#pragma unroll
+      for (int q = 0; q < kMaxC / 32; ++q) {
+        const int c = lane + 32 * q;
+        if (c < C) anc_f32[(size_t)row * C + c] = v[q];
+      }
+      continue;
+    }
     ss = warp_sum(ss);
     const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
     if (lane == 0) inv_norm[row] = inv;
@@ -192,6 +200,14 @@ scatter_sectors_body(const float* __restrict__ dF, int ldF, const float* __restr
     const int row = __shfl_sync(0xffffffffu, s_mine, j);
     if (row >= 0) {                                   // warp-uniform
       const float* g = (pull ? pull->p[row / pull->rows_per_rank] : dF) + (size_t)row * ldF;
+      if (anc_f32 == nullptr) {      // raw mode (projector-tail path): the rows ARE the pixel gradients
+#pragma unroll
+        for (int q = 0; q < kMaxC / 32; ++q) {
+          const int c = lane + 32 * q;
+          dx[j][q] = (c < C) ? g[c] : 0.f;
+        }
+        continue;
+      }
       const float* f = anc_f32 + (size_t)row * C;
       float gv[kMaxC / 32], fv[kMaxC / 32], dot = 0.f;
 #pragma unroll
@@ -440,6 +456,31 @@ extern "C" int mscs_gather_normalize_sectors(const float* feat, int n, int C, in
   const int n_oct = n * (plane / 8);
   k_gather_sectors<<<ceil_div(n_oct, 8), 256, 0, st>>>(feat, C, C_pad, plane, slot, n_oct, (__nv_bfloat16*)anc_bf16,
                                                        anc_f32, inv_norm, nullptr);
+  MSCS_LAUNCH_CHECK();
+  return 0;
+}
+
+// Projector-tail path: the sampled pixels' c_in-vectors as they are (no normalisation), rows in
+// sorted-anchor order, and the matching scatter of row gradients into the pre-zeroed dense (n, c_in, h, w) gradient.
+extern "C" int mscs_gather_rows_raw(const float* feat, int n, int C, int plane, const int32_t* slot, float* rows,
+                                    void* stream_) {
+  MSCS_CHECK_ARG(feat && slot && rows, "null pointer argument");
+  MSCS_CHECK_ARG(C >= 1 && C <= kMaxC, "C=%d unsupported (1..%d)", C, kMaxC);
+  MSCS_CHECK_ARG(n >= 1 && plane >= 8 && plane % 8 == 0, "bad sizes (plane must be a multiple of 8)");
+  const int n_oct = n * (plane / 8);
+  k_gather_sectors<<<ceil_div(n_oct, 8), 256, 0, (cudaStream_t)stream_>>>(feat, C, (C + 63) / 64 * 64, plane, slot, n_oct,
+                                                                          nullptr, rows, nullptr, nullptr);
+  MSCS_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int mscs_scatter_rows_raw(const float* drows, int ld, const int32_t* slot, int n, int C, int plane,
+                                     float* dfeat, void* stream_) {
+  MSCS_CHECK_ARG(drows && slot && dfeat, "null pointer argument");
+  MSCS_CHECK_ARG(C >= 1 && C <= kMaxC && ld >= C, "C=%d / ld=%d unsupported", C, ld);
+  MSCS_CHECK_ARG(plane % 8 == 0, "plane %d is not a multiple of 8 pixels", plane);
+  const int n_oct = n * (plane / 8);
+  k_scatter_sectors<<<ceil_div(n_oct, 8), 256, 0, (cudaStream_t)stream_>>>(drows, ld, nullptr, nullptr, slot, n_oct, C,
+                                                                           plane, dfeat, 0);
   MSCS_LAUNCH_CHECK();
   return 0;
 }

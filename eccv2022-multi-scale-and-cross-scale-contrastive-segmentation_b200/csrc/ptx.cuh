@@ -129,10 +129,6 @@ __device__ __forceinline__ void mbar_spin_wait(uint64_t* bar, uint32_t parity, u
 #endif
 }
 
-// ---- warpgroup register re-allocation (setmaxnreg; all four warps of a warpgroup execute the same call) ----------
-template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-
 // ---- fences -----------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() {   // generic-proxy smem writes -> async proxy (UMMA/TMA)
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

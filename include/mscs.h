@@ -291,6 +291,18 @@ int mscs_scatter_dense_batch(const mscs_scatter_item* items, const int32_t* rows
                              void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Projector tail on the sampled rows only (models/Projector.py:49-72: the projector ends in
+ * nn.Conv2d(c_prev, d, kernel_size=1), evaluated densely by the reference although the loss reads <= 10k pixels per
+ * scale).  The 1x1 convolution of the sampled pixels is a plain (N x c_in) x (c_in x d) GEMM on the host side's
+ * library of choice; these two calls move the rows.  plane % 8 == 0; slot = pixel -> sorted row map of K1.
+ *   mscs_gather_rows_raw   rows[slot[b*plane+p]][:] = feat[b, :, p]           (no normalisation)
+ *   mscs_scatter_rows_raw  dfeat[b, :, p] = drows[slot[b*plane+p]][:]          into a PRE-ZEROED dense gradient
+ * ------------------------------------------------------------------------------------- */
+int mscs_gather_rows_raw(const float* feat, int n, int C, int plane, const int32_t* slot, float* rows, void* stream);
+int mscs_scatter_rows_raw(const float* drows, int ld, const int32_t* slot, int n, int C, int plane, float* dfeat,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Pooled cross-batch mode -- the exchange between the GPUs of one box over NVLink peer memory.  (Not a reference
  * behaviour: the reference evaluates the loss per rank, utils/distributed.py:63-73 `concat_all_gather` is imported by
  * DenseContrastiveLossV2_ms.py:3 and never called; BASELINE.json's north_star adds this configuration.)

@@ -29,12 +29,13 @@ T = np.arange(lo, hi)
 print("tile period (issue done -> issue done)      ", m(mma[lo + 1:hi + 1, 2] - mma[lo:hi, 2]))
 print("MMA warp: wait for acc_empty                 ", m(mma[T, 1] - mma[T, 0]))
 print("MMA warp: issue of one tile (16 k-steps)     ", m(mma[T, 2] - mma[T, 1]))
-for name, e in (("warp 4", e4), ("warp 11", e11), ("warp 19", e12)):
-    print(f"{name}: wait acc_full {m(e[T, 1] - e[T, 0])} | copy-out {m(e[T, 3] - e[T, 1])} | math {m(e[T, 2] - e[T, 3])} | "
-          f"tile issued -> woken {m(e[T, 1] - mma[T, 2])} | buffer released -> MMA passes acc_empty of tile+2 "
-          f"{m(mma[T + 2, 1] - e[T, 3])}")
-print("first 24 tiles (cycles since first event): issue-start, issue-end | epi wake, copied out, math done")
+ev = T[T % 2 == 0]; od = T[T % 2 == 1]
+for name, e, sel in (("warp 4 (group 0)", e4, ev), ("warp 11 (group 0)", e11, ev), ("warp 12 (group 1)", e12, od)):
+    print(f"{name}: wait acc_full {m(e[sel, 1] - e[sel, 0])} | math {m(e[sel, 2] - e[sel, 1])} | "
+          f"tile issued -> woken {m(e[sel, 1] - mma[sel, 2])} | math done -> MMA passes acc_empty of tile+2 "
+          f"{m(mma[sel + 2, 1] - e[sel, 2])}")
+print("first 24 tiles (cycles since first event): issue-start, issue-end | epi wake, epi done")
 t0 = mma[0, 0]
 for i in range(min(24, n)):
-    e = e4
-    print(f"  tile {i:3d}: {mma[i,1]-t0:8d} {mma[i,2]-t0:8d} | {e[i,1]-t0:8d} {e[i,3]-t0:8d} {e[i,2]-t0:8d}")
+    e = e4 if i % 2 == 0 else e12
+    print(f"  tile {i:3d}: {mma[i,1]-t0:8d} {mma[i,2]-t0:8d} | {e[i,1]-t0:8d} {e[i,2]-t0:8d}")
