@@ -287,13 +287,17 @@ def measure_pooled(dev, rank, world, dist, steps=10, warmup=3):
             return loss
         for _ in range(warmup):
             one()
+        from mscs_b200 import _ops
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sync()
+        _ops.TIMING = {}
         e0.record()
         for _ in range(steps):
             loss = one()
         e1.record()
         sync()
+        mod.stage_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in _ops.TIMING.items()}
+        _ops.TIMING = None
         NS = [s_.N for s_ in mod.last_samples]
         return e0.elapsed_time(e1) / steps, float(loss.detach()), NS, mod
 
@@ -302,7 +306,8 @@ def measure_pooled(dev, rank, world, dist, steps=10, warmup=3):
     if rank == 0:        # the single-GPU reference time of the same batch (the other ranks wait at the barrier below)
         lab, fts = inputs(0, n)
         single_ms, loss1, NS, _m = run(None, lab, fts, torch.cuda.synchronize)
-        out.update(single_gpu_ms_per_step=single_ms, single_gpu_loss=loss1, anchors_per_scale=NS)
+        out.update(single_gpu_ms_per_step=single_ms, single_gpu_loss=loss1, anchors_per_scale=NS,
+                   single_gpu_stage_ms=_m.stage_ms)
         del lab, fts, _m
         torch.cuda.empty_cache()
     if world > 1:
@@ -315,7 +320,7 @@ def measure_pooled(dev, rank, world, dist, steps=10, warmup=3):
         ms = float(t)
         if rank == 0:
             pairs = pairs_per_step(NS, True)
-            out.update(ms_per_step=ms, value=pairs / (ms * 1e-3), unit=UNIT, loss=loss,
+            out.update(ms_per_step=ms, value=pairs / (ms * 1e-3), unit=UNIT, loss=loss, stage_ms_rank0=mod.stage_ms,
                        speedup_vs_single_gpu=single_ms / ms, efficiency=single_ms / ms / world,
                        exchange=mod.last_state.exchange_info if hasattr(mod.last_state, "exchange_info") else None)
     elif rank == 0:

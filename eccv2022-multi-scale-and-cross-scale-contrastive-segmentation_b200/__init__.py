@@ -7,6 +7,8 @@ hand-written sm_100a CUDA (libmscs.so, C ABI in include/mscs.h) behind one autog
 from . import synth  # noqa: F401
 from ._lib import EXPORTS, LIB_PATH, load  # noqa: F401
 from .losses import DenseContrastiveLossV2, DenseContrastiveLossV2_ms, install_into_reference  # noqa: F401
-from ._ops import TorchDistComm, ThreadComm, shard_rows  # noqa: F401
+from ._ops import CompactLabels, TorchDistComm, ThreadComm, shard_rows  # noqa: F401
+from .projector import ProjectorTailContrastive_ms  # noqa: F401
+from .coloss import CrossEntropyLabelPass, FusedCoLosses, label_pass  # noqa: F401
 
 __all__ = ["DenseContrastiveLossV2", "DenseContrastiveLossV2_ms", "install_into_reference", "synth", "load"]

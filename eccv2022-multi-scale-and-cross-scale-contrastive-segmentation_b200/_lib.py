@@ -110,6 +110,13 @@ _SIGNATURES = {
                                        C.c_int, C.c_void_p, C.c_void_p]),
     "mscs_scatter_grad": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "mscs_label_pass": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mscs_sample_hist_i16": (C.c_int, [C.POINTER(SampleCfg), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mscs_sample_plan_i16": (C.c_int, [C.POINTER(SampleCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mscs_ce_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                  C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mscs_ce_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "mscs_gather_rows_raw": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mscs_scatter_rows_raw": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                         C.c_void_p]),
@@ -120,8 +127,8 @@ _SIGNATURES = {
     "mscs_xchg_barrier": (C.c_int, [_PTRS, C.c_int, C.c_int, C.c_uint32, C.c_double, C.c_void_p]),
     "mscs_xchg_push": (C.c_int, [_PTRS, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.c_int,
                                  C.c_void_p]),
-    "mscs_gather_normalize_p2p": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, _PTRS, C.c_int,
-                                            C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mscs_gather_normalize_p2p": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, _PTRS,
+                                            C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mscs_scatter_sectors_pull": (C.c_int, [_PTRS, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
 }

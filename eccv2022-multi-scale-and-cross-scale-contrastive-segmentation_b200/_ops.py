@@ -18,6 +18,14 @@ import torch
 from . import _lib
 
 _MT_N = 624
+# experiment switches, read once at import (nothing on the per-step path calls getenv)
+_NO_PREFETCH = bool(os.environ.get("MSCS_NO_PREFETCH"))      # regenerate the MT19937 stream inline at every call
+_USE_HP_STREAM = os.environ.get("MSCS_HP", "1") != "0"       # sampling kernels on a high-priority stream
+# dense gradients: 1 (default) = ONE streaming pass in the backward (k_dense_stream: zeros and values alike, every byte
+# written once); 0 = zero-fill ahead of time on a side stream (memset) + rewrite of the sampled sectors.  Measured
+# (r02, cfg-2): 1.033-1.041 against 1.050-1.054 ms per step -- the memset costs the sampling and gather stages it
+# overlaps 14 + 45 us, the one-pass writer costs 37 us more than the sector rewrite.
+_DENSE_ONE_PASS = os.environ.get("MSCS_DENSE", "1") != "0"
 
 # optional per-stage device timing (bench.py): {stage: [(start_event, end_event), ...]} or None
 TIMING = None
@@ -135,6 +143,27 @@ class _pin_stream:
         _stream_override[0] = _stream_override[1] = None
 
 
+class CompactLabels:
+    """int16 label map produced by the fused label pass (csrc/ce.cu:k_label_pass; -1 = outside [0, A)): accepted by the
+    loss classes in place of the int64 labels -- K1 then reads a quarter of the bytes, with identical results."""
+    __slots__ = ("lab16", "hist", "shape", "num_classes")
+
+    def __init__(self, lab16, hist, num_classes):
+        self.lab16, self.hist, self.shape, self.num_classes = lab16, hist, tuple(lab16.shape), num_classes
+
+    @property
+    def device(self):
+        return self.lab16.device
+
+
+def _plan_entry(lib, labels, hist_only=False):
+    """(function, name) of the K1 entry point for int64 or compact int16 labels."""
+    i16 = labels.dtype == torch.int16
+    if hist_only:
+        return (lib.mscs_sample_hist_i16, "mscs_sample_hist_i16") if i16 else (lib.mscs_sample_hist, "mscs_sample_hist")
+    return (lib.mscs_sample_plan_i16, "mscs_sample_plan_i16") if i16 else (lib.mscs_sample_plan, "mscs_sample_plan")
+
+
 def _require_device(t):
     if not t.is_cuda:
         raise RuntimeError("mscs_b200 runs on a B200 GPU only: got a CPU tensor (there is no CPU fallback)")
@@ -249,7 +278,7 @@ class _StreamCache:
         return host, newpos
 
     def release_and_prefetch(self, mt_next, pos_next, words):
-        if os.environ.get("MSCS_NO_PREFETCH"):      # experiment switch: regenerate inline at the next call
+        if _NO_PREFETCH:      # experiment switch: regenerate inline at the next call
             return
         with self.lock:
             ev = torch.cuda.Event()
@@ -274,7 +303,7 @@ def sample_anchors(labels, feat_hw, spec, mt_state=None, defer_rng=False):
     torch CPU default generator exactly as the reference does, or an explicit (uint32[624], pos)."""
     lib = _lib.load()
     _require_device(labels)
-    if labels.dtype != torch.int64:
+    if labels.dtype not in (torch.int64, torch.int16):
         labels = labels.long()
     labels = labels.contiguous()
     n, H, W = labels.shape
@@ -292,8 +321,8 @@ def sample_anchors(labels, feat_hw, spec, mt_state=None, defer_rng=False):
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     plan_dev = torch.empty(S * C.sizeof(_lib.ScalePlan), dtype=torch.uint8, device=dev)
     st = _stream()
-    _lib.check(lib.mscs_sample_plan(C.byref(cfg), labels.data_ptr(), ws.data_ptr(), plan_dev.data_ptr(), st),
-               "mscs_sample_plan")
+    fn, fname = _plan_entry(lib, labels)
+    _lib.check(fn(C.byref(cfg), labels.data_ptr(), ws.data_ptr(), plan_dev.data_ptr(), st), fname)
     plan = (_lib.ScalePlan * S)()
     _lib.check(lib.mscs_plan_fetch(plan_dev.data_ptr(), plan, S, st), "mscs_plan_fetch")
     for s in range(S):
@@ -950,7 +979,7 @@ def _run_forward_fast(sp, labels, feats32, needs, philox=None):
         job.term_loss, job.total_loss = out.data_ptr(), out.data_ptr() + 4 * nt
         job.total_out = total_t.data_ptr()
     # the small, latency-bound sampling kernels run on a high-priority stream (see _hp_stream)
-    hp = _hp_stream(dev) if os.environ.get("MSCS_HP", "1") != "0" else None
+    hp = _hp_stream(dev) if _USE_HP_STREAM else None
     st_s = st
     if hp is not None:
         hp.wait_stream(cur)
@@ -971,19 +1000,20 @@ def _run_forward_fast(sp, labels, feats32, needs, philox=None):
                                               st_s), "mscs_philox_stream")
         _t = _seg("fwd: rng state + stream acquire", _t)
         # dense gradients + gradient rows: pre-zeroed on a side stream, sampled sectors rewritten by the backward
-        # (MSCS_DENSE=1: the backward writes them in one streaming pass instead -- measured equal, see gather.cu).
+        # (default: the backward writes them in one streaming pass instead, see _DENSE_ONE_PASS and gather.cu).
         # Started here, next to the small sampling kernels: the fill (535 MB at cfg-2) costs ~70 us of step time
         # WHEREVER it runs (measured next to the sampling kernels, under the forward, under the backward, and as a
         # device-to-device copy from a persistent zero buffer) -- memset and D2D copies run on the SMs.
         gradbufs = _GradBuffers(feats32, needs, sp.nhwc, sp.dF_n) \
-            if (any(needs) and (sp.nhwc or os.environ.get("MSCS_DENSE") != "1")) else None
+            if (any(needs) and (sp.nhwc or not _DENSE_ONE_PASS)) else None
         if gradbufs is not None:
             gradbufs.start_fill()
         _t = _seg("fwd: grad buffers", _t)
         # workspace fills, then hist -> tile scan -> plan -> select back to back (programmatic dependent launches);
         # the plan records travel to the host on a private stream (mscs_plan_fetch_begin)
         _lib.check(lib.mscs_fill_bytes(e.fill_ptrs, e.fill_vals, e.fill_bytes, 2, st_s), "mscs_fill_bytes")
-        _lib.check(lib.mscs_sample_plan(C.byref(sp.cfg), labels.data_ptr(), e.ws, e.plan_dev, st_s), "mscs_sample_plan")
+        fn, fname = _plan_entry(lib, labels)
+        _lib.check(fn(C.byref(sp.cfg), labels.data_ptr(), e.ws, e.plan_dev, st_s), fname)
         _lib.check(lib.mscs_plan_fetch_begin(e.plan_dev, S, st_s), "mscs_plan_fetch_begin")
         _lib.check(lib.mscs_sample_select_async(C.byref(sp.cfg), e.plan_dev, sp.v_cap, e.ws, draws_ptr, *e.arrs,
                                                 e.sarr, st_s), "mscs_sample_select_async")
@@ -1037,8 +1067,8 @@ def _run_forward_general(sp, labels, feats32, needs):
     ws = torch.empty(sp.ws_bytes, dtype=u8, device=dev)
     plan_dev = torch.empty(S * C.sizeof(_lib.ScalePlan), dtype=u8, device=dev)
     with _timed("sample"):
-        _lib.check(lib.mscs_sample_plan(C.byref(sp.cfg), labels.data_ptr(), ws.data_ptr(), plan_dev.data_ptr(), st),
-                   "mscs_sample_plan")
+        fn, fname = _plan_entry(lib, labels)
+        _lib.check(fn(C.byref(sp.cfg), labels.data_ptr(), ws.data_ptr(), plan_dev.data_ptr(), st), fname)
         sizes = sp.slot_sizes
         islab = torch.empty(sp.islab_n, dtype=i32, device=dev)
         fslab = torch.empty(sp.fslab_n, dtype=f32, device=dev)
@@ -1135,7 +1165,8 @@ def _run_forward_pooled(sp, labels, feats32, needs, comm):
     plan_dev = torch.empty(S * C.sizeof(_lib.ScalePlan), dtype=u8, device=dev)
     with _timed("sample"):
         # local histograms -> all-gather of the (image, class) counts -> identical global plan on every rank
-        _lib.check(lib.mscs_sample_hist(C.byref(sp.cfg), labels.data_ptr(), ws.data_ptr(), st), "mscs_sample_hist")
+        fn, fname = _plan_entry(lib, labels, hist_only=True)
+        _lib.check(fn(C.byref(sp.cfg), labels.data_ptr(), ws.data_ptr(), st), fname)
         nA = sp.n_local * A
         local = torch.cat([ws[sp.counts_off[s]:sp.counts_off[s] + 4 * nA].view(i32) for s in range(S)])
         gathered = comm.all_gather(local).view(world, S, nA)
@@ -1153,11 +1184,11 @@ def _run_forward_pooled(sp, labels, feats32, needs, comm):
         for x in sizes:
             slots.append(slot_slab[off:off + x])
             off += x
-        # dense gradients (local) and this parity's gradient rows in the slab: zero-filled on the side stream;
-        # this parity's row statistics: zeroed here, i.e. before this rank's barrier A, hence before any peer's push
+        # dense gradients (local): zero-filled on the side stream; this parity's row statistics: zeroed here, i.e.
+        # before this rank's barrier A, hence before any peer's push
         gradbufs = _GradBuffers(feats32, needs, False, 0) if any(needs) else None
         if gradbufs is not None:
-            gradbufs.start_fill(extra=(xs.local + xo["dF"], 4 * sp.dF_n))
+            gradbufs.start_fill()
         _lib.check(lib.mscs_fill_bytes(_lib.ptr_array([xs.local + xo["stats"]]), (C.c_int32 * 1)(0),
                                        (C.c_size_t * 1)(4 * sp.stats_n), 1, st), "mscs_fill_bytes")
         mt, pos = torch_mt_state()
@@ -1174,22 +1205,46 @@ def _run_forward_pooled(sp, labels, feats32, needs, comm):
         job.term_loss, job.total_loss = mbase + 4 * sp.out_off, mbase + 4 * (sp.out_off + nt)
         total_t = torch.empty((), dtype=f32, device=dev)      # own buffer, not a view (see _run_forward_fast)
         job.total_out = total_t.data_ptr()
-        _lib.check(lib.mscs_plan_fetch(plan_dev.data_ptr(), plan, S, st), "mscs_plan_fetch")     # the host sync
-        _raise_plan_errors(plan, S, spec)
-        total = sum(int(plan[s].draws) for s in range(S))
-        _lib.check(lib.mscs_sample_select(C.byref(sp.cfg), plan, ws.data_ptr(), draws.data_ptr(), *arrs, sarr, st),
-                   "mscs_sample_select")
-    samples = [ScaleSample(plan[s].T, plan[s].V, plan[s].N, bool(plan[s].log_flag), plan[s].dl_h, plan[s].dl_w,
-                           islab, sp.ioff[s], A) for s in range(S)]
-    sent = 0
+        # Selection and the peer-store gather are driven by the DEVICE plan records and enqueued before the host looks
+        # at the plan: the one host wait of the forward (errors, row ranges) overlaps them instead of idling the GPU.
+        device_driven = sp.v_cap * 12 <= 200 * 1024
+        plan_sz = C.sizeof(_lib.ScalePlan)
+        if device_driven:
+            _lib.check(lib.mscs_plan_fetch_begin(plan_dev.data_ptr(), S, st), "mscs_plan_fetch_begin")
+            _lib.check(lib.mscs_sample_select_async(C.byref(sp.cfg), plan_dev.data_ptr(), sp.v_cap, ws.data_ptr(),
+                                                    draws.data_ptr(), *arrs, sarr, st), "mscs_sample_select_async")
+        else:
+            _lib.check(lib.mscs_plan_fetch(plan_dev.data_ptr(), plan, S, st), "mscs_plan_fetch")     # the host sync
+            _raise_plan_errors(plan, S, spec)
+            _lib.check(lib.mscs_sample_select(C.byref(sp.cfg), plan, ws.data_ptr(), draws.data_ptr(), *arrs, sarr, st),
+                       "mscs_sample_select")
     with _timed("gather"):
         for s in range(S):
             n, Cc, h, w = sp.feat_shapes[s]
-            _lib.check(lib.mscs_gather_normalize_p2p(feats32[s].data_ptr(), n, Cc, h * w, slots[s].data_ptr(),
-                                                     samples[s].N, xs.peers, world, rank, xo["b"] + 2 * sp.boff[s],
-                                                     fbase + 4 * sp.foff[s][0], fbase + 4 * sp.foff[s][1], st),
-                       "mscs_gather_normalize_p2p")
+            _lib.check(lib.mscs_gather_normalize_p2p(
+                feats32[s].data_ptr(), n, Cc, h * w, slots[s].data_ptr(), 0 if device_driven else plan[s].N,
+                plan_dev.data_ptr() + s * plan_sz + 8 if device_driven else None, xs.peers, world, rank,
+                xo["b"] + 2 * sp.boff[s], fbase + 4 * sp.foff[s][0], fbase + 4 * sp.foff[s][1], st),
+                "mscs_gather_normalize_p2p")
         comm.barrier(xs)                                   # A: every rank's key rows have landed here
+    if device_driven:
+        _lib.check(lib.mscs_plan_fetch_end(plan, S), "mscs_plan_fetch_end")       # the host wait (plan records only)
+        _raise_plan_errors(plan, S, spec)
+    total = sum(int(plan[s].draws) for s in range(S))
+    samples = [ScaleSample(plan[s].T, plan[s].V, plan[s].N, bool(plan[s].log_flag), plan[s].dl_h, plan[s].dl_w,
+                           islab, sp.ioff[s], A) for s in range(S)]
+    # this parity's gradient rows: only the 128-aligned row blocks this rank computes are accumulated into (and
+    # pulled from): clear those (1/world of the slab), on the main stream, long before the backward
+    if any(needs):
+        zp, zb = [], []
+        for s in range(S):
+            rb, re_ = shard_rows(samples[s].N, world, rank)
+            if re_ > rb:
+                zp.append(xs.local + xo["dF"] + 4 * (sp.dF_off[s] + rb * sp.C_pad))
+                zb.append(4 * ((re_ + 127) // 128 * 128 - rb) * sp.C_pad)
+        if zp:
+            _lib.check(lib.mscs_fill_bytes(_lib.ptr_array(zp), (C.c_int32 * len(zp))(*([0] * len(zp))),
+                                           (C.c_size_t * len(zb))(*zb), len(zp), st), "mscs_fill_bytes")
     push_off, push_len = [], []
     for i, (a, k, *_rest) in enumerate(sp.terms):      # the plan-dependent fields of the job
         t = job.terms[i]
@@ -1418,7 +1473,7 @@ class MsCsContrastiveFn(torch.autograd.Function):
         if labels.device != feats32[0].device:
             labels = labels.to(feats32[0].device)
         needs = [bool(ctx.needs_input_grad[4 + i]) for i in range(len(feats))]
-        if labels.dtype != torch.int64:
+        if labels.dtype not in (torch.int64, torch.int16):     # int16: compact labels of the fused label pass
             labels = labels.long()
         labels = labels.contiguous()
         with torch.cuda.device(feats32[0].device), _pin_stream():

@@ -6,6 +6,7 @@
 // HBM-bound byte movers: NCHW means one anchor is C scalars `plane` floats apart (one 32 B
 // sector per useful 4 B), so one warp owns one anchor and keeps 8 independent loads in flight.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace mscs {
 
@@ -439,6 +440,42 @@ __global__ void __launch_bounds__(256) k_scatter_rows_nhwc(const __grid_constant
   }
 }
 
+// One-pass dense writer, second form (round 2): a thread OWNS 4 consecutive pixels and walks the channel planes.
+// Its four slot entries are fetched once (one coalesced int4), so the sampled / not-sampled decision is loop
+// invariant: 97 % of the threads run a pure store loop, the others add up to four independent (predicated) loads of
+// dx[row][c] per channel.  A block writes 2 KB contiguous per channel plane (512 pixels), i.e. whole DRAM pages in
+// linear order per plane -- the order of the memset it replaces, without its second pass over the sampled sectors.
+struct DenseStream {
+  const float* dx[MSCS_MAX_SCALES]; const int* slot[MSCS_MAX_SCALES]; float* dfeat[MSCS_MAX_SCALES];
+  int ld[MSCS_MAX_SCALES], C[MSCS_MAX_SCALES], plane[MSCS_MAX_SCALES], npix[MSCS_MAX_SCALES], blk0[MSCS_MAX_SCALES + 1];
+  int count;
+};
+__global__ void __launch_bounds__(128) k_dense_stream(const __grid_constant__ DenseStream g) {
+  int s = 0;
+  while (s + 1 < g.count && (int)blockIdx.x >= g.blk0[s + 1]) ++s;
+  const int lin = (((int)blockIdx.x - g.blk0[s]) * 128 + (int)threadIdx.x) * 4;
+  if (lin >= g.npix[s]) return;
+  const int plane = g.plane[s], C = g.C[s], ld = g.ld[s];
+  const int4 sl = *reinterpret_cast<const int4*>(g.slot[s] + lin);
+  const int b = lin / plane, p = lin - b * plane;
+  float* __restrict__ out = g.dfeat[s] + ((size_t)b * C) * plane + p;
+  const float* __restrict__ dx = g.dx[s];
+  const float* r0 = dx + (size_t)max(sl.x, 0) * ld;
+  const float* r1 = dx + (size_t)max(sl.y, 0) * ld;
+  const float* r2 = dx + (size_t)max(sl.z, 0) * ld;
+  const float* r3 = dx + (size_t)max(sl.w, 0) * ld;
+  const bool h0 = sl.x >= 0, h1 = sl.y >= 0, h2 = sl.z >= 0, h3 = sl.w >= 0;
+#pragma unroll 8
+  for (int c = 0; c < C; ++c) {
+    float4 v;
+    v.x = h0 ? __ldg(r0 + c) : 0.f;
+    v.y = h1 ? __ldg(r1 + c) : 0.f;
+    v.z = h2 ? __ldg(r2 + c) : 0.f;
+    v.w = h3 ? __ldg(r3 + c) : 0.f;
+    __stcs(reinterpret_cast<float4*>(out + (size_t)c * plane), v);
+  }
+}
+
 }  // namespace mscs
 
 using namespace mscs;
@@ -560,6 +597,8 @@ extern "C" int mscs_gather_normalize_sectors_batch(const mscs_gather_item* items
     g.feat[s] = it.feat; g.slot[s] = it.slot; g.n_rows_dev[s] = it.n_rows_dev;
     g.bf16[s] = (__nv_bfloat16*)it.anc_bf16; g.f32[s] = it.anc_f32; g.inv[s] = it.inv_norm;
     g.C[s] = it.C; g.plane[s] = it.plane; g.n_oct[s] = it.n * (it.plane / 8);
+  }
+  for (int s = 0; s < count; ++s) {
     g.block0[s] = blocks;
     blocks += ceil_div(g.n_oct[s], 8) + 1;      // + the block that zeroes the padding rows
   }
@@ -654,9 +693,27 @@ extern "C" int mscs_scatter_dense_batch(const mscs_scatter_item* items, const in
   }
   g.v4_0[count] = v4; g.rowblk0[count] = rb; g.maskblk0[count] = mblk;
   cudaStream_t st = (cudaStream_t)stream_;
-  k_dx_rows<<<rb + mblk, 256, 0, st>>>(g);
+  static const int writer = [] { const char* e = getenv("MSCS_DENSE_WRITER"); return e ? atoi(e) : 1; }();
+  if (writer == 0) {      // first form (round 1): linear float4 walk with a pixel mask
+    k_dx_rows<<<rb + mblk, 256, 0, st>>>(g);
+    MSCS_LAUNCH_CHECK();
+    k_dense_write<<<(unsigned)v4, 256, 0, st>>>(g);
+    MSCS_LAUNCH_CHECK();
+    return 0;
+  }
+  g.maskblk0[count] = 0;      // no mask blocks: k_dx_rows only turns the gradient rows into dx rows
+  k_dx_rows<<<rb > 0 ? rb : 1, 256, 0, st>>>(g);
   MSCS_LAUNCH_CHECK();
-  k_dense_write<<<(unsigned)v4, 256, 0, st>>>(g);
+  DenseStream d{};
+  d.count = count;
+  int blk = 0;
+  for (int s = 0; s < count; ++s) {
+    d.dx[s] = g.dF[s]; d.slot[s] = g.slot[s]; d.dfeat[s] = g.dfeat[s]; d.ld[s] = g.ldF[s]; d.C[s] = g.C[s];
+    d.plane[s] = g.plane[s]; d.npix[s] = g.n[s] * g.plane[s]; d.blk0[s] = blk;
+    blk += ceil_div(d.npix[s], 512);
+  }
+  d.blk0[count] = blk;
+  k_dense_stream<<<blk, 128, 0, st>>>(d);
   MSCS_LAUNCH_CHECK();
   return 0;
 }

@@ -109,8 +109,11 @@ __device__ __forceinline__ int nearest_src(int dst, float scale, int in_size, in
   return min(src, in_size - 1);
 }
 
+// LabT = long long: the reference's int64 label map; LabT = short: the compact labels of the fused label pass
+// (ce.cu:k_label_pass, -1 = outside [0, A)) -- same results, a quarter of the bytes
+template <typename LabT>
 __global__ void __launch_bounds__(256)
-k_label_hist(const __grid_constant__ SampleLayout L, const long long* __restrict__ labels, char* ws) {
+k_label_hist(const __grid_constant__ SampleLayout L, const LabT* __restrict__ labels, char* ws) {
   extern __shared__ int hist[];
   pdl_trigger();
   int t = blockIdx.x;
@@ -123,7 +126,7 @@ k_label_hist(const __grid_constant__ SampleLayout L, const long long* __restrict
   for (int c = threadIdx.x; c < L.A; c += blockDim.x) hist[c] = 0;
   __syncthreads();
   short* dlab = reinterpret_cast<short*>(ws + g.off_dlab) + (size_t)b * g.hw;
-  const long long* lab = labels + (size_t)b * L.H * L.W;
+  const LabT* lab = labels + (size_t)b * L.H * L.W;
 #pragma unroll
   for (int i = 0; i < kTile / 256; ++i) {
     int p = tile * kTile + i * 256 + threadIdx.x;
@@ -131,7 +134,7 @@ k_label_hist(const __grid_constant__ SampleLayout L, const long long* __restrict
       int y = p / g.dl_w, x = p - y * g.dl_w;
       int sy = nearest_src(y, g.sy, L.H, g.ident_y);
       int sx = nearest_src(x, g.sx, L.W, g.ident_x);
-      long long v = lab[(size_t)sy * L.W + sx];
+      long long v = (long long)lab[(size_t)sy * L.W + sx];
       // the reference converts label -> float32 -> int64 (V2.py:205-206)
       float f = (float)v;
       long long c = (long long)f;
@@ -491,7 +494,7 @@ extern "C" size_t mscs_sample_counts_offset(const mscs_sample_cfg* cfg, int scal
   return L.g[scale].off_counts;
 }
 
-extern "C" int mscs_sample_hist(const mscs_sample_cfg* cfg, const int64_t* labels, void* workspace, void* stream_) {
+static int sample_hist_any(const mscs_sample_cfg* cfg, const void* labels, bool compact, void* workspace, void* stream_) {
   SampleLayout L;
   int rc = make_layout(cfg, &L);
   if (rc) return rc;
@@ -499,12 +502,20 @@ extern "C" int mscs_sample_hist(const mscs_sample_cfg* cfg, const int64_t* label
   cudaStream_t st = (cudaStream_t)stream_;
   char* ws = (char*)workspace;
   MSCS_CUDA(cudaMemsetAsync(ws + L.counts_begin, 0, L.counts_bytes, st));
-  k_label_hist<<<L.total_tiles, 256, sizeof(int) * L.A, st>>>(L, (const long long*)labels, ws);
+  if (compact) k_label_hist<short><<<L.total_tiles, 256, sizeof(int) * L.A, st>>>(L, (const short*)labels, ws);
+  else k_label_hist<long long><<<L.total_tiles, 256, sizeof(int) * L.A, st>>>(L, (const long long*)labels, ws);
   MSCS_LAUNCH_CHECK();
   dim3 gs(ceil_div(L.n * L.A, 128), L.S);
   MSCS_CUDA(launch_k(k_tile_scan, gs, 128, 0, st, L, ws));
   MSCS_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int mscs_sample_hist(const mscs_sample_cfg* cfg, const int64_t* labels, void* workspace, void* stream_) {
+  return sample_hist_any(cfg, labels, false, workspace, stream_);
+}
+extern "C" int mscs_sample_hist_i16(const mscs_sample_cfg* cfg, const int16_t* lab16, void* workspace, void* stream_) {
+  return sample_hist_any(cfg, lab16, true, workspace, stream_);
 }
 
 extern "C" int mscs_sample_plan_from_counts(const mscs_sample_cfg* cfg, const int32_t* const* counts_global,
@@ -525,6 +536,12 @@ extern "C" int mscs_sample_plan_from_counts(const mscs_sample_cfg* cfg, const in
 extern "C" int mscs_sample_plan(const mscs_sample_cfg* cfg, const int64_t* labels, void* workspace,
                                 mscs_scale_plan* plan_dev, void* stream_) {
   int rc = mscs_sample_hist(cfg, labels, workspace, stream_);
+  if (rc) return rc;
+  return mscs_sample_plan_from_counts(cfg, nullptr, workspace, plan_dev, stream_);
+}
+extern "C" int mscs_sample_plan_i16(const mscs_sample_cfg* cfg, const int16_t* lab16, void* workspace,
+                                    mscs_scale_plan* plan_dev, void* stream_) {
+  int rc = mscs_sample_hist_i16(cfg, lab16, workspace, stream_);
   if (rc) return rc;
   return mscs_sample_plan_from_counts(cfg, nullptr, workspace, plan_dev, stream_);
 }

@@ -77,11 +77,12 @@ struct GatherP2P {
   PeerPtrs bf16;            // the operand matrix of this scale in every rank's slab (same sorted row index everywhere)
   int C, C_pad, plane, n_octets, rank;
   int n_rows;               // N: the local padding rows [N, N_pad) are zeroed by the extra last block
+  const int* n_rows_dev;    // optional: N lives in device memory (the launch then does not wait for the host)
 };
 __global__ void __launch_bounds__(256) k_gather_p2p(const __grid_constant__ GatherP2P g) {
   const int lane = threadIdx.x & 31;
   if (blockIdx.x == gridDim.x - 1) {      // padding rows of the LOCAL matrix (the TMA tiles read them)
-    const int N = g.n_rows, N_pad = (N + 255) / 256 * 256;
+    const int N = g.n_rows_dev ? *g.n_rows_dev : g.n_rows, N_pad = (N + 255) / 256 * 256;
     uint32_t* z = reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(g.bf16.p[g.rank]) + (size_t)N * g.C_pad);
     for (int i = threadIdx.x; i < (N_pad - N) * (g.C_pad / 2); i += blockDim.x) z[i] = 0u;
     return;
@@ -200,15 +201,15 @@ extern "C" int mscs_xchg_push(void* const* slabs, int world, int rank, const int
 }
 
 extern "C" int mscs_gather_normalize_p2p(const float* feat, int n, int C, int plane, const int32_t* slot, int N,
-                                         void* const* slabs, int world, int rank, size_t bf16_byte_off,
-                                         float* anc_f32, float* inv_norm, void* stream_) {
+                                         const int32_t* n_rows_dev, void* const* slabs, int world, int rank,
+                                         size_t bf16_byte_off, float* anc_f32, float* inv_norm, void* stream_) {
   MSCS_CHECK_ARG(feat && slot && anc_f32 && inv_norm, "null pointer argument");
   MSCS_CHECK_ARG(C >= 1 && C <= kMaxC && plane % 8 == 0 && n >= 1 && N >= 0, "unsupported shape (C %d, plane %d)", C, plane);
   MSCS_CHECK_ARG(rank >= 0 && rank < world && bf16_byte_off % 16 == 0, "bad rank / offset");
   GatherP2P g{};
   if (int rc = fill_peers(&g.bf16, slabs, world, bf16_byte_off)) return rc;
   g.feat = feat; g.slot = slot; g.anc_f32 = anc_f32; g.inv_norm = inv_norm;
-  g.C = C; g.C_pad = (C + 63) / 64 * 64; g.plane = plane; g.n_octets = n * plane / 8; g.rank = rank; g.n_rows = N;
+  g.C = C; g.C_pad = (C + 63) / 64 * 64; g.plane = plane; g.n_octets = n * plane / 8; g.rank = rank; g.n_rows = N; g.n_rows_dev = n_rows_dev;
   k_gather_p2p<<<ceil_div(g.n_octets, 8) + 1, 256, 0, (cudaStream_t)stream_>>>(g);
   MSCS_LAUNCH_CHECK();
   return 0;

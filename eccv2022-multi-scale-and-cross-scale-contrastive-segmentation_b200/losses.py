@@ -14,7 +14,7 @@ import sys
 import torch
 import torch.nn as nn
 
-from ._ops import LossSpec, MsCsContrastiveFn
+from ._ops import CompactLabels, LossSpec, MsCsContrastiveFn
 from .datasets import class_facts
 
 
@@ -81,6 +81,8 @@ class DenseContrastiveLossV2(nn.Module):
         self._sampler_calls = 0
 
     def forward(self, label: torch.Tensor, features: torch.Tensor):
+        if isinstance(label, CompactLabels):           # labels of the fused label pass (coloss.py): same results
+            label = label.lab16
         holder = {}
         _philox_key(self, holder)
         self._spec.num_classes = self.num_all_classes          # the reference lets callers override it (V2.py:238)
@@ -134,6 +136,8 @@ class DenseContrastiveLossV2_ms(nn.Module):
         self._sampler_calls = 0
 
     def forward(self, label: torch.Tensor, features: list, **kwargs):
+        if isinstance(label, CompactLabels):           # labels of the fused label pass (coloss.py): same results
+            label = label.lab16
         self.cs_losses, self.ms_losses = [], []
         feats = list(features[:self.scales])
         if len(feats) < self.scales:

@@ -291,6 +291,32 @@ int mscs_scatter_dense_batch(const mscs_scatter_item* items, const int32_t* rows
                              void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Co-loss on the same label read.  The reference's LossWrapper evaluates a class-weighted
+ * nn.CrossEntropyLoss(ignore_index, weight) on the full-resolution logits next to the contrastive loss
+ * (losses/LossWrapper.py:22-31,81-82; TwoScaleLoss.py:62-73 applies it to two logit maps); both start from the int64
+ * label map.
+ *   mscs_label_pass    ONE sweep over the labels: compact int16 labels (-1 = outside [0, num_classes)) + the
+ *                      full-resolution class histogram int32[num_classes] (zeroed inside).  The compact labels feed K1
+ *                      (mscs_sample_hist_i16 / mscs_sample_plan_i16: same results as the int64 entry points) and the
+ *                      CE kernels; the histogram gives the CE normaliser sum_valid w[y] before the logits are read.
+ *   mscs_ce_forward    loss_and_denom[0] = sum_valid w[y] (logsumexp(x) - x_y) / denom,  [1] = denom = sum_c w[c] hist[c]
+ *                      (c < K, c != ignore_index); logits fp32 NCHW (n, K, plane), plane % 4 == 0; weight NULL = ones;
+ *                      labels >= K or == ignore_index are ignored; loss_sum_scratch: one double of device scratch.
+ *   mscs_ce_backward   dlogits = (*grad_out / *denom) w[y] (softmax(x) - onehot(y)), zeros on ignored pixels: one fused
+ *                      pass (ATen: log_softmax backward + nll_loss backward).
+ * ------------------------------------------------------------------------------------- */
+int mscs_label_pass(const int64_t* labels, int64_t n_pixels, int num_classes, int16_t* lab16, int32_t* hist,
+                    void* stream);
+int mscs_sample_hist_i16(const mscs_sample_cfg* cfg, const int16_t* lab16, void* workspace, void* stream);
+int mscs_sample_plan_i16(const mscs_sample_cfg* cfg, const int16_t* lab16, void* workspace, mscs_scale_plan* plan_dev,
+                         void* stream);
+int mscs_ce_forward(const float* logits, const int16_t* lab16, int n, int K, int plane, const float* weight,
+                    int ignore_index, const int32_t* hist, int num_classes, double* loss_sum_scratch,
+                    float* loss_and_denom, void* stream);
+int mscs_ce_backward(const float* logits, const int16_t* lab16, int n, int K, int plane, const float* weight,
+                     int ignore_index, const float* grad_out, const float* denom, float* dlogits, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Projector tail on the sampled rows only (models/Projector.py:49-72: the projector ends in
  * nn.Conv2d(c_prev, d, kernel_size=1), evaluated densely by the reference although the loss reads <= 10k pixels per
  * scale).  The 1x1 convolution of the sampled pixels is a plain (N x c_in) x (c_in x d) GEMM on the host side's
@@ -328,6 +354,7 @@ int mscs_xchg_push(void* const* slabs, int world, int rank, const int64_t* float
  * is stored into the operand matrix at byte offset bf16_byte_off of EVERY rank's slab (same sorted row everywhere: the
  * plan is global); fp32 rows and inverse norms stay local.  Also zeroes the local padding rows [N, N_pad). */
 int mscs_gather_normalize_p2p(const float* feat, int n, int C, int plane, const int32_t* slot, int N,
+                              const int32_t* n_rows_dev /* optional: N read on the device, e.g. &plan_dev[s].N */,
                               void* const* slabs, int world, int rank, size_t bf16_byte_off, float* anc_f32,
                               float* inv_norm, void* stream);
 /* as mscs_scatter_sectors, with gradient row i read from rank (i / rows_per_rank)'s slab at dF_byte_off (the rank

@@ -1,6 +1,7 @@
-"""CPU: the JSON-line contract of bench.py.  The reference arm (`--impl reference`: the reference's algorithm on the
-host cores, oracle/torch_port.py) runs here for one bounded step; the main arm needs a B200, so its contract is checked
-on the line committed under profiles/ (written by the same bench.py on the GPU box)."""
+"""CPU: the JSON-line contract of bench.py.  The reference arm (`--impl reference`: the reference's own loss files on
+the host cores -- oracle/_ref or /root/reference, else the torch port of the oracle) runs here for one bounded step; the
+main arm needs a B200, so its contract is checked on the line committed under profiles/ (written by the same bench.py
+on the GPU box)."""
 import json
 import os
 import subprocess
@@ -27,8 +28,12 @@ def test_reference_arm_line():
     assert d["impl"] == "reference" and d["unit"] == "anchor-pairs/s" and d["higher_is_better"] is True
     assert d["config"]["workload"].startswith("cfg2: HRNet-W48 Cityscapes")
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == os.cpu_count() and cb["value"] == d["value"] > 0
+    from oracle import ref_loader
+    assert cb["kind"] == ("reference" if ref_loader.find_root() else "port")
+    assert cb["cores"] == os.cpu_count() and cb["value"] == d["value"] > 0
     assert "images of the cfg2 inputs" in cb["sample"]
+    assert d["steps"] == 1 and d["warmup"] == 0          # exactly what was asked for, on a sample sized to the budget
+    assert set(d["config"]) == {"workload", "layout", "per_gpu_batch", "l2", "parallelism"}
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and d["vs_baseline"] is None
     # rank != 0 of a torchrun launch exits 0 without work or output
