@@ -26,6 +26,10 @@ _USE_HP_STREAM = os.environ.get("MSCS_HP", "1") != "0"       # sampling kernels 
 # (r02, cfg-2): 1.033-1.041 against 1.050-1.054 ms per step -- the memset costs the sampling and gather stages it
 # overlaps 14 + 45 us, the one-pass writer costs 37 us more than the sector rewrite.
 _DENSE_ONE_PASS = os.environ.get("MSCS_DENSE", "1") != "0"
+# K2 through bulk-tensor copies (MSCS_GATHER=tma) instead of strided lane loads: measured SLOWER at cfg-2 (0.137 against
+# 0.094 ms, r02: a box of {8 pixels x 256 channels} is 256 rows of 32 bytes, which the TMA unit streams at ~0.2 rows per
+# clock and SM), so the lane-load kernel stays the default
+_GATHER_TMA = os.environ.get("MSCS_GATHER", "lanes") == "tma"
 
 # optional per-stage device timing (bench.py): {stage: [(start_event, end_event), ...]} or None
 TIMING = None
@@ -1026,7 +1030,11 @@ def _run_forward_fast(sp, labels, feats32, needs, philox=None):
         if sp.nhwc:
             _lib.check(lib.mscs_gather_rows_nhwc_batch(e.gitems, S, st), "mscs_gather_rows_nhwc_batch")
         else:
-            _lib.check(lib.mscs_gather_normalize_sectors_batch(e.gitems, S, st), "mscs_gather_normalize_sectors_batch")
+            if _GATHER_TMA:
+                _lib.check(lib.mscs_gather_normalize_tma_batch(e.gitems, S, st), "mscs_gather_normalize_tma_batch")
+            else:
+                _lib.check(lib.mscs_gather_normalize_sectors_batch(e.gitems, S, st),
+                           "mscs_gather_normalize_sectors_batch")
     with _timed("sim_fwd"):
         _lib.check(lib.mscs_sim_forward(C.byref(e.job_fwd), st), "mscs_sim_forward")
     _t = _seg("fwd: select + gather + sim_forward", _t)

@@ -5,7 +5,7 @@
 //             a dense zero (n,C,h,w) gradient at the sampled pixels.
 // HBM-bound byte movers: NCHW means one anchor is C scalars `plane` floats apart (one 32 B
 // sector per useful 4 B), so one warp owns one anchor and keeps 8 independent loads in flight.
-#include "common.cuh"
+#include "sim_tc.cuh"
 #include <stdlib.h>
 
 namespace mscs {
@@ -169,6 +169,117 @@ __global__ void __launch_bounds__(256) k_gather_sectors_batch(const __grid_const
   gather_sectors_body(blockIdx.x - g.block0[s], g.block0[s + 1] - g.block0[s], g.feat[s], g.C[s],
                       (g.C[s] + 63) / 64 * 64, g.plane[s], g.slot[s], g.n_oct[s], g.bf16[s], g.f32[s], g.inv[s],
                       g.n_rows_dev[s]);
+}
+
+// ---------------------------------------------------------------------------------------
+// Gather through TMA (round 2; opt-in, MSCS_GATHER=tma -- measured slower than the octet kernel: 0.137 against 0.094 ms
+// at cfg-2, the TMA unit handles the 256 32-byte rows of a box at ~0.2 rows per clock and SM).  The octet kernel above issues, per sampled pixel, 8 load instructions whose 32 lanes
+// hit 32 different channel planes: 256 L1 wavefronts per pixel -- the LSU, not DRAM, bounds it (93 us at cfg-2 with the
+// stream to itself, 2.9 TB/s of sector traffic).  Here the strided walk over the channel planes is ONE bulk-tensor
+// copy per 8-pixel octet: the feature map is described as a 2D tensor [n*C rows][plane columns] and a box of
+// {8 pixels, C rows} (C x 32 bytes, exactly the sectors the octet kernel touches) lands in shared memory as
+// tile[c][8 px]; the lanes then read 32-byte rows of it (two 128-bit loads per channel) and hold all eight pixels of
+// their channels in registers.  Block = 4 warps; a block first compacts the octets of its 1024-pixel chunk of the slot
+// map that hold a sampled pixel, then every warp streams its share through two tile slots (the copy of the next octet
+// is in flight while the current one is normalised and stored).
+// ---------------------------------------------------------------------------------------
+constexpr int kTmaOctets = 128;      // octets per block chunk (1024 pixels)
+struct GatherTma {
+  alignas(64) CUtensorMap map[MSCS_MAX_SCALES];
+  const int* slot[MSCS_MAX_SCALES]; const int* n_rows_dev[MSCS_MAX_SCALES];
+  __nv_bfloat16* bf16[MSCS_MAX_SCALES]; float* f32[MSCS_MAX_SCALES]; float* inv[MSCS_MAX_SCALES];
+  int C[MSCS_MAX_SCALES], plane[MSCS_MAX_SCALES], n_oct[MSCS_MAX_SCALES], block0[MSCS_MAX_SCALES + 1];
+  int count;
+};
+__global__ void __launch_bounds__(128) k_gather_tma_batch(const __grid_constant__ GatherTma g) {
+  extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  float* tiles = reinterpret_cast<float*>(smem);                       // [4 warps][2 slots][kMaxC][8]
+  int* l_oct = reinterpret_cast<int*>(smem + 4 * 2 * kMaxC * 32);     // compacted octets of the chunk
+  uint64_t* bars = reinterpret_cast<uint64_t*>(l_oct + kTmaOctets);   // [4 warps][2 slots]
+  int* cnt = reinterpret_cast<int*>(bars + 8);
+  int s = 0;
+  while (s + 1 < g.count && (int)blockIdx.x >= g.block0[s + 1]) ++s;
+  const int lb = (int)blockIdx.x - g.block0[s], nb = g.block0[s + 1] - g.block0[s];
+  const int C = g.C[s], C_pad = (C + 63) / 64 * 64, plane = g.plane[s];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lb == nb - 1) {      // padding rows [N, N_pad) of the operand matrix (the TMA tiles of K3 read them)
+    const int N = *g.n_rows_dev[s], N_pad = (N + 255) / 256 * 256;
+    uint32_t* z = reinterpret_cast<uint32_t*>(g.bf16[s] + (size_t)N * C_pad);
+    for (int i = threadIdx.x; i < (N_pad - N) * (C_pad / 2); i += blockDim.x) z[i] = 0u;
+    return;
+  }
+  if (threadIdx.x == 0) {
+    *cnt = 0;
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(&bars[i], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  {      // one octet per thread: keep those with a sampled pixel
+    const int oct = lb * kTmaOctets + (int)threadIdx.x;
+    if (oct < g.n_oct[s]) {
+      const int4 a = *reinterpret_cast<const int4*>(g.slot[s] + (size_t)oct * 8);
+      const int4 b = *reinterpret_cast<const int4*>(g.slot[s] + (size_t)oct * 8 + 4);
+      if ((a.x & a.y & a.z & a.w & b.x & b.y & b.z & b.w) >= 0) l_oct[atomicAdd(cnt, 1)] = oct;      // any entry >= 0
+    }
+  }
+  __syncthreads();
+  const int total = *cnt;
+  float* my_tiles = tiles + (size_t)warp * 2 * kMaxC * 8;
+  uint64_t* my_bars = bars + warp * 2;
+  const uint32_t tx = (uint32_t)C * 32u;
+  auto issue = [&](int k, int slot_i) {      // lane 0: bulk copy of octet l_oct[k] into tile slot slot_i
+    const int oct = l_oct[k];
+    const int gp = oct * 8, b = gp / plane, p = gp - b * plane;
+    ptx::mbar_expect_tx(&my_bars[slot_i], tx);
+    ptx::tma_load_2d(my_tiles + (size_t)slot_i * kMaxC * 8, &g.map[s], &my_bars[slot_i], p, b * C);
+  };
+  int k = warp;
+  if (k < total && lane == 0) issue(k, 0);
+  uint32_t n_done = 0;
+  for (; k < total; k += 4, ++n_done) {
+    const int cur = n_done & 1;
+    if (k + 4 < total && lane == 0) issue(k + 4, cur ^ 1);      // the other slot was consumed two iterations ago
+    ptx::mbar_wait(&my_bars[cur], (n_done >> 1) & 1, 301);
+    const int oct = l_oct[k];
+    const int row_mine = lane < 8 ? g.slot[s][(size_t)oct * 8 + lane] : -1;
+    const float* tile = my_tiles + (size_t)cur * kMaxC * 8;
+    float v[kMaxC / 32][8];
+#pragma unroll
+    for (int q = 0; q < kMaxC / 32; ++q) {
+      const int c = lane + 32 * q;
+      if (c < C) {
+        const float4 lo = *reinterpret_cast<const float4*>(tile + c * 8);
+        const float4 hi = *reinterpret_cast<const float4*>(tile + c * 8 + 4);
+        v[q][0] = lo.x; v[q][1] = lo.y; v[q][2] = lo.z; v[q][3] = lo.w;
+        v[q][4] = hi.x; v[q][5] = hi.y; v[q][6] = hi.z; v[q][7] = hi.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[q][j] = 0.f;
+      }
+    }
+    __syncwarp();      // every lane has read its rows: the slot may be refilled by the issue of the next iteration
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int row = __shfl_sync(0xffffffffu, row_mine, j);
+      if (row < 0) continue;      // warp-uniform
+      float ss = 0.f;
+#pragma unroll
+      for (int q = 0; q < kMaxC / 32; ++q) ss = fmaf(v[q][j], v[q][j], ss);
+      ss = warp_sum(ss);
+      const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+      if (lane == 0) g.inv[s][row] = inv;
+      __nv_bfloat16* orow = g.bf16[s] + (size_t)row * C_pad;
+#pragma unroll
+      for (int q = 0; q < kMaxC / 32; ++q) {
+        const int c = lane + 32 * q;
+        const float f = v[q][j] * inv;
+        if (c < C) g.f32[s][(size_t)row * C + c] = f;
+        if (c < C_pad) orow[c] = __float2bfloat16(c < C ? f : 0.f);
+      }
+    }
+  }
 }
 
 // slot map: slot[image*plane + pixel] = sorted anchor row sampled there, or -1
@@ -604,6 +715,40 @@ extern "C" int mscs_gather_normalize_sectors_batch(const mscs_gather_item* items
   }
   g.block0[count] = blocks;
   k_gather_sectors_batch<<<blocks, 256, 0, (cudaStream_t)stream_>>>(g);
+  MSCS_LAUNCH_CHECK();
+  return 0;
+}
+
+// the same gather through bulk-tensor copies (k_gather_tma_batch)
+extern "C" int mscs_gather_normalize_tma_batch(const mscs_gather_item* items, int count, void* stream_) {
+  MSCS_CHECK_ARG(items && count >= 1 && count <= MSCS_MAX_SCALES, "bad item count %d", count);
+  GatherTma g{};
+  g.count = count;
+  int blocks = 0;
+  for (int s = 0; s < count; ++s) {
+    const mscs_gather_item& it = items[s];
+    MSCS_CHECK_ARG(it.feat && it.slot && it.n_rows_dev && it.anc_bf16 && it.anc_f32 && it.inv_norm,
+                   "item %d: null pointer argument", s);
+    MSCS_CHECK_ARG(it.C >= 1 && it.C <= kMaxC, "item %d: C=%d unsupported (1..%d)", s, it.C, kMaxC);
+    MSCS_CHECK_ARG(it.n >= 1 && it.plane >= 8 && it.plane % 8 == 0, "item %d: plane must be a multiple of 8", s);
+    MSCS_CHECK_ARG((uintptr_t)it.feat % 16 == 0, "item %d: feature map must be 16-byte aligned", s);
+    if (make_tensor_map_2d(&g.map[s], (int)CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, it.feat, (unsigned long long)it.plane,
+                           (unsigned long long)it.n * it.C, (unsigned long long)it.plane * 4, 8, (unsigned)it.C))
+      return -1;
+    g.slot[s] = it.slot; g.n_rows_dev[s] = it.n_rows_dev;
+    g.bf16[s] = (__nv_bfloat16*)it.anc_bf16; g.f32[s] = it.anc_f32; g.inv[s] = it.inv_norm;
+    g.C[s] = it.C; g.plane[s] = it.plane; g.n_oct[s] = it.n * (it.plane / 8);
+    g.block0[s] = blocks;
+    blocks += ceil_div(g.n_oct[s], kTmaOctets) + 1;      // + the block that zeroes the padding rows
+  }
+  g.block0[count] = blocks;
+  const size_t smem = 128 + (size_t)4 * 2 * kMaxC * 32 + sizeof(int) * kTmaOctets + 8 * sizeof(uint64_t) + 16;
+  static bool attr_done = false;
+  if (!attr_done) {
+    MSCS_CUDA(cudaFuncSetAttribute(k_gather_tma_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  k_gather_tma_batch<<<blocks, 128, smem, (cudaStream_t)stream_>>>(g);
   MSCS_LAUNCH_CHECK();
   return 0;
 }

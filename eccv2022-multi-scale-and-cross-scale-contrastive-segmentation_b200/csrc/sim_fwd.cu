@@ -423,6 +423,29 @@ int make_tensor_map(CUtensorMap* out, const void* base, int rows, int c_pad) {
   return 0;
 }
 
+// generic 2D tiled tensor map (no swizzle): `rows` x `cols` elements of `elem_bytes`, row pitch in bytes, box in elements
+int make_tensor_map_2d(CUtensorMap* out, int dtype, int elem_bytes, const void* base, unsigned long long cols,
+                       unsigned long long rows, unsigned long long row_pitch_bytes, unsigned box_cols, unsigned box_rows) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    MSCS_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr));
+    MSCS_CHECK_ARG(p != nullptr && qr == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    fn = (EncodeTiledFn)p;
+  }
+  (void)elem_bytes;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)row_pitch_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, (CUtensorMapDataType)dtype, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MSCS_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (2d) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 int launch_build_work(const BuildArgs& b, cudaStream_t st) {
   MSCS_CUDA(launch_k(k_build_work, b.items1 ? 2 : 1, 1024, 0, st, b));
   MSCS_LAUNCH_CHECK();

@@ -179,6 +179,10 @@ typedef struct {
   void* anc_bf16; float* anc_f32; float* inv_norm;
 } mscs_gather_item;
 int mscs_gather_normalize_sectors_batch(const mscs_gather_item* items, int count, void* stream);
+/* The same gather with the strided walk over the channel planes done by the TMA unit: one bulk-tensor copy of
+ * {8 pixels x C channels} per octet of the slot map that holds a sampled pixel, staged in shared memory
+ * (feature maps 16-byte aligned). */
+int mscs_gather_normalize_tma_batch(const mscs_gather_item* items, int count, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * K3 / K4 -- fused similarity + loss forward and backward for every term of one call.
