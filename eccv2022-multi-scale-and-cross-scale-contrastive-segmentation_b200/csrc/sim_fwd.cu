@@ -18,11 +18,14 @@
 // one atomicAdd per row, half and tile.
 #include "sim_tc.cuh"
 #include <stdlib.h>
-#ifdef MSCS_TRACE      // the forward trace records sweep 0 only (sweep 1 would overwrite it)
+#ifdef MSCS_TRACE      // the forward trace records ONE sweep (the other would overwrite it): -DMSCS_TRACE_MODE=0|1
+#ifndef MSCS_TRACE_MODE
+#define MSCS_TRACE_MODE 0
+#endif
 #undef MSCS_TRACE_EV
 #define MSCS_TRACE_EV(slot, k, tile)                                                                 \
   do {                                                                                               \
-    if (MODE == 0 && blockIdx.x == 5 && (threadIdx.x & 31) == 0 && (tile) < 256u)                    \
+    if (MODE == MSCS_TRACE_MODE && blockIdx.x == 5 && (threadIdx.x & 31) == 0 && (tile) < 256u)                    \
       mscs::ptx::g_trace[(slot) * 2048 + (tile) * 8 + (k)] = (unsigned long long)clock64();          \
   } while (0)
 #endif
@@ -137,7 +140,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+#ifdef MSCS_TRACE
+  if (MODE == MSCS_TRACE_MODE && blockIdx.x == 5 && threadIdx.x == 0) ptx::g_trace[3 * 2048 + 255 * 8 + 5] = (unsigned long long)clock64();
+#endif
   pdl_wait();       // barriers and tensor memory are set up while the previous grid drains
+#ifdef MSCS_TRACE
+  if (MODE == MSCS_TRACE_MODE && blockIdx.x == 5 && threadIdx.x == 0) ptx::g_trace[3 * 2048 + 255 * 8 + 7] = (unsigned long long)clock64();
+#endif
 #ifdef MSCS_WAIT_PROFILE     // effective SM clock of this launch: slot 31 accumulates (ns, cycles) of CTA 0
   const unsigned long long prof_t0 = ptx::globaltimer_ns();
   const long long prof_c0 = clock64();
@@ -180,8 +189,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
     int stage = 0; uint32_t phase = 0, k_phase = 0, it = 0;
     const uint32_t k_addr = ptx::smem_u32(smK), a_addr = ptx::smem_u32(smA);
     while (wk.next(sg)) {
+      MSCS_TRACE_EV(0, 3, it);
       ptx::mbar_wait(k_full, k_phase, 111); k_phase ^= 1;
       ptx::tc_fence_after();
+      MSCS_TRACE_EV(0, 4, it);
       for (int rt = sg.c_begin; rt < sg.c_end; ++rt, ++it) {
         const uint32_t buf = it & 1;
         MSCS_TRACE_EV(0, 0, it);
@@ -269,21 +280,71 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
             }
           }
         } else if (touches) {
-#pragma unroll 1
-          for (int c4 = 0; c4 < NCH; ++c4) {
-            const int c0 = cb + c4 * 32;
-            if (c0 + 32 <= wmin || c0 >= wmax) continue;      // warp-uniform
-            uint32_t v[32];
-            ptx::tmem_ld32(taddr + c4 * 32, v);
-            ptx::tmem_ld_wait(v);
+          // Positive sweep.  The event trace (tools/trace_fwd1.py) showed ~11.7k cycles per tile in this epilogue with
+          // three MUFU ops (ex2, lg2, rcp) and ~14 issue slots per element, for 8 % of the tiles 56 us.  With
+          // den = e + neg_i and u = e / neg_i:  lg2(den) = lg2(neg_i) + lg2(1 + u),  1/den = (1/neg_i) / (1 + u), and a
+          // positive's e is normally a tiny fraction of the row's negative sum (u ~ 1e-4 at cfg-2), so both become
+          // short series on the FMA pipe -- ln(1+u) = u - u^2/2 + u^3/3 (error u^4/4), 1/(1+u) = 1 - u + u^2 - u^3
+          // (error u^4) -- evaluated two elements per instruction; ONE MUFU op per element is left.  Chunks of 16
+          // columns that lie inside the positive range of EVERY row of the warp and off the diagonal need no masks
+          // (rows are class-sorted: all but the warps on a class boundary).  Anything else -- mixed chunks, or a chunk
+          // where some e reaches neg_i / 64 -- takes the per-element path with lg2 / rcp.
+          const float rneg = valid ? ptx::rcp(negi) : 1.f, lneg = valid ? ptx::lg2(negi) : 0.f;
+          int fmin = valid ? p0 : 0x7fffffff, fmax = valid ? p1 : 0;      // columns positive for every row of the warp
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const int col = c0 + c;
-              const bool ispos = ((unsigned)(col - p0) < plen) && (col != self_col);
-              const float x = __uint_as_float(v[c]) * scale;      // logit in log2 units
-              const float den = ptx::ex2(x) + negi;
-              acc0 += ispos ? (x - ptx::lg2(den)) : 0.f;
-              acc1 += ispos ? ptx::rcp(den) : 0.f;
+          for (int o = 16; o > 0; o >>= 1) {
+            fmin = max(fmin, __shfl_xor_sync(0xffffffffu, fmin, o));
+            fmax = min(fmax, __shfl_xor_sync(0xffffffffu, fmax, o));
+          }
+          const int row0 = rt * 128 + quad * 32;      // diagonal columns of this warp's rows: [row0, row0 + 32)
+          const uint64_t scale2 = ptx::pack2(scale, scale), rneg2 = ptx::pack2(rneg, rneg);
+          const uint64_t one2 = ptx::pack2(1.f, 1.f), mone2 = ptx::pack2(-1.f, -1.f), mhalf2 = ptx::pack2(-0.5f, -0.5f),
+                         third2 = ptx::pack2(0.3333333433f, 0.3333333433f), ml2e2 = ptx::pack2(-kLog2e, -kLog2e);
+#pragma unroll 1
+          for (int c4 = 0; c4 < CPT / 16; ++c4) {
+            const int c0 = cb + c4 * 16;
+            if (c0 + 16 <= wmin || c0 >= wmax) continue;      // warp-uniform
+            uint32_t v[16];
+            ptx::tmem_ld16(taddr + c4 * 16, v);
+            ptx::tmem_ld_wait16(v);
+            const bool full = c0 >= fmin && c0 + 16 <= fmax && !(t.self_mask && c0 < row0 + 32 && c0 + 16 > row0);
+            bool done = false;
+            if (full) {      // warp-uniform
+              uint64_t plg2 = 0ull, prc2 = 0ull;
+              float emax = 0.f;
+#pragma unroll
+              for (int c = 0; c < 16; c += 2) {
+                const uint64_t x2 = ptx::mul2(ptx::pack2u(v[c], v[c + 1]), scale2);      // logits in log2 units
+                float x0, x1;
+                ptx::unpack2(x2, x0, x1);
+                const float e0 = ptx::ex2(x0), e1 = ptx::ex2(x1);
+                emax = fmaxf(emax, fmaxf(e0, e1));
+                const uint64_t u2 = ptx::mul2(ptx::pack2(e0, e1), rneg2);
+                uint64_t l = ptx::fma2(u2, third2, mhalf2);
+                l = ptx::mul2(u2, ptx::fma2(u2, l, one2));                               // ln(1 + u)
+                uint64_t r = ptx::fma2(u2, mone2, one2);
+                r = ptx::fma2(u2, ptx::fma2(u2, r, mone2), one2);                        // 1 / (1 + u)
+                plg2 = ptx::add2(plg2, ptx::fma2(l, ml2e2, x2));                         // x - lg2(1 + u)
+                prc2 = ptx::add2(prc2, r);
+              }
+              if (!__any_sync(0xffffffffu, emax * rneg >= 0.015625f)) {
+                float a0, a1, b0, b1;
+                ptx::unpack2(plg2, a0, a1); ptx::unpack2(prc2, b0, b1);
+                acc0 += fmaf(-16.f, lneg, a0 + a1);
+                acc1 = fmaf(b0 + b1, rneg, acc1);
+                done = true;
+              }
+            }
+            if (!done) {
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                const int col = c0 + c;
+                const bool ispos = ((unsigned)(col - p0) < plen) && (col != self_col);
+                const float x = __uint_as_float(v[c]) * scale;      // logit in log2 units
+                const float den = ptx::ex2(x) + negi;
+                acc0 += ispos ? (x - ptx::lg2(den)) : 0.f;
+                acc1 += ispos ? ptx::rcp(den) : 0.f;
+              }
             }
           }
         }
@@ -308,6 +369,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+#ifdef MSCS_TRACE
+  if (MODE == MSCS_TRACE_MODE && blockIdx.x == 5 && threadIdx.x == 0) ptx::g_trace[3 * 2048 + 255 * 8 + 6] = (unsigned long long)clock64();
+#endif
 #ifdef MSCS_WAIT_PROFILE
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     atomicAdd(&ptx::g_wait_ns[31], ptx::globaltimer_ns() - prof_t0);
