@@ -1192,13 +1192,12 @@ def _run_forward_pooled(sp, labels, feats32, needs, comm):
         for x in sizes:
             slots.append(slot_slab[off:off + x])
             off += x
-        # dense gradients (local): zero-filled on the side stream; this parity's row statistics: zeroed here, i.e.
-        # before this rank's barrier A, hence before any peer's push
+        # dense gradients (local): zero-filled on the side stream.  Row statistics: the sweeps accumulate them (one
+        # atomic per row, quarter and tile) in PRIVATE memory; pushed to every rank's slab afterwards
         gradbufs = _GradBuffers(feats32, needs, False, 0) if any(needs) else None
         if gradbufs is not None:
             gradbufs.start_fill()
-        _lib.check(lib.mscs_fill_bytes(_lib.ptr_array([xs.local + xo["stats"]]), (C.c_int32 * 1)(0),
-                                       (C.c_size_t * 1)(4 * sp.stats_n), 1, st), "mscs_fill_bytes")
+        stats_priv = torch.zeros(sp.stats_n, dtype=f32, device=dev)
         mt, pos = torch_mt_state()
         draws = _stream_cache(dev).acquire(mt, pos, sp.max_draws + _MT_N)
         plan = (_lib.ScalePlan * S)()
@@ -1206,13 +1205,17 @@ def _run_forward_pooled(sp, labels, feats32, needs, comm):
         arrs = [_lib.ptr_array([ibase + 4 * sp.ioff[s][k] for s in range(S)]) for k in range(5)]
         sarr = _lib.ptr_array([x.data_ptr() for x in slots])
         fbase, bbase = fslab.data_ptr(), xs.local + xo["b"]
-        job = _lib.SimJob()
+        # two views of the same terms: `job_sw` (sweeps: statistics in private memory) and `job` (finalise and
+        # backward: statistics of ALL rows in the exchange slab)
+        job, job_sw = _lib.SimJob(), _lib.SimJob()
         _fill_job(job, sp, A, bbase, ibase, xs.local + xo["stats"], misc.data_ptr(), work.data_ptr())
+        _fill_job(job_sw, sp, A, bbase, ibase, stats_priv.data_ptr(), misc.data_ptr(), work.data_ptr())
         nt = len(sp.terms)
         mbase = misc.data_ptr()
-        job.term_loss, job.total_loss = mbase + 4 * sp.out_off, mbase + 4 * (sp.out_off + nt)
         total_t = torch.empty((), dtype=f32, device=dev)      # own buffer, not a view (see _run_forward_fast)
-        job.total_out = total_t.data_ptr()
+        for jb in (job, job_sw):
+            jb.term_loss, jb.total_loss = mbase + 4 * sp.out_off, mbase + 4 * (sp.out_off + nt)
+            jb.total_out = total_t.data_ptr()
         # Selection and the peer-store gather are driven by the DEVICE plan records and enqueued before the host looks
         # at the plan: the one host wait of the forward (errors, row ranges) overlaps them instead of idling the GPU.
         device_driven = sp.v_cap * 12 <= 200 * 1024
@@ -1253,28 +1256,31 @@ def _run_forward_pooled(sp, labels, feats32, needs, comm):
         if zp:
             _lib.check(lib.mscs_fill_bytes(_lib.ptr_array(zp), (C.c_int32 * len(zp))(*([0] * len(zp))),
                                            (C.c_size_t * len(zb))(*zb), len(zp), st), "mscs_fill_bytes")
-    push_off, push_len = [], []
-    for i, (a, k, *_rest) in enumerate(sp.terms):      # the plan-dependent fields of the job
-        t = job.terms[i]
-        t.N1, t.N2 = samples[a].N, samples[k].N
-        # anchor (and key) rows are sharded over the ranks in 128-row granules
-        t.row_begin, t.row_end = shard_rows(samples[a].N, world, rank)
-        t.krow_begin, t.krow_end = shard_rows(samples[k].N, world, rank)
+    push_off, push_src, push_len = [], [], []
+    for i, (a, k, *_rest) in enumerate(sp.terms):      # the plan-dependent fields of the jobs
+        rb, re_ = shard_rows(samples[a].N, world, rank)      # anchor (and key) rows: sharded in 128-row granules
+        kb, ke = shard_rows(samples[k].N, world, rank)
+        for jb in (job, job_sw):
+            t = jb.terms[i]
+            t.N1, t.N2 = samples[a].N, samples[k].N
+            t.row_begin, t.row_end, t.krow_begin, t.krow_end = rb, re_, kb, ke
         n1 = (sp.Ncap[a] + 15) // 16 * 16
         for q in range(3):      # neg, pos, S of this rank's rows
-            push_off.append(xo["stats"] // 4 + sp.soff[i] + q * n1 + t.row_begin)
-            push_len.append(t.row_end - t.row_begin)
+            push_src.append(sp.soff[i] + q * n1 + rb)
+            push_off.append(xo["stats"] // 4 + sp.soff[i] + q * n1 + rb)
+            push_len.append(re_ - rb)
     with _timed("sim_fwd"):
-        _lib.check(lib.mscs_sim_forward_sweeps(C.byref(job), st), "mscs_sim_forward_sweeps")
-        _lib.check(lib.mscs_xchg_push(xs.peers, world, rank, (C.c_int64 * len(push_off))(*push_off),
-                                      (C.c_int32 * len(push_len))(*push_len), len(push_off), st), "mscs_xchg_push")
+        _lib.check(lib.mscs_sim_forward_sweeps(C.byref(job_sw), st), "mscs_sim_forward_sweeps")
+        _lib.check(lib.mscs_xchg_push(xs.peers, world, stats_priv.data_ptr(), (C.c_int64 * len(push_src))(*push_src),
+                                      (C.c_int64 * len(push_off))(*push_off), (C.c_int32 * len(push_len))(*push_len),
+                                      len(push_off), st), "mscs_xchg_push")
         comm.barrier(xs)                                   # B: the statistics of every row are complete here
         _lib.check(lib.mscs_sim_finalize(C.byref(job), st), "mscs_sim_finalize")
     if comm.owns_rng:
         _finish_rng(sp, dev, mt, pos, total)
     state = _StepState()
     state.sp, state.job, state.samples, state.gradbufs, state.slots = sp, job, samples, gradbufs, slots
-    state.keep = (ws, islab, fslab, misc, work, slot_slab)
+    state.keep = (ws, islab, fslab, misc, work, slot_slab, stats_priv)
     state.stats = None
     state.fslab, state.term_loss = fslab, misc[sp.out_off:sp.out_off + nt]
     state.total = total_t

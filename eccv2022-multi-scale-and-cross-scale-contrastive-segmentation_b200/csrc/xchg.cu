@@ -9,7 +9,9 @@
 //   k_gather_p2p        K2 fused with the all-gather: every normalised bf16 anchor row is stored -- 16 bytes per lane,
 //                       one 512-byte row per warp instruction -- straight into the SAME sorted row of the operand
 //                       matrix of every rank (its own included).  No packing, no collective, no zero slab.
-//   k_push_ranges       row statistics of this rank's anchor-row range -> the same rows on every peer.
+//   k_push_ranges       row statistics of this rank's anchor-row range (accumulated in PRIVATE memory: the sweeps'
+//                       per-tile atomics into the peer-mapped slab itself ran sweep 0 1.7x slower) -> the same rows
+//                       of every rank's slab.
 //   k_xchg_barrier      release/acquire flag barrier across the ranks (one flag word per rank, monotonic epoch):
 //                       orders "my stores have landed everywhere" before "I read what the others stored".
 //   scatter (pull)      gather.cu: the scatter reads every gradient row from the rank that computed it.
@@ -55,18 +57,17 @@ __global__ void k_xchg_barrier(PeerPtrs flags, int rank, uint32_t epoch, unsigne
   __threadfence_system();
 }
 
-// up to 48 ranges per call: copy [begin, end) floats of `src` (an offset into this rank's slab) to the same offset
-// of every peer's slab
-struct PushArgs { PeerPtrs slab; int rank; int count; long long off[48]; int len[48]; };
+// up to 48 ranges per call: copy len[j] floats from src + src_off[j] (private memory of this rank) to float offset
+// off[j] of EVERY rank's slab, this rank's own included
+struct PushArgs { PeerPtrs slab; const float* src; int count; long long off[48]; long long src_off[48]; int len[48]; };
 __global__ void __launch_bounds__(256) k_push_ranges(const __grid_constant__ PushArgs a) {
   const int j = blockIdx.y;
   if (j >= a.count) return;
-  const float* src = reinterpret_cast<const float*>(a.slab.p[a.rank]) + a.off[j];
+  const float* src = a.src + a.src_off[j];
   const int len = a.len[j];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
     const float v = src[i];
-    for (int r = 0; r < a.slab.n; ++r)
-      if (r != a.rank) reinterpret_cast<float*>(a.slab.p[r])[a.off[j] + i] = v;
+    for (int r = 0; r < a.slab.n; ++r) reinterpret_cast<float*>(a.slab.p[r])[a.off[j] + i] = v;
   }
 }
 
@@ -184,15 +185,19 @@ extern "C" int mscs_xchg_barrier(void* const* slabs, int world, int rank, uint32
   return 0;
 }
 
-extern "C" int mscs_xchg_push(void* const* slabs, int world, int rank, const int64_t* float_off, const int32_t* len,
-                              int count, void* stream_) {
-  MSCS_CHECK_ARG(float_off && len && count >= 0 && count <= 48, "bad range list (%d ranges, at most 48)", count);
-  if (count == 0 || world == 1) return 0;
+extern "C" int mscs_xchg_push(void* const* slabs, int world, const float* src, const int64_t* src_float_off,
+                              const int64_t* float_off, const int32_t* len, int count, void* stream_) {
+  MSCS_CHECK_ARG(src && src_float_off && float_off && len && count >= 0 && count <= 48,
+                 "bad range list (%d ranges, at most 48)", count);
+  if (count == 0) return 0;
   PushArgs a{};
   if (int rc = fill_peers(&a.slab, slabs, world, 0)) return rc;
-  a.rank = rank; a.count = count;
+  a.src = src; a.count = count;
   int maxlen = 0;
-  for (int j = 0; j < count; ++j) { a.off[j] = float_off[j]; a.len[j] = len[j]; if (len[j] > maxlen) maxlen = len[j]; }
+  for (int j = 0; j < count; ++j) {
+    a.off[j] = float_off[j]; a.src_off[j] = src_float_off[j]; a.len[j] = len[j];
+    if (len[j] > maxlen) maxlen = len[j];
+  }
   if (maxlen == 0) return 0;
   const int bx = ceil_div(maxlen, 256) < 64 ? ceil_div(maxlen, 256) : 64;
   k_push_ranges<<<dim3(bx, count), 256, 0, (cudaStream_t)stream_>>>(a);

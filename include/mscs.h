@@ -56,6 +56,8 @@ int mscs_device_ok(void);
 /* small device->host read on `stream`, ordered after `wait_event` (cudaEvent_t or NULL), synchronised before return */
 int mscs_read_to_host(void* dst_host, const void* src_dev, size_t bytes, void* wait_event, void* stream);
 int mscs_fill_bytes(void* const* ptrs, const int32_t* values, const size_t* bytes, int count, void* stream);
+/* asynchronous device-to-device copy on `stream` */
+int mscs_copy_d2d(void* dst, const void* src, size_t bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * K1 -- sampling.  Replaces get_dist_and_classes (DenseContrastiveLossV2.py:194-206),
@@ -350,10 +352,10 @@ int mscs_xchg_free(void* dev_ptr);
  * `epoch`: strictly increasing per slab (1, 2, 3, ...), the same sequence on every rank.  A rank that waits longer than
  * timeout_s seconds (<= 0: 20 s) traps, i.e. the stream reports a launch failure instead of hanging. */
 int mscs_xchg_barrier(void* const* slabs, int world, int rank, uint32_t epoch, double timeout_s, void* stream);
-/* copy `count` (<= 48) float ranges [float_off[j], float_off[j] + len[j]) of the local slab to the same offsets of
- * every peer's slab (row statistics of this rank's anchor rows) */
-int mscs_xchg_push(void* const* slabs, int world, int rank, const int64_t* float_off, const int32_t* len, int count,
-                   void* stream);
+/* copy `count` (<= 48) float ranges src[src_float_off[j] .. + len[j]) (private memory of this rank: the row statistics
+ * of its anchor rows, accumulated by the sweeps) to float offset float_off[j] of EVERY rank's slab, its own included */
+int mscs_xchg_push(void* const* slabs, int world, const float* src, const int64_t* src_float_off,
+                   const int64_t* float_off, const int32_t* len, int count, void* stream);
 /* K2 fused with the all-gather of the normalised key set: as mscs_gather_normalize_sectors, but every bf16 anchor row
  * is stored into the operand matrix at byte offset bf16_byte_off of EVERY rank's slab (same sorted row everywhere: the
  * plan is global); fp32 rows and inverse norms stay local.  Also zeroes the local padding rows [N, N_pad). */

@@ -1,0 +1,40 @@
+"""Forward timeline of the pooled cfg5 step on every rank (torchrun; MSCS_FWD_TIMELINE=1): milliseconds between the
+launches of the forward sweeps as seen by CUDA events on each rank's stream."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+import mscs_b200
+from mscs_b200 import synth, _lib
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+cfg = synth.CONFIGS["cfg5"]
+labels_all = synth.make_labels(cfg)
+n = cfg["n"]; nl = n // world
+fts = []
+for si, st in enumerate(cfg["strides"]):
+    f = torch.empty((nl, cfg["C"], cfg["H"] // st, cfg["W"] // st), device=dev)
+    for b in range(rank * nl, (rank + 1) * nl):
+        g = torch.Generator(device=dev); g.manual_seed(100003 * (si + 1) + b)
+        f[b - rank * nl].normal_(generator=g)
+    fts.append(f.requires_grad_(True))
+lab = labels_all[rank * nl:(rank + 1) * nl].contiguous().to(dev)
+mod = mscs_b200.DenseContrastiveLossV2_ms(dict(cfg["loss"]), comm=mscs_b200.TorchDistComm())
+torch.manual_seed(0)
+def step():
+    for f in fts: f.grad = None
+    mod(lab, fts).backward()
+for _ in range(3): step()
+lib = _lib.load()
+buf = np.zeros(8, np.float32); acc = np.zeros(8); K = 8
+for _ in range(K):
+    dist.barrier(); torch.cuda.synchronize()
+    step()
+    k = lib.mscs_debug_fwd_timeline(buf.ctypes.data, 8)
+    acc[:k] += buf[:k]
+print(f"rank {rank}: row_ranges, work tables, sweep0, sweep1 (us) = {[round(float(x) / K * 1e3, 1) for x in acc[:k]]}", flush=True)
+dist.destroy_process_group()
