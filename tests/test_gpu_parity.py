@@ -696,7 +696,10 @@ def test_channels_last_matches_nchw_full_size(dev):
     for s, (a, b) in enumerate(zip(ga, gb)):
         err, ref = float((a - b).abs().max()), float(a.abs().max())
         print(f"cfg2 nhwc vs nchw scale {s}: max-abs {err:.3e} (max {ref:.3e})")
-        assert err <= 1e-4 * ref
+        # the two gathers sum the squares of a row in different orders: a last-ulp difference of the norm flips the
+        # bf16 rounding of a few operand elements (2^-9 relative each), and the backward accumulates with atomics in
+        # an order that changes from run to run -- observed 0.6e-4 ... 1.1e-4 of the largest gradient entry
+        assert err <= 3e-4 * ref
         assert torch.equal(a != 0, b != 0)
 
 
