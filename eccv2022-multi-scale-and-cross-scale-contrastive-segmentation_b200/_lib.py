@@ -69,6 +69,7 @@ _SIGNATURES = {
     "mscs_debug_trace_bwd": (C.c_int, [C.c_void_p, C.c_int]),
     "mscs_debug_trace_fwd": (C.c_int, [C.c_void_p, C.c_int]),
     "mscs_debug_fwd_timeline": (C.c_int, [C.c_void_p, C.c_int]),
+    "mscs_debug_cta_spans_fwd": (C.c_int, [C.c_void_p, C.c_int]),
     "mscs_sample_workspace_bytes": (C.c_size_t, [C.POINTER(SampleCfg)]),
     "mscs_sample_max_draws": (C.c_size_t, [C.POINTER(SampleCfg)]),
     "mscs_sample_plan": (C.c_int, [C.POINTER(SampleCfg), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -568,6 +568,17 @@ extern "C" int mscs_mt19937_stream(const uint32_t* mt_state_host, int mt_pos, ui
   // the 624 state words are staged behind the stream (the buffer holds n_words + 1024 words)
   uint32_t* state_dev = draws_dev + align_up((size_t)n_words, 64);
   MSCS_CUDA(cudaMemcpyAsync(state_dev, mt_state_host, sizeof(uint32_t) * 624, cudaMemcpyHostToDevice, st));
+  // The SM this CTA lands on must keep its shared memory at the maximum carve-out: a CTA of the persistent tensor
+  // kernels (215 KB) joins it later, and an SM is not re-partitioned while a CTA is resident -- with the default
+  // (small) carve-out that SM was lost to the sweeps for as long as this kernel ran (148 CTAs on 147 SMs).
+  static thread_local int carve_dev = -1;
+  int dev_now = 0;
+  MSCS_CUDA(cudaGetDevice(&dev_now));
+  if (carve_dev != dev_now) {
+    MSCS_CUDA(cudaFuncSetAttribute(k_mt_stream, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   (int)cudaSharedmemCarveoutMaxShared));
+    carve_dev = dev_now;
+  }
   k_mt_stream<<<1, kMtThreads, 0, st>>>(state_dev, mt_pos, (long long)n_words, draws_dev);
   MSCS_LAUNCH_CHECK();
   return 0;

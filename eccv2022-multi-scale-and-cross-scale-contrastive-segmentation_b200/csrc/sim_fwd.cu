@@ -45,7 +45,19 @@ constexpr int kFwdKeys = 256;       // resident key block = N of the MMA
 constexpr int kFwdEpiWarps = 16;
 constexpr int kFwdThreads = 128 + 32 * kFwdEpiWarps;
 constexpr int kFwdColsPerThread = kFwdKeys / 2;      // thread = (anchor row, 128-key half) of its group's tiles
-constexpr int kFwdStages = 5;
+#ifndef MSCS_FWD_SPLITN
+#define MSCS_FWD_SPLITN 0
+#endif
+#ifndef MSCS_FWD_STAGES
+#define MSCS_FWD_STAGES 5
+#endif
+constexpr int kFwdStages = MSCS_FWD_STAGES;
+// MSCS_FWD_SPLITN: the 128 x 256 tile is accumulated as two 128-column halves one after the other (N = 128 MMAs, the
+// four anchor K-blocks of the tile stay in the ring for both passes), each half with its own full / empty barrier: the
+// four epilogue warps of the first half start while the second half is still being multiplied, and the MMA warp
+// re-enters a half as soon as ITS four warps are done -- four accumulators of 128 columns in flight instead of two of 256.
+constexpr bool kSplitN = MSCS_FWD_SPLITN != 0;
+constexpr int kAccBars = kSplitN ? 4 : 2;
 
 struct FwdTerm {
   const int* a_cls; const int* k_seg;
@@ -110,6 +122,11 @@ __device__ __forceinline__ void neg_chunk(const uint32_t (&cur)[16], int c0, int
   }
 }
 
+#ifdef MSCS_WAIT_PROFILE
+// per CTA and sweep of the last launch: start / end (globaltimer ns), SM cycles, SM id  (profiling build only)
+static __device__ unsigned long long g_cta_span[2][160][4];
+#endif
+
 // POLY: pair mask of fast_chunk (sweep 0 only): 0x88 = a quarter of the exponentials on the FMA pipe
 template <int KB, int MODE, int POLY>
 __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constant__ FwdArgs args) {
@@ -122,9 +139,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
   uint64_t* a_empty = bars + kFwdStages;      // [stages]
   uint64_t* k_full = bars + 2 * kFwdStages;   // resident key block
   uint64_t* k_empty = k_full + 1;
-  uint64_t* acc_full = k_full + 2;            // [2]
-  uint64_t* acc_empty = k_full + 4;           // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(k_full + 6);
+  uint64_t* acc_full = k_full + 2;            // [kAccBars]
+  uint64_t* acc_empty = acc_full + kAccBars;  // [kAccBars]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccBars);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -132,7 +149,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < kFwdStages; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
     ptx::mbar_init(k_full, 1); ptx::mbar_init(k_empty, 1);
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], kFwdEpiWarps / 2); }
+    for (int i = 0; i < kAccBars; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], kFwdEpiWarps / kAccBars); }
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc(tmem_slot, 512);
@@ -196,26 +213,54 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
       for (int rt = sg.c_begin; rt < sg.c_end; ++rt, ++it) {
         const uint32_t buf = it & 1;
         MSCS_TRACE_EV(0, 0, it);
-        ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1, 112);
-        ptx::tc_fence_after();
-        MSCS_TRACE_EV(0, 1, it);
-        for (int kb = 0; kb < KB; ++kb) {
-          ptx::mbar_wait(&a_full[stage], phase, 113);
-          ptx::tc_fence_after();
-          if (ptx::elect_one()) {
+        if constexpr (kSplitN) {
+          constexpr uint32_t idesc_h = ptx::umma_idesc_bf16(128, 128, 0, 0);
+          const int stage0 = stage; const uint32_t phase0 = phase;
+#pragma unroll 1
+          for (int h = 0; h < 2; ++h) {
+            ptx::mbar_wait(&acc_empty[buf * 2 + h], ((it >> 1) & 1) ^ 1, 112);
+            ptx::tc_fence_after();
+            if (h == 0) MSCS_TRACE_EV(0, 1, it);
+            stage = stage0; phase = phase0;
+            for (int kb = 0; kb < KB; ++kb) {
+              if (h == 0) { ptx::mbar_wait(&a_full[stage], phase, 113); ptx::tc_fence_after(); }
+              if (ptx::elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ad = ptx::umma_desc_sw128(a_addr + stage * kBlkBytes + k * 32, 16, 1024);
-              const uint64_t bd = ptx::umma_desc_sw128(k_addr + kb * 2 * kBlkBytes + k * 32, 16, 1024);
-              ptx::umma_ss(tmem_base + buf * kFwdKeys, ad, bd, idesc, (kb | k) != 0);
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t ad = ptx::umma_desc_sw128(a_addr + stage * kBlkBytes + k * 32, 16, 1024);
+                  const uint64_t bd = ptx::umma_desc_sw128(k_addr + (kb * 2 + h) * kBlkBytes + k * 32, 16, 1024);
+                  ptx::umma_ss(tmem_base + buf * kFwdKeys + h * 128, ad, bd, idesc_h, (kb | k) != 0);
+                }
+                if (h == 1) ptx::umma_commit(&a_empty[stage]);
+              }
+              __syncwarp();
+              if (++stage == kFwdStages) { stage = 0; phase ^= 1; }
             }
-            ptx::umma_commit(&a_empty[stage]);
+            if (ptx::elect_one()) ptx::umma_commit(&acc_full[buf * 2 + h]);
+            __syncwarp();
           }
+        } else {
+          ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1, 112);
+          ptx::tc_fence_after();
+          MSCS_TRACE_EV(0, 1, it);
+          for (int kb = 0; kb < KB; ++kb) {
+            ptx::mbar_wait(&a_full[stage], phase, 113);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t ad = ptx::umma_desc_sw128(a_addr + stage * kBlkBytes + k * 32, 16, 1024);
+                const uint64_t bd = ptx::umma_desc_sw128(k_addr + kb * 2 * kBlkBytes + k * 32, 16, 1024);
+                ptx::umma_ss(tmem_base + buf * kFwdKeys, ad, bd, idesc, (kb | k) != 0);
+              }
+              ptx::umma_commit(&a_empty[stage]);
+            }
+            __syncwarp();
+            if (++stage == kFwdStages) { stage = 0; phase ^= 1; }
+          }
+          if (ptx::elect_one()) ptx::umma_commit(&acc_full[buf]);
           __syncwarp();
-          if (++stage == kFwdStages) { stage = 0; phase ^= 1; }
         }
-        if (ptx::elect_one()) ptx::umma_commit(&acc_full[buf]);
-        __syncwarp();
         MSCS_TRACE_EV(0, 2, it);
       }
       if (ptx::elect_one()) ptx::umma_commit(k_empty);
@@ -253,7 +298,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
         const int tslot = warp == 4 ? 1 : (warp == 11 ? 2 : (warp == 12 ? 3 : -1));
         if (tslot > 0) MSCS_TRACE_EV(tslot, 0, it);
 #endif
-        ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1, 121);
+        ptx::mbar_wait(&acc_full[kSplitN ? buf * 2 + ch : buf], (it >> 1) & 1, 121);
         ptx::tc_fence_after();
 #ifdef MSCS_TRACE
         if (tslot > 0) MSCS_TRACE_EV(tslot, 1, it);
@@ -353,7 +398,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
 #endif
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+        if (lane == 0) ptx::mbar_arrive(&acc_empty[kSplitN ? buf * 2 + ch : buf]);
         if (valid) {
           if (MODE == 0) {
             float a0, a1, b0, b1;
@@ -376,6 +421,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     atomicAdd(&ptx::g_wait_ns[31], ptx::globaltimer_ns() - prof_t0);
     atomicAdd(&ptx::g_wait_cnt[31], (unsigned long long)(clock64() - prof_c0));
+  }
+  if (threadIdx.x == 0 && blockIdx.x < 160) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    unsigned long long* sp = g_cta_span[MODE][blockIdx.x];
+    sp[0] = prof_t0; sp[1] = ptx::globaltimer_ns(); sp[2] = (unsigned long long)(clock64() - prof_c0); sp[3] = smid;
   }
 #endif
 }
@@ -695,6 +746,19 @@ extern "C" int mscs_debug_trace_fwd(unsigned long long* out, int max_events) {
   return n;
 #else
   (void)out; (void)max_events;
+  return 0;
+#endif
+}
+
+// debug (profiling build only): per-CTA spans of the last launch of sweep `mode`: 160 x {start ns, end ns, SM cycles, SM id}
+extern "C" int mscs_debug_cta_spans_fwd(unsigned long long* out, int mode) {
+#ifdef MSCS_WAIT_PROFILE
+  MSCS_CUDA(cudaDeviceSynchronize());
+  MSCS_CUDA(cudaMemcpyFromSymbol(out, g_cta_span, sizeof(unsigned long long) * 160 * 4,
+                                 sizeof(unsigned long long) * 160 * 4 * (mode ? 1 : 0)));
+  return 160;
+#else
+  (void)out; (void)mode;
   return 0;
 #endif
 }

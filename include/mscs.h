@@ -50,6 +50,9 @@ int mscs_debug_trace_fwd(unsigned long long* out, int max_events);
 /* debug (MSCS_FWD_TIMELINE set in the environment): milliseconds between the launches of the last forward call
    (row ranges, work table 0, sweep 0, work table 1, sweep 1); returns the number of intervals */
 int mscs_debug_fwd_timeline(float* ms_out, int max_n);
+/* profiling build (make prof) only: per-CTA spans of the last launch of forward sweep `mode`:
+   160 x {start ns, end ns, SM cycles, SM id}; returns 160 (0 in the product build) */
+int mscs_debug_cta_spans_fwd(unsigned long long* out, int mode);
 /* 1 if a CUDA device with compute capability 10.x is present */
 int mscs_device_ok(void);
 /* up to 8 asynchronous byte fills in one call (per-step workspace initialisation: statistics = 0, slot maps = 0xFF) */

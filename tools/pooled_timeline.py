@@ -36,5 +36,17 @@ for _ in range(K):
     step()
     k = lib.mscs_debug_fwd_timeline(buf.ctypes.data, 8)
     acc[:k] += buf[:k]
-print(f"rank {rank}: row_ranges, work tables, sweep0, sweep1 (us) = {[round(float(x) / K * 1e3, 1) for x in acc[:k]]}", flush=True)
+spans = np.zeros((160, 4), np.uint64)
+for mode in (0, 1):
+    if lib.mscs_debug_cta_spans_fwd(spans.ctypes.data, mode) == 0:
+        break
+    sp = spans[:148].astype(np.int64)
+    t0, t1, cyc, sm = sp[:, 0], sp[:, 1], sp[:, 2], sp[:, 3]
+    dur = (t1 - t0) / 1e3
+    order = np.argsort(-dur)[:3]
+    print(f"\nrank {rank} sweep{mode} CTAs: kernel span {(t1.max() - t0.min()) / 1e3:.1f} us | start spread {(t0.max() - t0.min()) / 1e3:.1f} us | "
+          f"duration min/median/max {dur.min():.1f}/{np.median(dur):.1f}/{dur.max():.1f} us | clock {np.median(cyc / (t1 - t0)):.3f} GHz | "
+          f"slowest CTAs (cta, sm, us, start offset us): {[(int(i), int(sm[i]), round(float(dur[i]), 1), round(float(t0[i] - t0.min()) / 1e3, 1)) for i in order]} | "
+          f"distinct SMs {len(set(sm.tolist()))}", flush=True)
+print(f"\nrank {rank}: row_ranges, work tables, sweep0, sweep1 (us) = {[round(float(x) / K * 1e3, 1) for x in acc[:k]]}", flush=True)
 dist.destroy_process_group()
