@@ -45,19 +45,12 @@ constexpr int kFwdKeys = 256;       // resident key block = N of the MMA
 constexpr int kFwdEpiWarps = 16;
 constexpr int kFwdThreads = 128 + 32 * kFwdEpiWarps;
 constexpr int kFwdColsPerThread = kFwdKeys / 2;      // thread = (anchor row, 128-key half) of its group's tiles
-#ifndef MSCS_FWD_SPLITN
-#define MSCS_FWD_SPLITN 0
-#endif
-#ifndef MSCS_FWD_STAGES
-#define MSCS_FWD_STAGES 5
-#endif
-constexpr int kFwdStages = MSCS_FWD_STAGES;
-// MSCS_FWD_SPLITN: the 128 x 256 tile is accumulated as two 128-column halves one after the other (N = 128 MMAs, the
-// four anchor K-blocks of the tile stay in the ring for both passes), each half with its own full / empty barrier: the
-// four epilogue warps of the first half start while the second half is still being multiplied, and the MMA warp
-// re-enters a half as soon as ITS four warps are done -- four accumulators of 128 columns in flight instead of two of 256.
-constexpr bool kSplitN = MSCS_FWD_SPLITN != 0;
-constexpr int kAccBars = kSplitN ? 4 : 2;
+constexpr int kFwdStages = 5;
+// (Tried in round 2: accumulating the 128 x 256 tile as two 128-column halves with N = 128 MMAs and one full / empty
+// barrier pair per half -- four accumulators in flight, the first half's warps start 1000 cycles earlier.  Correct, but
+// the forward stage went from 0.223 to 0.393 ms at cfg-2: the N = 128 form reads the anchor K-blocks twice and runs at
+// the shared-memory read limit of the MMA unit (128 B/clk) next to the TMA writes.  profiles/r02_fwd_trace.md.)
+constexpr int kAccBars = 2;
 
 struct FwdTerm {
   const int* a_cls; const int* k_seg;
@@ -213,54 +206,26 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
       for (int rt = sg.c_begin; rt < sg.c_end; ++rt, ++it) {
         const uint32_t buf = it & 1;
         MSCS_TRACE_EV(0, 0, it);
-        if constexpr (kSplitN) {
-          constexpr uint32_t idesc_h = ptx::umma_idesc_bf16(128, 128, 0, 0);
-          const int stage0 = stage; const uint32_t phase0 = phase;
-#pragma unroll 1
-          for (int h = 0; h < 2; ++h) {
-            ptx::mbar_wait(&acc_empty[buf * 2 + h], ((it >> 1) & 1) ^ 1, 112);
-            ptx::tc_fence_after();
-            if (h == 0) MSCS_TRACE_EV(0, 1, it);
-            stage = stage0; phase = phase0;
-            for (int kb = 0; kb < KB; ++kb) {
-              if (h == 0) { ptx::mbar_wait(&a_full[stage], phase, 113); ptx::tc_fence_after(); }
-              if (ptx::elect_one()) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint64_t ad = ptx::umma_desc_sw128(a_addr + stage * kBlkBytes + k * 32, 16, 1024);
-                  const uint64_t bd = ptx::umma_desc_sw128(k_addr + (kb * 2 + h) * kBlkBytes + k * 32, 16, 1024);
-                  ptx::umma_ss(tmem_base + buf * kFwdKeys + h * 128, ad, bd, idesc_h, (kb | k) != 0);
-                }
-                if (h == 1) ptx::umma_commit(&a_empty[stage]);
-              }
-              __syncwarp();
-              if (++stage == kFwdStages) { stage = 0; phase ^= 1; }
-            }
-            if (ptx::elect_one()) ptx::umma_commit(&acc_full[buf * 2 + h]);
-            __syncwarp();
-          }
-        } else {
-          ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1, 112);
+        ptx::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1, 112);
+        ptx::tc_fence_after();
+        MSCS_TRACE_EV(0, 1, it);
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::mbar_wait(&a_full[stage], phase, 113);
           ptx::tc_fence_after();
-          MSCS_TRACE_EV(0, 1, it);
-          for (int kb = 0; kb < KB; ++kb) {
-            ptx::mbar_wait(&a_full[stage], phase, 113);
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {
+          if (ptx::elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t ad = ptx::umma_desc_sw128(a_addr + stage * kBlkBytes + k * 32, 16, 1024);
-                const uint64_t bd = ptx::umma_desc_sw128(k_addr + kb * 2 * kBlkBytes + k * 32, 16, 1024);
-                ptx::umma_ss(tmem_base + buf * kFwdKeys, ad, bd, idesc, (kb | k) != 0);
-              }
-              ptx::umma_commit(&a_empty[stage]);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = ptx::umma_desc_sw128(a_addr + stage * kBlkBytes + k * 32, 16, 1024);
+              const uint64_t bd = ptx::umma_desc_sw128(k_addr + kb * 2 * kBlkBytes + k * 32, 16, 1024);
+              ptx::umma_ss(tmem_base + buf * kFwdKeys, ad, bd, idesc, (kb | k) != 0);
             }
-            __syncwarp();
-            if (++stage == kFwdStages) { stage = 0; phase ^= 1; }
+            ptx::umma_commit(&a_empty[stage]);
           }
-          if (ptx::elect_one()) ptx::umma_commit(&acc_full[buf]);
           __syncwarp();
+          if (++stage == kFwdStages) { stage = 0; phase ^= 1; }
         }
+        if (ptx::elect_one()) ptx::umma_commit(&acc_full[buf]);
+        __syncwarp();
         MSCS_TRACE_EV(0, 2, it);
       }
       if (ptx::elect_one()) ptx::umma_commit(k_empty);
@@ -298,7 +263,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
         const int tslot = warp == 4 ? 1 : (warp == 11 ? 2 : (warp == 12 ? 3 : -1));
         if (tslot > 0) MSCS_TRACE_EV(tslot, 0, it);
 #endif
-        ptx::mbar_wait(&acc_full[kSplitN ? buf * 2 + ch : buf], (it >> 1) & 1, 121);
+        ptx::mbar_wait(&acc_full[buf], (it >> 1) & 1, 121);
         ptx::tc_fence_after();
 #ifdef MSCS_TRACE
         if (tslot > 0) MSCS_TRACE_EV(tslot, 1, it);
@@ -398,7 +363,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) k_sim_fwd(const __grid_constan
 #endif
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&acc_empty[kSplitN ? buf * 2 + ch : buf]);
+        if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
         if (valid) {
           if (MODE == 0) {
             float a0, a1, b0, b1;
