@@ -288,6 +288,10 @@ class _StreamCache:
             ev = torch.cuda.Event()
             ev.record(_cur_stream())
             self.last_use[self.cur] = ev
+            # start the single-CTA generator kernel NEXT TO the persistent sweep, not next to the small sampling /
+            # gather kernels (their shared-memory carve-out would pin the SM it lands on; csrc/sim_fwd.cu)
+            _lib.check(_lib.load().mscs_sim_wait_sweeps_begin(C.c_void_p(self.side.cuda_stream)),
+                       "mscs_sim_wait_sweeps_begin")
             self._generate(self.cur ^ 1, mt_next, pos_next, words)
 
 

@@ -614,6 +614,21 @@ extern "C" int mscs_debug_fwd_timeline(float* ms_out, int max_n) {
   return n;
 }
 
+// Event recorded right before the launch of sweep 0 of the last forward of this (thread, device).  Long-running helper
+// kernels on side streams (the MT19937 stream of the NEXT call, sample.cu) are made to start behind it: a single CTA
+// that becomes resident while the small sampling / gather kernels run pins its SM to THEIR shared-memory carve-out,
+// the 215 KB CTA of the persistent sweep then cannot join it, and with 148 CTAs on 147 SMs the sweep takes until a
+// second CTA has run on some SM (measured: forward stage 0.30 instead of 0.22 ms at cfg-2, sweep 0 1.31 instead of
+// 0.79 ms in pooled cfg-5 on 8 GPUs).  Started next to the sweep's CTAs, the helper shares an SM with one of them.
+static thread_local cudaEvent_t t_sweeps_begin[64];
+extern "C" int mscs_sim_wait_sweeps_begin(void* side_stream) {
+  int dev = 0;
+  MSCS_CUDA(cudaGetDevice(&dev));
+  MSCS_CHECK_ARG(dev >= 0 && dev < 64, "device index %d out of range", dev);
+  if (t_sweeps_begin[dev]) MSCS_CUDA(cudaStreamWaitEvent((cudaStream_t)side_stream, t_sweeps_begin[dev], 0));
+  return 0;
+}
+
 extern "C" int mscs_sim_forward_sweeps(const mscs_sim_job* job, void* stream_) {
   int rc = validate_job(job);
   if (rc) return rc;
@@ -669,6 +684,13 @@ extern "C" int mscs_sim_forward_sweeps(const mscs_sim_job* job, void* stream_) {
   rc = launch_build_work(b, st);
   if (rc) return rc;
   tl_mark(st);
+  {
+    int dev = 0;
+    MSCS_CUDA(cudaGetDevice(&dev));
+    MSCS_CHECK_ARG(dev >= 0 && dev < 64, "device index %d out of range", dev);
+    if (!t_sweeps_begin[dev]) MSCS_CUDA(cudaEventCreateWithFlags(&t_sweeps_begin[dev], cudaEventDisableTiming));
+    MSCS_CUDA(cudaEventRecord(t_sweeps_begin[dev], st));
+  }
   for (int mode = 0; mode < 2; ++mode) {
     args.work = mode ? WorkTable{b.items1, b.prefix1, nitems, b.pad} : WorkTable{b.items, b.prefix, nitems, b.pad};
     switch (job->C_pad / 64) {

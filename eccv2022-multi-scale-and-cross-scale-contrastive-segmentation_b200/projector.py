@@ -54,7 +54,8 @@ class _ProjTailFn(torch.autograd.Function):
             for n, c, h, w in shapes:
                 if (h * w) % 8 != 0:
                     raise NotImplementedError("the projector-tail path needs feature planes that are a multiple of 8 pixels")
-            samples = _ops.sample_anchors(labels, [(s[2], s[3]) for s in shapes], spec)       # K1 (host-driven order)
+            # K1 (host-driven order); the generator bookkeeping + prefetch of the next call's stream run after the sweeps
+            samples, finish_rng = _ops.sample_anchors(labels, [(s[2], s[3]) for s in shapes], spec, defer_rng=True)
             d = Ws[0].shape[0]
             C_pad = (d + 63) // 64 * 64
             sets, slots, Zs, iotas = [], [], [], []
@@ -83,6 +84,7 @@ class _ProjTailFn(torch.autograd.Function):
             _lib.check(lib.mscs_gather_rows_nhwc_batch(items, S, st), "mscs_gather_rows_nhwc_batch")
             state = _ops.build_job(spec, samples, sets, single_scale=False)
             _ops.sim_forward(state)
+            finish_rng()
         holder["samples"], holder["state"] = samples, state
         ctx.state, ctx.sets, ctx.slots, ctx.Zs, ctx.iotas, ctx.shapes, ctx.S = state, sets, slots, Zs, iotas, shapes, S
         ctx.save_for_backward(*Ws)

@@ -36,6 +36,20 @@ for _ in range(K):
     step()
     k = lib.mscs_debug_fwd_timeline(buf.ctypes.data, 8)
     acc[:k] += buf[:k]
+# steady state (no synchronisation between steps, as in bench.py): stage times of THIS rank + the timeline of the last step
+from mscs_b200 import _ops
+dist.barrier(); torch.cuda.synchronize()
+_ops.TIMING = {}
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    step()
+e1.record()
+torch.cuda.synchronize()
+stage = {k: round(sum(a.elapsed_time(b) for a, b in v) / len(v), 3) for k, v in _ops.TIMING.items()}
+_ops.TIMING = None
+k = lib.mscs_debug_fwd_timeline(buf.ctypes.data, 8)
+print(f"\nrank {rank} steady: {e0.elapsed_time(e1) / 10:.3f} ms/step, stages {stage}, last step's sweeps (us) {[round(float(x) * 1e3, 1) for x in buf[:k]]}", flush=True)
 spans = np.zeros((160, 4), np.uint64)
 for mode in (0, 1):
     if lib.mscs_debug_cta_spans_fwd(spans.ctypes.data, mode) == 0:
