@@ -101,7 +101,6 @@ _SIGNATURES = {
     "mscs_sim_workspace_bytes": (C.c_size_t, [C.POINTER(SimJob)]),
     "mscs_sim_forward": (C.c_int, [C.POINTER(SimJob), C.c_void_p]),
     "mscs_sim_forward_sweeps": (C.c_int, [C.POINTER(SimJob), C.c_void_p]),
-    "mscs_sim_wait_sweeps_begin": (C.c_int, [C.c_void_p]),
     "mscs_sim_finalize": (C.c_int, [C.POINTER(SimJob), C.c_void_p]),
     "mscs_sim_backward": (C.c_int, [C.POINTER(SimJob), C.c_void_p, _PTRS, C.POINTER(C.c_int32), C.c_void_p]),
     "mscs_sim_backward_sets": (C.c_int, [C.POINTER(SimJob), C.c_void_p, _PTRS, C.POINTER(C.c_int32), C.c_uint32,

@@ -244,9 +244,16 @@ class _StreamCache:
         # stream, only after the last reader of this buffer (the selection kernel two calls ago)
         if self.last_use[which] is not None:
             self.side.wait_event(self.last_use[which])
+        if TIMING is not None:          # stage accounting (bench.py): duration of the generator kernel on the side stream
+            t0 = torch.cuda.Event(enable_timing=True)
+            t0.record(self.side)
         _lib.check(lib.mscs_mt19937_stream(mt.ctypes.data_as(C.c_void_p), pos, C.c_uint64(words),
                                            self.bufs[which].data_ptr(), C.c_void_p(self.side.cuda_stream)),
                    "mscs_mt19937_stream")
+        if TIMING is not None:
+            t1 = torch.cuda.Event(enable_timing=True)
+            t1.record(self.side)
+            TIMING.setdefault("mt_stream_side", []).append((t0, t1))
         ev = torch.cuda.Event()
         ev.record(self.side)
         self.cur, self.key, self.words, self.ready = which, (mt.tobytes(), pos), words, ev
@@ -288,10 +295,6 @@ class _StreamCache:
             ev = torch.cuda.Event()
             ev.record(_cur_stream())
             self.last_use[self.cur] = ev
-            # start the single-CTA generator kernel NEXT TO the persistent sweep, not next to the small sampling /
-            # gather kernels (their shared-memory carve-out would pin the SM it lands on; csrc/sim_fwd.cu)
-            _lib.check(_lib.load().mscs_sim_wait_sweeps_begin(C.c_void_p(self.side.cuda_stream)),
-                       "mscs_sim_wait_sweeps_begin")
             self._generate(self.cur ^ 1, mt_next, pos_next, words)
 
 

@@ -301,43 +301,48 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
   return y;
 }
 
-// Footprint: 128 threads x <= 24 registers + 5 KB of shared memory, so that the CTA fits on an SM NEXT TO a CTA of the
-// persistent tensor kernels (640 threads x 88 / 96 registers).  It runs on a side stream for up to a millisecond
-// (pooled cfg-5: 2.8 M words); as a 1024-thread CTA it could not share an SM with them, and whenever it was resident
-// at the launch of a sweep, that sweep's 148th CTA started only after another had finished (pooled cfg-5, 8 GPUs:
-// sweep 0 took 1.31 ms instead of 0.79 ms on six ranks of eight).
-constexpr int kMtThreads = 128;
-__global__ void __launch_bounds__(kMtThreads)
+// One CTA on a side stream for 0.2 ms (cfg-2) to 1 ms (pooled cfg-5: 2.8 M words).  It cannot share an SM with a CTA of
+// the persistent tensor kernels in any useful way: as a 1024-thread CTA it does not fit next to one (registers), and a
+// 128-thread form that does fit is starved of issue slots by the twenty busy warps next to it (0.75 ms at cfg-2) and
+// still loses the SM whenever it became resident under the small shared-memory carve-out of the sampling kernels.
+// Instead the persistent kernels leave ONE SM free (sim_tc.cuh: persistent_ctas()), which this kernel takes whenever
+// it starts; before that, a sweep of 148 CTAs found 147 SMs and took until a second CTA had run on one of them
+// (forward stage 0.30 instead of 0.22 ms at cfg-2; sweep 0 of pooled cfg-5 on 8 GPUs 1.31 instead of 0.79 ms).
+__global__ void __launch_bounds__(1024)
 k_mt_stream(const uint32_t* __restrict__ state, int pos, long long total, uint32_t* __restrict__ out) {
   __shared__ uint32_t buf[2][624];
   const int tid = threadIdx.x;
-  for (int i = tid; i < 624; i += kMtThreads) buf[0][i] = state[i];
+  for (int i = tid; i < 624; i += 1024) buf[0][i] = state[i];
   __syncthreads();
-  // One barrier per 624-word block.  Every thread first stores its share of the CURRENT block (raw words; tempering
-  // is left to the consumer, which touches only V of the count-1 words of a pair), then regenerates the NEXT block
-  // into the other buffer: virtual lane v < 227 owns the words v, v+227 and v+454 -- new[v] needs only the old block,
-  // new[v+227] = new[v] ^ twist(old[v+227], old[v+228]) and new[v+454] = new[v+227] ^ twist(old[v+454], old[v+455])
-  // chain inside the lane, so the three dependent phases of the textbook regeneration need no synchronisation
-  // between threads (word 623 needs new[0], which its owner recomputes).
+  // Two warp groups, one barrier per 624-word block:
+  //  * threads 0..226 regenerate the NEXT block.  Thread t owns the words t, t+227 and t+454:
+  //    new[t] needs only the old block, new[t+227] = new[t] ^ twist(old[t+227], old[t+228]) and
+  //    new[t+454] = new[t+227] ^ twist(old[t+454], old[t+455]) chain inside the thread, so the three
+  //    dependent phases of the textbook regeneration need no inter-thread synchronisation (word 623
+  //    needs new[0], which its owner recomputes);
+  //  * threads 256..879 store the CURRENT block meanwhile (one raw word each; tempering is left to
+  //    the consumer, which touches only V of the count-1 words of a pair).
   long long produced = 0;
   int first = pos, cur = 0;          // words [first, 624) of buf[cur] are the next outputs
   while (produced < total) {
     const uint32_t* c = buf[cur];
-    uint32_t* nx = buf[cur ^ 1];
-    const long long left = total - produced;
-    const int n = (int)(left < (long long)(624 - first) ? left : (long long)(624 - first));
-    for (int j = tid; j < n; j += kMtThreads) out[produced + j] = c[first + j];   // k_fy_select tempers what it uses
-    for (int v = tid; v < 227; v += kMtThreads) {
-      const uint32_t a = c[v + 397] ^ mt_twist(c[v], c[v + 1]);
-      const uint32_t b = a ^ mt_twist(c[v + 227], c[v + 228]);
-      nx[v] = a;
-      nx[v + 227] = b;
-      if (v < 169) {
-        nx[v + 454] = b ^ mt_twist(c[v + 454], c[v + 455]);
-      } else if (v == 169) {
+    if (tid < 227) {
+      uint32_t* nx = buf[cur ^ 1];
+      const uint32_t a = c[tid + 397] ^ mt_twist(c[tid], c[tid + 1]);
+      const uint32_t b = a ^ mt_twist(c[tid + 227], c[tid + 228]);
+      nx[tid] = a;
+      nx[tid + 227] = b;
+      if (tid < 169) {
+        nx[tid + 454] = b ^ mt_twist(c[tid + 454], c[tid + 455]);
+      } else if (tid == 169) {
         const uint32_t n0 = c[397] ^ mt_twist(c[0], c[1]);
         nx[623] = b ^ mt_twist(c[623], n0);
       }
+    } else if (tid >= 256) {
+      const long long left = total - produced;
+      const int n = (int)(left < (long long)(624 - first) ? left : (long long)(624 - first));
+      const int j = tid - 256;
+      if (j < n) out[produced + j] = c[first + j];      // raw state word: k_fy_select tempers what it uses
     }
     __syncthreads();
     produced += 624 - first;
@@ -568,18 +573,7 @@ extern "C" int mscs_mt19937_stream(const uint32_t* mt_state_host, int mt_pos, ui
   // the 624 state words are staged behind the stream (the buffer holds n_words + 1024 words)
   uint32_t* state_dev = draws_dev + align_up((size_t)n_words, 64);
   MSCS_CUDA(cudaMemcpyAsync(state_dev, mt_state_host, sizeof(uint32_t) * 624, cudaMemcpyHostToDevice, st));
-  // The SM this CTA lands on must keep its shared memory at the maximum carve-out: a CTA of the persistent tensor
-  // kernels (215 KB) joins it later, and an SM is not re-partitioned while a CTA is resident -- with the default
-  // (small) carve-out that SM was lost to the sweeps for as long as this kernel ran (148 CTAs on 147 SMs).
-  static thread_local int carve_dev = -1;
-  int dev_now = 0;
-  MSCS_CUDA(cudaGetDevice(&dev_now));
-  if (carve_dev != dev_now) {
-    MSCS_CUDA(cudaFuncSetAttribute(k_mt_stream, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                   (int)cudaSharedmemCarveoutMaxShared));
-    carve_dev = dev_now;
-  }
-  k_mt_stream<<<1, kMtThreads, 0, st>>>(state_dev, mt_pos, (long long)n_words, draws_dev);
+  k_mt_stream<<<1, 1024, 0, st>>>(state_dev, mt_pos, (long long)n_words, draws_dev);
   MSCS_LAUNCH_CHECK();
   return 0;
 }

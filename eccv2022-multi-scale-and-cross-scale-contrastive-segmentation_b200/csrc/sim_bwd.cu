@@ -415,7 +415,7 @@ static int launch_bwd(const BwdArgs& args, cudaStream_t st) {
   const size_t smem = bwd_smem_bytes(KB);
   if (int rc = ensure_trap_buffer()) return rc;
   MSCS_CUDA(cudaFuncSetAttribute(k_sim_bwd<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  MSCS_CUDA(launch_k(k_sim_bwd<KB>, sm_count(), kBwdThreads, smem, st, args));
+  MSCS_CUDA(launch_k(k_sim_bwd<KB>, persistent_ctas(), kBwdThreads, smem, st, args));
   MSCS_LAUNCH_CHECK();
   return 0;
 }

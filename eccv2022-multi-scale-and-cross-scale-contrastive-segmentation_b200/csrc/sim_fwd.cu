@@ -538,6 +538,17 @@ int sm_count() {
   return n > 0 ? n : 148;
 }
 
+// Grid of the persistent tensor kernels: one CTA per SM, minus `MSCS_SPARE_SMS` (default 1, read once).  The work
+// tables are cut into gridDim.x equal shares, and a CTA fills its SM (215 KB of shared memory, ~60 k registers), so a
+// single foreign CTA resident anywhere -- the MT19937 generator of the next call on its side stream (sample.cu), a
+// communication kernel of the training loop -- leaves 148 CTAs with 147 SMs and the kernel then lasts until a SECOND
+// CTA has run on one of them.  One SM left free costs 1/148 of the tensor throughput and takes that hit away.
+int persistent_ctas() {
+  static const int spare = [] { const char* e = getenv("MSCS_SPARE_SMS"); const int v = e ? atoi(e) : 1; return v < 0 ? 0 : v; }();
+  const int n = sm_count() - spare;
+  return n > 0 ? n : 1;
+}
+
 // environment switches of the tuning experiments, read ONCE per process (no getenv on the per-step path)
 struct FwdTuning { int poly, pad; bool timeline; };
 static const FwdTuning& fwd_tuning() {
@@ -562,7 +573,7 @@ static int launch_fwd_k(const FwdArgs& args, cudaStream_t st) {
     MSCS_CUDA(cudaFuncSetAttribute(k_sim_fwd<KB, MODE, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  MSCS_CUDA(launch_k(k_sim_fwd<KB, MODE, POLY>, sm_count(), kFwdThreads, smem, st, args));
+  MSCS_CUDA(launch_k(k_sim_fwd<KB, MODE, POLY>, persistent_ctas(), kFwdThreads, smem, st, args));
   MSCS_LAUNCH_CHECK();
   return 0;
 }
@@ -612,21 +623,6 @@ extern "C" int mscs_debug_fwd_timeline(float* ms_out, int max_n) {
   int n = 0;
   for (int i = 1; i < g_tl_n && n < max_n; ++i, ++n) cudaEventElapsedTime(&ms_out[n], g_tl[i - 1], g_tl[i]);
   return n;
-}
-
-// Event recorded right before the launch of sweep 0 of the last forward of this (thread, device).  Long-running helper
-// kernels on side streams (the MT19937 stream of the NEXT call, sample.cu) are made to start behind it: a single CTA
-// that becomes resident while the small sampling / gather kernels run pins its SM to THEIR shared-memory carve-out,
-// the 215 KB CTA of the persistent sweep then cannot join it, and with 148 CTAs on 147 SMs the sweep takes until a
-// second CTA has run on some SM (measured: forward stage 0.30 instead of 0.22 ms at cfg-2, sweep 0 1.31 instead of
-// 0.79 ms in pooled cfg-5 on 8 GPUs).  Started next to the sweep's CTAs, the helper shares an SM with one of them.
-static thread_local cudaEvent_t t_sweeps_begin[64];
-extern "C" int mscs_sim_wait_sweeps_begin(void* side_stream) {
-  int dev = 0;
-  MSCS_CUDA(cudaGetDevice(&dev));
-  MSCS_CHECK_ARG(dev >= 0 && dev < 64, "device index %d out of range", dev);
-  if (t_sweeps_begin[dev]) MSCS_CUDA(cudaStreamWaitEvent((cudaStream_t)side_stream, t_sweeps_begin[dev], 0));
-  return 0;
 }
 
 extern "C" int mscs_sim_forward_sweeps(const mscs_sim_job* job, void* stream_) {
@@ -684,13 +680,6 @@ extern "C" int mscs_sim_forward_sweeps(const mscs_sim_job* job, void* stream_) {
   rc = launch_build_work(b, st);
   if (rc) return rc;
   tl_mark(st);
-  {
-    int dev = 0;
-    MSCS_CUDA(cudaGetDevice(&dev));
-    MSCS_CHECK_ARG(dev >= 0 && dev < 64, "device index %d out of range", dev);
-    if (!t_sweeps_begin[dev]) MSCS_CUDA(cudaEventCreateWithFlags(&t_sweeps_begin[dev], cudaEventDisableTiming));
-    MSCS_CUDA(cudaEventRecord(t_sweeps_begin[dev], st));
-  }
   for (int mode = 0; mode < 2; ++mode) {
     args.work = mode ? WorkTable{b.items1, b.prefix1, nitems, b.pad} : WorkTable{b.items, b.prefix, nitems, b.pad};
     switch (job->C_pad / 64) {

@@ -73,6 +73,7 @@ static inline int ensure_trap_buffer() {
   return 0;
 }
 int sm_count();
+int persistent_ctas();   // grid of the persistent tensor kernels (SM count minus the spare SMs, sim_fwd.cu)
 
 // TMA tensor map for a row-major (rows, C_pad) bf16 matrix, box = {64 elements, 128 rows}, 128B swizzle
 int make_tensor_map(CUtensorMap* out, const void* base, int rows, int c_pad);

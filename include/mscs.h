@@ -242,11 +242,6 @@ int mscs_sim_forward(const mscs_sim_job* job, void* stream);
 /* the same in two halves for the pooled mode: the sweeps over this rank's anchor rows, then (after the
  * caller has all-reduced the row statistics) the finalisation over all rows */
 int mscs_sim_forward_sweeps(const mscs_sim_job* job, void* stream);
-/* makes `side_stream` wait until the device has reached the launch of sweep 0 of the calling thread's last forward on
- * the current device (no-op before the first forward).  Used to start long single-CTA helper kernels (the MT19937
- * stream of the next call) next to the persistent sweep instead of next to the small sampling / gather kernels, whose
- * shared-memory carve-out would keep the sweep's CTA off that SM. */
-int mscs_sim_wait_sweeps_begin(void* side_stream);
 int mscs_sim_finalize(const mscs_sim_job* job, void* stream);
 /* backward: dF[set] (N_set, C) fp32 += d total_loss / d unit rows * (*grad_out), for every
  * set; the caller zero-initialises dF.  grad_out is a device scalar (upstream gradient). */

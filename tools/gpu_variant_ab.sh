@@ -14,7 +14,7 @@ import json
 try:
     d=json.loads([l for l in open("gpurun_out/bench_${v}_$round.json") if l.startswith("{")][-1])
     r=d["roofline"]
-    print("$v", $round, "ms/step %.4f" % d["ms_per_step"], {k: round(x, 4) for k, x in r["stage_ms"].items()}, "fwd", r.get("fwd"), flush=True)
+    print("$v", $round, "ms/step %.4f" % d["ms_per_step"], {k: round(x, 4) for k, x in r["stage_ms"].items()}, "fwdfrac %.3f" % r["fwd"]["frac"], flush=True)
 except Exception as e:
     print("$v", $round, "FAILED", e)
 EOF
