@@ -523,12 +523,26 @@ def main():
                                      "achieved_gbs": fill_bytes / (stage_ms["zero_fill"] * 1e-3) / 1e9,
                                      "peak_gbs": pk["hbm"]}
     if args.layout == "nchw":
-        # the scatter kernel's OWN algorithmic bytes: gradient rows + unit rows read, slot maps read, and one 32-byte
-        # sector written per sampled pixel and channel (the dense zero fill is the separate entry above)
-        sc_bytes = 2 * row_bytes + 4 * sum(f.shape[0] * f.shape[2] * f.shape[3] for f in feats_h) + sum(NS) * Cdim * 32
-        roofline["scatter_hbm"] = {"kernel": "k_scatter_sectors_batch", "bytes": sc_bytes,
-                                   "achieved_gbs": sc_bytes / (stage_ms["scatter"] * 1e-3) / 1e9,
-                                   "peak_gbs": pk["hbm"], "launch_ms": stage_ms["scatter"]}
+        from mscs_b200 import _ops as _o
+        if _o._DENSE_ONE_PASS:
+            # default path: k_dx_rows (gradient rows + unit rows read, dx rows written) + k_dense_stream (slot maps and
+            # dx rows read, EVERY byte of the dense gradients written once; no memset anywhere)
+            sc_bytes = 3 * row_bytes + 4 * sum(f.shape[0] * f.shape[2] * f.shape[3] for f in feats_h) + row_bytes \
+                + dense_bytes
+            roofline["scatter_hbm"] = {"kernel": "k_dx_rows + k_dense_stream (one-pass dense-gradient writer)",
+                                       "bytes": sc_bytes, "dense_gradient_bytes_written": dense_bytes,
+                                       "achieved_gbs": sc_bytes / (stage_ms["scatter"] * 1e-3) / 1e9,
+                                       "peak_gbs": pk["hbm"], "launch_ms": stage_ms["scatter"],
+                                       "note": "pure-write stream: the measured memset rate on this part is ~4.7 TB/s; "
+                                               "peak_gbs is the copy (read + write) figure of MEASURED_PEAKS.json"}
+        else:
+            # MSCS_DENSE=0: the scatter kernel's OWN algorithmic bytes: gradient rows + unit rows read, slot maps read,
+            # one 32-byte sector written per sampled pixel and channel (the dense zero fill is the separate entry above)
+            sc_bytes = 2 * row_bytes + 4 * sum(f.shape[0] * f.shape[2] * f.shape[3] for f in feats_h) \
+                + sum(NS) * Cdim * 32
+            roofline["scatter_hbm"] = {"kernel": "k_scatter_sectors_batch", "bytes": sc_bytes,
+                                       "achieved_gbs": sc_bytes / (stage_ms["scatter"] * 1e-3) / 1e9,
+                                       "peak_gbs": pk["hbm"], "launch_ms": stage_ms["scatter"]}
         # gather: useful bytes (N*C*4 read + rows written) and the sector traffic NCHW forces (one 32 B sector per value)
         roofline["gather_hbm"] = {"kernel": "k_gather_sectors_batch", "bytes": row_bytes + sum(NS) * (Cdim * 6 + 4),
                                   "sector_bytes": sum(NS) * Cdim * 32 + sum(NS) * (Cdim * 6 + 4),

@@ -68,9 +68,9 @@ class _timed:
 def LAUNCHES_PER_STEP(num_scales, single_scale):
     """Kernels of libmscs.so launched by one forward+backward (torch fills not counted; checked against the ncu
     launch list in profiles/): K1 hist, tile-scan, plan, MT19937 stream, select (5); K2 (1); K3 row ranges,
-    work tables of both sweeps (one launch), 2 sweeps, 2 finalise kernels (6); K4 work table + backward (2);
-    scatter (1)."""
-    return 5 + 1 + 6 + 2 + 1      # gather and scatter: one launch each for all scales
+    work tables of both sweeps (one launch), 2 sweeps, finalise (5); K4 work table + backward (2);
+    normalisation backward of the rows + one-pass dense writer (2)."""
+    return 5 + 1 + 5 + 2 + 2      # gather and scatter: one launch each for all scales
 
 
 @dataclass

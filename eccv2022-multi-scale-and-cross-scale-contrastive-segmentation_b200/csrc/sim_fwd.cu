@@ -404,6 +404,8 @@ __global__ void __launch_bounds__(256) k_row_ranges(const __grid_constant__ Rang
   pdl_trigger();
   pdl_wait();
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < MSCS_MAX_TERMS) a.fin_acc[threadIdx.x] = 0.0;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == MSCS_MAX_TERMS)      // the finalise kernel's ticket (simt.cu)
+    *reinterpret_cast<unsigned*>(reinterpret_cast<char*>(a.fin_acc) + 1024) = 0u;
   const RangeTerm& t = a.t[blockIdx.y];
   const int r = blockIdx.x * 256 + threadIdx.x;
   const int tN1 = t.n1_dev ? *t.n1_dev : t.N1;

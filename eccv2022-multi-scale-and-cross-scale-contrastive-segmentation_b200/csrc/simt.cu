@@ -18,49 +18,55 @@ struct FinArgs { FinTerm t[MSCS_MAX_TERMS]; int num_terms; float* term_loss; flo
 
 // loss = mean_i(-pos_i / div_i)  (V2.py:187-188, _ms.py:148-156); coefficients for K4.
 // grid = (row chunks, terms): per-row work is two dependent loads deep, so it is spread over many CTAs;
-// the per-term sums are reduced in fp64 (order-insensitive to far below fp32 resolution).
-__global__ void __launch_bounds__(256) k_finalize_rows(const __grid_constant__ FinArgs a, double* acc) {
+// the per-term sums are reduced in fp64 (order-insensitive to far below fp32 resolution).  The LAST block to finish
+// (ticket counter next to the accumulators) turns the sums into the term losses and the weighted total: one launch
+// less on the critical path between the positive sweep and the backward.
+__global__ void __launch_bounds__(256) k_finalize(const __grid_constant__ FinArgs a, double* acc, unsigned* ticket) {
   pdl_trigger();
   pdl_wait();
   const FinTerm& t = a.t[blockIdx.y];
   __shared__ double red[8];
+  __shared__ bool last;
   double part = 0.0;
   const int base = blockIdx.x * 1024;
   const int tN1 = t.n1_dev ? *t.n1_dev : t.N1;
-  if (base >= tN1) return;
+  if (base < tN1) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int i = base + k * 256 + threadIdx.x;
-    if (i < tN1) {
-      const int y = t.a_cls[i];
-      const int P = t.k_seg[y + 1] - t.k_seg[y] - (t.self_mask ? 1 : 0);
-      // single-scale: 0/0 -> NaN exactly like the reference; cross-scale: divisor max(P,1)
-      const float div = t.self_mask ? (float)P : (float)max(P, 1);
-      part += (double)(-t.pos[i] / div);
-      const float invd = 1.f / (div * (float)tN1);
-      t.coef_s[i] = t.ssum[i] * invd;
-      t.coef_pn[i] = t.neg[i] * invd;
+    for (int k = 0; k < 4; ++k) {
+      const int i = base + k * 256 + threadIdx.x;
+      if (i < tN1) {
+        const int y = t.a_cls[i];
+        const int P = t.k_seg[y + 1] - t.k_seg[y] - (t.self_mask ? 1 : 0);
+        // single-scale: 0/0 -> NaN exactly like the reference; cross-scale: divisor max(P,1)
+        const float div = t.self_mask ? (float)P : (float)max(P, 1);
+        part += (double)(-t.pos[i] / div);
+        const float invd = 1.f / (div * (float)tN1);
+        t.coef_s[i] = t.ssum[i] * invd;
+        t.coef_pn[i] = t.neg[i] * invd;
+      }
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int w = 0; w < 8; ++w) s += red[w];
-    atomicAdd(&acc[blockIdx.y], s);
+    if (base < tN1) {
+      double s = 0.0;
+      for (int w = 0; w < 8; ++w) s += red[w];
+      atomicAdd(&acc[blockIdx.y], s);
+    }
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
   }
-}
-
-__global__ void k_finalize_total(const __grid_constant__ FinArgs a, const double* acc) {
-  pdl_trigger();
-  pdl_wait();
-  if (threadIdx.x != 0) return;
+  __syncthreads();
+  if (!last || threadIdx.x != 0) return;
+  __threadfence();
   double total = 0.0;
   bool bad = false;
   for (int ti = 0; ti < a.num_terms; ++ti) {
-    const float l = (float)(acc[ti] / (double)(a.t[ti].n1_dev ? *a.t[ti].n1_dev : a.t[ti].N1));
+    const double sum = *reinterpret_cast<volatile double*>(&acc[ti]);
+    const float l = (float)(sum / (double)(a.t[ti].n1_dev ? *a.t[ti].n1_dev : a.t[ti].N1));
     a.term_loss[ti] = l;
     bad = bad || !isfinite(l);
     total += (double)a.t[ti].weight * (double)l;
@@ -72,8 +78,9 @@ __global__ void k_finalize_total(const __grid_constant__ FinArgs a, const double
   a.total_loss[1] = (bad || !isfinite((float)total)) ? 1.f : 0.f;
 }
 
-// job->work: the first 4096 bytes are reserved for these accumulators (zeroed by k_row_ranges, the first kernel of
-// the forward sweeps: no memset between the kernels of the chain)
+// job->work: the first 4096 bytes are reserved for these accumulators and the ticket (zeroed by k_row_ranges, the first
+// kernel of the forward sweeps: no memset between the kernels of the chain)
+constexpr int kFinTicketOffset = 1024;      // bytes: behind the MSCS_MAX_TERMS doubles
 int launch_finalize(const mscs_sim_job* job, cudaStream_t st, bool zero_acc) {
   FinArgs a{};
   a.num_terms = job->num_terms; a.term_loss = job->term_loss; a.total_loss = job->total_loss;
@@ -86,10 +93,9 @@ int launch_finalize(const mscs_sim_job* job, cudaStream_t st, bool zero_acc) {
     if (m.N1 > maxN) maxN = m.N1;
   }
   double* acc = (double*)job->work;
-  if (zero_acc) MSCS_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * MSCS_MAX_TERMS, st));
-  MSCS_CUDA(launch_k(k_finalize_rows, dim3(ceil_div(maxN, 1024), job->num_terms), 256, 0, st, a, acc));
-  MSCS_LAUNCH_CHECK();
-  MSCS_CUDA(launch_k(k_finalize_total, 1, 32, 0, st, a, (const double*)acc));
+  unsigned* ticket = (unsigned*)((char*)job->work + kFinTicketOffset);
+  if (zero_acc) MSCS_CUDA(cudaMemsetAsync(acc, 0, kFinTicketOffset + sizeof(unsigned), st));
+  MSCS_CUDA(launch_k(k_finalize, dim3(ceil_div(maxN, 1024), job->num_terms), 256, 0, st, a, acc, ticket));
   MSCS_LAUNCH_CHECK();
   return 0;
 }
