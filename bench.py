@@ -290,11 +290,15 @@ def measure_pooled(dev, rank, world, dist, steps=10, warmup=3):
         from mscs_b200 import _ops
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sync()
-        _ops.TIMING = {}
         e0.record()
         for _ in range(steps):
             loss = one()
         e1.record()
+        sync()
+        # stage breakdown: a second pass (the stage events are not part of the product path and cost ~50 us per step)
+        _ops.TIMING, _ops.TIMING_ALL = {}, True
+        for _ in range(max(3, steps // 2)):
+            one()
         sync()
         mod.stage_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in _ops.TIMING.items()}
         _ops.TIMING = None
@@ -410,15 +414,25 @@ def main():
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # per-stage CUDA events are recorded INSIDE the timed region (on the launching stream): the kernel durations
-    # behind the roofline are those of the sustained loop, not of a cold burst
-    _ops.TIMING = {}
+    # the DOMINANT kernel (k_sim_bwd) is bracketed by CUDA events INSIDE the timed region, on the launching stream: the
+    # duration behind the roofline is that of the sustained loop, not of a cold burst.  The other stages are timed in a
+    # second pass right after it: a full set of stage events costs ~50 us per step (16 records, which also sit between
+    # kernels that otherwise overlap through programmatic dependent launch), and that is not part of the product path.
+    _ops.TIMING, _ops.TIMING_ALL = {}, False
     e0.record()
     for i in range(args.steps):
         loss = step(labels, feats, 100 + i)
     e1.record()
     barrier()
     stage_ms = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in _ops.TIMING.items()}
+    _ops.TIMING, _ops.TIMING_ALL = {}, True
+    n_stage = max(3, min(args.steps, 50))
+    for i in range(n_stage):
+        step(labels, feats, 5000 + i)
+    barrier()
+    stage_all = {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in _ops.TIMING.items()}
+    stage_all["sim_bwd_second_pass"] = stage_all["sim_bwd"]
+    stage_ms = {**stage_all, **stage_ms}        # sim_bwd: from the timed region
     _ops.TIMING = None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     clocks = sampler.stop() if rank == 0 else None
@@ -512,7 +526,10 @@ def main():
                                                                                * 1e-3) / 1e12,
                                        "frac": (fwd_flops + bwd_flops) / ((stage_ms["sim_fwd"] + stage_ms["sim_bwd"])
                                                                           * 1e-3) / 1e12 / pk["tflops"]},
-                "stage_ms": stage_ms}
+                "stage_ms": stage_ms,
+                "stage_ms_note": "sim_bwd: CUDA events inside the timed region; the other stages: a second pass of %d "
+                                 "steps right after it with the full set of stage events (not in the timed region: "
+                                 "they cost ~50 us per step)" % n_stage}
     dense_bytes = sum(f.numel() * 4 for f in feats_h)
     row_bytes = sum(NS) * Cdim * 4
     if "zero_fill" in stage_ms:

@@ -55,6 +55,18 @@ class SimJob(C.Structure):
                 ("work", C.c_void_p), ("total_out", C.c_void_p)]
 
 
+class ForwardChainArgs(C.Structure):
+    """mscs_forward_chain_args (include/mscs.h)."""
+    _fields_ = [("cfg", C.c_void_p), ("labels", C.c_void_p), ("labels_i16", C.c_int32), ("v_cap", C.c_int32),
+                ("workspace", C.c_void_p), ("plan_dev", C.c_void_p), ("draws", C.c_void_p), ("wait_event", C.c_void_p),
+                ("idx_ref", C.c_void_p), ("pair_ref", C.c_void_p), ("pix", C.c_void_p), ("cls", C.c_void_p),
+                ("seg", C.c_void_p), ("slot", C.c_void_p),
+                ("fill_ptrs", C.c_void_p), ("fill_values", C.c_void_p), ("fill_bytes", C.c_void_p), ("n_fill", C.c_int32),
+                ("main_zero_ptr", C.c_void_p), ("main_zero_bytes", C.c_size_t),
+                ("gather_kind", C.c_int32), ("gather_items", C.c_void_p), ("job", C.c_void_p),
+                ("stage_events", C.c_void_p * 5)]
+
+
 _PTRS = C.POINTER(C.c_void_p)
 _SIGNATURES = {
     "mscs_version": (C.c_char_p, []),
@@ -100,6 +112,9 @@ _SIGNATURES = {
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "mscs_sim_workspace_bytes": (C.c_size_t, [C.POINTER(SimJob)]),
     "mscs_sim_forward": (C.c_int, [C.POINTER(SimJob), C.c_void_p]),
+    "mscs_forward_chain": (C.c_int, [C.POINTER(ForwardChainArgs), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mscs_backward_chain": (C.c_int, [C.POINTER(SimJob), C.c_void_p, _PTRS, C.POINTER(C.c_int32), C.c_void_p,
+                                      C.POINTER(C.c_int32), C.c_int, C.c_void_p, _PTRS, C.c_void_p]),
     "mscs_sim_forward_sweeps": (C.c_int, [C.POINTER(SimJob), C.c_void_p]),
     "mscs_sim_finalize": (C.c_int, [C.POINTER(SimJob), C.c_void_p]),
     "mscs_sim_backward": (C.c_int, [C.POINTER(SimJob), C.c_void_p, _PTRS, C.POINTER(C.c_int32), C.c_void_p]),

@@ -33,6 +33,10 @@ _GATHER_TMA = os.environ.get("MSCS_GATHER", "lanes") == "tma"
 
 # optional per-stage device timing (bench.py): {stage: [(start_event, end_event), ...]} or None
 TIMING = None
+# stage accounting level: True = every stage (16 extra event records per step: ~50 us of step time at cfg-2, the
+# records also sit between kernels that otherwise overlap through programmatic dependent launch); False = only the
+# dominant kernel (`sim_bwd`, 2 events) -- what bench.py uses inside its timed region
+TIMING_ALL = True
 # optional host-side accounting (tools/stage_times.py): seconds the host spent blocked in the plan fetch, per call
 HOST_WAIT = None
 # optional host-side segment accounting (tools/stage_times.py): {segment: seconds}
@@ -54,12 +58,13 @@ class _timed:
         self.name = name
 
     def __enter__(self):
-        if TIMING is not None:
+        self.on = TIMING is not None and (TIMING_ALL or self.name == "sim_bwd")
+        if self.on:
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e0.record()
 
     def __exit__(self, *exc):
-        if TIMING is not None:
+        if self.on:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
             TIMING.setdefault(self.name, []).append((self.e0, e1))
@@ -232,6 +237,7 @@ class _StreamCache:
         self.ready = None        # event: buffer `cur` complete
         self.last_use = [None, None]   # event: last main-stream reader of each buffer
         self.lock = threading.Lock()
+        self.pending = None      # deferred prefetch request (mt, pos, words), see release_and_prefetch
         self.copy = torch.cuda.Stream(device=dev)      # read-back of the generator state (see state_after)
 
     def _generate(self, which, mt, pos, words):
@@ -244,13 +250,14 @@ class _StreamCache:
         # stream, only after the last reader of this buffer (the selection kernel two calls ago)
         if self.last_use[which] is not None:
             self.side.wait_event(self.last_use[which])
-        if TIMING is not None:          # stage accounting (bench.py): duration of the generator kernel on the side stream
+        timed = TIMING is not None and TIMING_ALL
+        if timed:          # stage accounting (bench.py): duration of the generator kernel on the side stream
             t0 = torch.cuda.Event(enable_timing=True)
             t0.record(self.side)
         _lib.check(lib.mscs_mt19937_stream(mt.ctypes.data_as(C.c_void_p), pos, C.c_uint64(words),
                                            self.bufs[which].data_ptr(), C.c_void_p(self.side.cuda_stream)),
                    "mscs_mt19937_stream")
-        if TIMING is not None:
+        if timed:
             t1 = torch.cuda.Event(enable_timing=True)
             t1.record(self.side)
             TIMING.setdefault("mt_stream_side", []).append((t0, t1))
@@ -260,10 +267,20 @@ class _StreamCache:
 
     def acquire(self, mt, pos, words):
         """Buffer holding >= words outputs from (mt,pos); the current stream is made to wait for it."""
+        self.flush()
         with self.lock:
             if self.key != (mt.tobytes(), pos) or self.words < words:
                 self._generate(self.cur ^ 1, mt, pos, words)
             _cur_stream().wait_event(self.ready)
+            return self.bufs[self.cur]
+
+    def acquire_nowait(self, mt, pos, words):
+        """As acquire, but the caller orders its consumer behind `self.ready` itself (mscs_forward_chain makes the
+        sampling stream wait for it)."""
+        self.flush()
+        with self.lock:
+            if self.key != (mt.tobytes(), pos) or self.words < words:
+                self._generate(self.cur ^ 1, mt, pos, words)
             return self.bufs[self.cur]
 
     def state_after(self, mt, pos, total):
@@ -288,14 +305,30 @@ class _StreamCache:
                        "mscs_read_to_host")
         return host, newpos
 
-    def release_and_prefetch(self, mt_next, pos_next, words):
+    def release_and_prefetch(self, mt_next, pos_next, words, defer=False):
+        """defer: only note the request; `flush` launches it.  The forward of a training step defers: between the plan
+        fetch and the launch of the backward the host races ~0.35 ms of queued GPU work (cfg-2), and the generator
+        launch (state upload, kernel, events: ~40 us) can as well follow the backward's launches."""
         if _NO_PREFETCH:      # experiment switch: regenerate inline at the next call
             return
         with self.lock:
             ev = torch.cuda.Event()
             ev.record(_cur_stream())
             self.last_use[self.cur] = ev
-            self._generate(self.cur ^ 1, mt_next, pos_next, words)
+            if defer:
+                self.pending = (mt_next, pos_next, words)
+            else:
+                self.pending = None
+                self._generate(self.cur ^ 1, mt_next, pos_next, words)
+
+    def flush(self):
+        """Launches a deferred prefetch, if any (after the backward has been enqueued; the next acquire does it too)."""
+        if self.pending is None:
+            return
+        with self.lock:
+            p, self.pending = self.pending, None
+            if p is not None:
+                self._generate(self.cur ^ 1, *p)
 
 
 _stream_caches = {}
@@ -768,22 +801,23 @@ class _StepPlan:
             t.self_mask, t.need_dk, t.temperature, t.weight, t.a_set, t.k_set = int(self_mask), int(need_dk), tau, \
                 weight, a, k
         self.work_bytes = lib.mscs_sim_workspace_bytes(C.byref(job))
+        self.dF_off, off = [], 0
+        for s in range(S):
+            self.dF_off.append(off)
+            off += (self.Ncap[s] + 128 * world) * self.C_pad      # slack: `world` 128-aligned row blocks (pooled mode)
+        self.dF_n = off
         # single-process calls: ONE allocation per forward; byte offsets (256-aligned) of its parts
         self.slot_sizes = [shp[0] * shp[2] * shp[3] if (shp[2] * shp[3]) % 8 == 0 else 0 for shp in feat_shapes]
         parts = [("ws", self.ws_bytes), ("plan", S * C.sizeof(_lib.ScalePlan)), ("work", self.work_bytes),
                  ("stats", 4 * self.stats_n), ("misc", 4 * self.misc_n), ("fslab", 4 * self.fslab_n),
-                 ("islab", 4 * self.islab_n), ("slot", 4 * sum(self.slot_sizes)), ("bslab", 2 * self.bslab_n)]
+                 ("islab", 4 * self.islab_n), ("slot", 4 * sum(self.slot_sizes)), ("bslab", 2 * self.bslab_n),
+                 ("dF", 4 * self.dF_n)]
         self.slab_off, off = {}, 0
         for name, nbytes in parts:
             self.slab_off[name] = off
             off += (nbytes + 255) // 256 * 256
         self.slab_bytes = off
         self.ws_pool = []           # reusable _Workspace objects of the single-process fast path
-        self.dF_off, off = [], 0
-        for s in range(S):
-            self.dF_off.append(off)
-            off += (self.Ncap[s] + 128 * world) * self.C_pad      # slack: `world` 128-aligned row blocks (pooled mode)
-        self.dF_n = off
         # pooled mode: layout of the exchange slab (identical on every rank): barrier flags, then per step parity the
         # operand matrices (bf16), the row statistics and the gradient rows.  Two parities: a rank that runs ahead
         # writes the next step's rows while a slower rank still reads this step's.
@@ -898,9 +932,16 @@ class _Workspace:
         if sp.nhwc:                 # row gather / scatter: no slot maps
             self.slots = [None] * S
         self.sarr = _lib.ptr_array([x.data_ptr() if x is not None else 0 for x in self.slots])
+        # byte fills in front of the sampling chain: row statistics (0), slot maps (-1)
+        self.dF_ptr = sb + so["dF"]          # gradient-row accumulators of the backward (cleared by the forward chain)
         self.fill_ptrs = _lib.ptr_array([sb + so["stats"], sb + so["slot"]])
         self.fill_vals = (C.c_int32 * 2)(0, 0xFF)
         self.fill_bytes = (C.c_size_t * 2)(4 * sp.stats_n, 0 if sp.nhwc else 4 * sum(sp.slot_sizes))
+        # the backward's argument structures (one C call, csrc/step.cu): everything but the dense-gradient addresses
+        self.bw_ptrs = _lib.ptr_array([self.dF_ptr + 4 * sp.dF_off[s] for s in range(S)] + [0] * (_lib.MAX_SCALES - S))
+        self.bw_lds = (C.c_int32 * _lib.MAX_SCALES)(*([sp.C_pad] * S + [0] * (_lib.MAX_SCALES - S)))
+        self.bw_items = (_lib.ScatterItem * S)()
+        self.bw_rows = (C.c_int32 * S)()
         plan_sz = C.sizeof(_lib.ScalePlan)
         self.job_fwd, self.job_bwd = _lib.SimJob(), _lib.SimJob()
         for job in (self.job_fwd, self.job_bwd):
@@ -923,9 +964,26 @@ class _Workspace:
             it.n_rows_dev = self.plan_dev + s * plan_sz + 8
             it.anc_bf16, it.anc_f32 = self.bbase + 2 * sp.boff[s], self.fbase + 4 * sp.foff[s][0]
             it.inv_norm = self.fbase + 4 * sp.foff[s][1]
+        if not sp.nhwc:
+            for s in range(S):
+                n, Cc, h, w = sp.feat_shapes[s]
+                it = self.bw_items[s]
+                it.dF, it.ldF = self.dF_ptr + 4 * sp.dF_off[s], sp.C_pad
+                it.anc_f32, it.inv_norm = self.fbase + 4 * sp.foff[s][0], self.fbase + 4 * sp.foff[s][1]
+                it.slot, it.n, it.C, it.plane = self.slots[s].data_ptr(), n, Cc, h * w
         self.plan = (_lib.ScalePlan * S)()
         self.last_stream = None
         self.philox = None          # stream buffer of the opt-in counter-based sampler (allocated on first use)
+        # the whole forward as ONE C call (csrc/step.cu): every field that depends only on addresses, filled once
+        ch = self.chain = _lib.ForwardChainArgs()
+        ch.cfg, ch.v_cap, ch.workspace, ch.plan_dev = C.addressof(sp.cfg), sp.v_cap, self.ws, self.plan_dev
+        ch.idx_ref, ch.pair_ref, ch.pix, ch.cls, ch.seg = (C.addressof(a) for a in self.arrs)
+        ch.slot = C.addressof(self.sarr)
+        ch.fill_ptrs, ch.fill_values = C.addressof(self.fill_ptrs), C.addressof(self.fill_vals)
+        ch.fill_bytes, ch.n_fill = C.addressof(self.fill_bytes), 2
+        ch.main_zero_ptr = self.dF_ptr
+        ch.gather_kind = 1 if sp.nhwc else (2 if _GATHER_TMA else 0)
+        ch.gather_items, ch.job = C.addressof(self.gitems), C.addressof(self.job_fwd)
 
 
 class _StepState:
@@ -954,9 +1012,9 @@ def run_forward(sp, labels, feats32, needs, comm=None, philox=None):
     return _run_forward_general(sp, labels, feats32, needs)
 
 
-def _finish_rng(sp, dev, mt, pos, total):
+def _finish_rng(sp, dev, mt, pos, total, defer=False):
     """Host-side generator bookkeeping, off the GPU's critical path: publish the state the reference's randperm
-    calls would leave and start producing the next call's stream."""
+    calls would leave and start producing the next call's stream (defer: the launch follows the backward's)."""
     nxt = _stream_cache(dev).state_after(mt, pos, total)
     if nxt is None:
         mt2, pos2 = torch_mt_advance(mt, pos, total)
@@ -964,7 +1022,7 @@ def _finish_rng(sp, dev, mt, pos, total):
         mt2, pos2 = nxt
         if total > 0:
             _publish_mt_state(mt2, pos2)
-    _stream_cache(dev).release_and_prefetch(mt2, pos2, sp.max_draws + _MT_N)
+    _stream_cache(dev).release_and_prefetch(mt2, pos2, sp.max_draws + _MT_N, defer)
 
 
 def _run_forward_fast(sp, labels, feats32, needs, philox=None):
@@ -991,66 +1049,63 @@ def _run_forward_fast(sp, labels, feats32, needs, philox=None):
         job.total_out = total_t.data_ptr()
     # the small, latency-bound sampling kernels run on a high-priority stream (see _hp_stream)
     hp = _hp_stream(dev) if _USE_HP_STREAM else None
-    st_s = st
-    if hp is not None:
-        hp.wait_stream(cur)
-        st_s = C.c_void_p(hp.cuda_stream)
-    with _timed("sample"):
-        # MT19937 output stream of this call (normally produced ahead of time during the previous step): looked up
-        # first, so that nothing but kernels sits between the launches of the sampling chain
-        if philox is None:
-            mt, pos = torch_mt_state()
-            draws_ptr = _stream_cache(dev).acquire(mt, pos, sp.max_draws + _MT_N).data_ptr()
-            if hp is not None:
-                hp.wait_event(_stream_cache(dev).ready)
-        else:       # counter-based stream of this call: one small kernel in front of the chain, no generator state
-            if e.philox is None:
-                e.philox = torch.empty((sp.max_draws + 3) // 4 * 4 + 4, dtype=torch.int32, device=dev)
-            draws_ptr = e.philox.data_ptr()
-            _lib.check(lib.mscs_philox_stream(int(philox[0]) & (2 ** 64 - 1), int(philox[1]), sp.max_draws, draws_ptr,
-                                              st_s), "mscs_philox_stream")
-        _t = _seg("fwd: rng state + stream acquire", _t)
-        # dense gradients + gradient rows: pre-zeroed on a side stream, sampled sectors rewritten by the backward
-        # (default: the backward writes them in one streaming pass instead, see _DENSE_ONE_PASS and gather.cu).
-        # Started here, next to the small sampling kernels: the fill (535 MB at cfg-2) costs ~70 us of step time
-        # WHEREVER it runs (measured next to the sampling kernels, under the forward, under the backward, and as a
-        # device-to-device copy from a persistent zero buffer) -- memset and D2D copies run on the SMs.
-        gradbufs = _GradBuffers(feats32, needs, sp.nhwc, sp.dF_n) \
-            if (any(needs) and (sp.nhwc or not _DENSE_ONE_PASS)) else None
-        if gradbufs is not None:
-            gradbufs.start_fill()
-        _t = _seg("fwd: grad buffers", _t)
-        # workspace fills, then hist -> tile scan -> plan -> select back to back (programmatic dependent launches);
-        # the plan records travel to the host on a private stream (mscs_plan_fetch_begin)
-        _lib.check(lib.mscs_fill_bytes(e.fill_ptrs, e.fill_vals, e.fill_bytes, 2, st_s), "mscs_fill_bytes")
-        fn, fname = _plan_entry(lib, labels)
-        _lib.check(fn(C.byref(sp.cfg), labels.data_ptr(), e.ws, e.plan_dev, st_s), fname)
-        _lib.check(lib.mscs_plan_fetch_begin(e.plan_dev, S, st_s), "mscs_plan_fetch_begin")
-        _lib.check(lib.mscs_sample_select_async(C.byref(sp.cfg), e.plan_dev, sp.v_cap, e.ws, draws_ptr, *e.arrs,
-                                                e.sarr, st_s), "mscs_sample_select_async")
-        _t = _seg("fwd: workspace + sampling kernels", _t)
+    st_s = C.c_void_p(hp.cuda_stream) if hp is not None else st
+    ch = e.chain
+    # MT19937 output stream of this call (normally produced ahead of time during the previous step): looked up
+    # first, so that nothing but kernels sits between the launches of the sampling chain
+    if philox is None:
+        mt, pos = torch_mt_state()
+        ch.draws = _stream_cache(dev).acquire_nowait(mt, pos, sp.max_draws + _MT_N).data_ptr()
+        ch.wait_event = _stream_cache(dev).ready.cuda_event
+    else:       # counter-based stream of this call: one small kernel in front of the chain, no generator state
+        if e.philox is None:
+            e.philox = torch.empty((sp.max_draws + 3) // 4 * 4 + 4, dtype=torch.int32, device=dev)
         if hp is not None:
-            cur.wait_stream(hp)
-    with _timed("gather"):
-        for s in range(S):
-            e.gitems[s].feat = feats32[s].data_ptr()
-        if sp.nhwc:
-            _lib.check(lib.mscs_gather_rows_nhwc_batch(e.gitems, S, st), "mscs_gather_rows_nhwc_batch")
-        else:
-            if _GATHER_TMA:
-                _lib.check(lib.mscs_gather_normalize_tma_batch(e.gitems, S, st), "mscs_gather_normalize_tma_batch")
-            else:
-                _lib.check(lib.mscs_gather_normalize_sectors_batch(e.gitems, S, st),
-                           "mscs_gather_normalize_sectors_batch")
-    with _timed("sim_fwd"):
-        _lib.check(lib.mscs_sim_forward(C.byref(e.job_fwd), st), "mscs_sim_forward")
-    _t = _seg("fwd: select + gather + sim_forward", _t)
+            hp.wait_stream(cur)
+        ch.draws, ch.wait_event = e.philox.data_ptr(), None
+        _lib.check(lib.mscs_philox_stream(int(philox[0]) & (2 ** 64 - 1), int(philox[1]), sp.max_draws, ch.draws,
+                                          st_s), "mscs_philox_stream")
+    _t = _seg("fwd: rng state + stream acquire", _t)
+    # dense gradients + gradient rows: pre-zeroed on a side stream, sampled sectors rewritten by the backward
+    # (default: the backward writes them in one streaming pass instead, see _DENSE_ONE_PASS and gather.cu).
+    # Started here, next to the small sampling kernels: the fill (535 MB at cfg-2) costs ~70 us of step time
+    # WHEREVER it runs (measured next to the sampling kernels, under the forward, under the backward, and as a
+    # device-to-device copy from a persistent zero buffer) -- memset and D2D copies run on the SMs.
+    gradbufs = _GradBuffers(feats32, needs, sp.nhwc, sp.dF_n) \
+        if (any(needs) and (sp.nhwc or not _DENSE_ONE_PASS)) else None
+    if gradbufs is not None:
+        gradbufs.start_fill()
+    _t = _seg("fwd: grad buffers", _t)
+    ch.labels, ch.labels_i16 = labels.data_ptr(), int(labels.dtype == torch.int16)
+    for s in range(S):
+        e.gitems[s].feat = feats32[s].data_ptr()
+    # gradient-row accumulators of the backward: cleared by the chain on the caller's stream, next to the sampling
+    # kernels, when the one-pass dense writer will be used (otherwise they come pre-zeroed with the dense gradients, or
+    # no gradient is wanted at all)
+    dF_in_ws = any(needs) and gradbufs is None
+    ch.main_zero_bytes = 4 * sp.dF_n if dF_in_ws else 0
+    evs = None
+    if TIMING is not None and TIMING_ALL:      # stage accounting (bench.py): five events recorded INSIDE the chain
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        for i, ev in enumerate(evs):
+            ev.record()         # creates the CUDA event; the chain records it again at its stage boundary
+            ch.stage_events[i] = ev.cuda_event
+    else:
+        for i in range(5):
+            ch.stage_events[i] = None
     if HOST_WAIT is not None:
         _t0 = time.perf_counter()
     plan = e.plan
-    _lib.check(lib.mscs_plan_fetch_end(plan, S), "mscs_plan_fetch_end")       # the host wait (plan records only)
+    # ONE call: fills, hist -> tile scan -> plan -> select on the sampling stream (programmatic dependent launches; the
+    # plan records travel to the host on a private stream), gather + similarity forward on the caller's stream, all
+    # driven by the DEVICE plan records, then the one host wait of the forward pass (plan records only)
+    _lib.check(lib.mscs_forward_chain(C.byref(ch), st_s, st, plan), "mscs_forward_chain")
     if HOST_WAIT is not None:
         HOST_WAIT.append(time.perf_counter() - _t0)
+    if evs is not None:
+        TIMING.setdefault("sample", []).append((evs[0], evs[1]))
+        TIMING.setdefault("gather", []).append((evs[2], evs[3]))
+        TIMING.setdefault("sim_fwd", []).append((evs[3], evs[4]))
     _t = time.perf_counter() if HOST_SEG is not None else 0.0
     state = _StepState()
     state.sp, state.entry = sp, e          # (from here on an exception returns the workspace to the pool)
@@ -1063,12 +1118,15 @@ def _run_forward_fast(sp, labels, feats32, needs, philox=None):
         t.N1, t.N2 = samples[a].N, samples[k].N
     _t = _seg("fwd: after wait", _t)
     if philox is None:
-        _finish_rng(sp, dev, mt, pos, total)
+        _finish_rng(sp, dev, mt, pos, total, defer=any(needs))
     _t = _seg("fwd: rng advance + prefetch", _t)
     state.job, state.samples, state.gradbufs, state.slots = e.job_bwd, samples, gradbufs, e.slots
     state.keep, state.stats, state.fslab = out, e.stats, e.fslab
     state.term_loss, state.total, state.scalars = out[:nt], total_t, out
     state.num_ms, state.cs_logged, state.comm = S, sp.cs_logged, None
+    state.dF_ws = e.dF_ptr if dF_in_ws else None
+    for s in range(S):
+        e.bw_rows[s] = samples[s].N
     return state
 
 
@@ -1362,25 +1420,85 @@ def run_backward(state, grad_out, needs, shapes, dtypes):
     st = _stream()
     if state.comm is not None:
         return _run_backward_pooled(state, grad_out, needs, shapes, dtypes)
-    # gradient rows: zeroed ahead of time together with the dense gradients (side stream, during the forward)
-    dF = None
+    # gradient-row accumulators: cleared during the forward -- inside the workspace by the sampling chain's fills
+    # (default), or together with the pre-zeroed dense gradients on the side stream; a second backward through the
+    # same graph takes a fresh zeroed buffer
+    dF, base, e = None, None, getattr(state, "entry", None)
+    first = not getattr(state, "bwd_done", False)
+    state.bwd_done = True
     if state.gradbufs is not None:
         dF = state.gradbufs.take_dF()
         if dF is not None:
             _cur_stream().wait_event(state.gradbufs.ready)
-    if dF is None:          # second backward through the same graph, or no pre-zeroed buffers
-        dF = torch.zeros(sp.dF_n, dtype=torch.float32, device=dev)
-    base = dF.data_ptr()
-    ptrs = [0] * _lib.MAX_SCALES
-    lds = (C.c_int32 * _lib.MAX_SCALES)()
-    for s in range(S):
-        ptrs[s], lds[s] = base + 4 * sp.dF_off[s], sp.C_pad
-    g = grad_out.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
-    with _timed("sim_bwd"):
-        _lib.check(lib.mscs_sim_backward(C.byref(state.job), g.data_ptr(), _lib.ptr_array(ptrs), lds, st),
-                   "mscs_sim_backward")
+    elif first and getattr(state, "dF_ws", None):
+        base = state.dF_ws
+    in_ws = base is not None
+    if not in_ws:
+        if dF is None:
+            dF = torch.zeros(sp.dF_n, dtype=torch.float32, device=dev)
+        base = dF.data_ptr()
+    if in_ws:
+        ptrs_arr, lds = e.bw_ptrs, e.bw_lds
+        ptrs = [base + 4 * sp.dF_off[s] for s in range(S)]
+    else:
+        ptrs = [0] * _lib.MAX_SCALES
+        lds = (C.c_int32 * _lib.MAX_SCALES)()
+        for s in range(S):
+            ptrs[s], lds[s] = base + 4 * sp.dF_off[s], sp.C_pad
+        ptrs_arr = _lib.ptr_array(ptrs)
+    if grad_out.dtype == torch.float32 and grad_out.device == dev and grad_out.is_contiguous():
+        g = grad_out                      # (only its address is used)
+    else:
+        g = grad_out.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
     grads = []
     fbase = state.fslab.data_ptr()
+    dense = (not sp.nhwc) and state.gradbufs is None and \
+        all((not needs[s]) or (state.slots[s] is not None) for s in range(S))
+    if dense:
+        # default path: similarity backward + normalisation backward + one-pass dense writer in ONE C call
+        idx = [s for s in range(S) if needs[s]]
+        sizes = [shapes[s][0] * shapes[s][1] * shapes[s][2] * shapes[s][3] for s in idx]
+        mask_words = sum((shapes[s][0] * shapes[s][2] * shapes[s][3] + 31) // 32 for s in idx)
+        slab = torch.empty(sum(sizes) + mask_words, dtype=torch.float32, device=dev)    # gradients | pixel mask
+        sbase = slab.data_ptr()
+        outs, off = {}, 0
+        if in_ws and len(idx) == S:         # the structures built with the workspace: only the addresses change
+            items, rows = e.bw_items, e.bw_rows
+            for j in range(S):
+                outs[j] = slab[off:off + sizes[j]].view(shapes[j])
+                items[j].dfeat = sbase + 4 * off
+                off += sizes[j]
+        else:
+            items = (_lib.ScatterItem * max(1, len(idx)))()
+            rows = (C.c_int32 * max(1, len(idx)))()
+            for j, s in enumerate(idx):
+                n, Cc, h, w = shapes[s]
+                outs[s] = slab[off:off + sizes[j]].view(shapes[s])
+                it = items[j]
+                it.dF, it.ldF, it.anc_f32, it.inv_norm = ptrs[s], sp.C_pad, fbase + 4 * sp.foff[s][0], fbase + 4 * sp.foff[s][1]
+                it.slot, it.n, it.C, it.plane = state.slots[s].data_ptr(), n, Cc, h * w
+                it.dfeat = sbase + 4 * off
+                rows[j] = state.samples[s].N
+                off += sizes[j]
+        evs, evp = None, None
+        if TIMING is not None:
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(3 if TIMING_ALL else 2)]
+            for ev in evs:
+                ev.record()         # creates the CUDA event; the chain records it again at its stage boundary
+            evp = _lib.ptr_array([ev.cuda_event for ev in evs] + [None] * (3 - len(evs)))
+        _lib.check(lib.mscs_backward_chain(C.byref(state.job), g.data_ptr(), ptrs_arr, lds, items, rows,
+                                           len(idx), sbase + 4 * sum(sizes), evp, st), "mscs_backward_chain")
+        _stream_cache(dev).flush()        # the deferred generator launch of the next call's stream
+        if evs is not None:
+            TIMING.setdefault("sim_bwd", []).append((evs[0], evs[1]))
+            if len(evs) == 3:
+                TIMING.setdefault("scatter", []).append((evs[1], evs[2]))
+        return [None if not needs[s] else (outs[s] if dtypes[s] == torch.float32 else outs[s].to(dtypes[s]))
+                for s in range(S)]
+    with _timed("sim_bwd"):
+        _lib.check(lib.mscs_sim_backward(C.byref(state.job), g.data_ptr(), ptrs_arr, lds, st),
+                   "mscs_sim_backward")
+    _stream_cache(dev).flush()            # the deferred generator launch of the next call's stream
     if sp.nhwc:
         with _timed("scatter"):
             gb = state.gradbufs
@@ -1403,32 +1521,6 @@ def run_backward(state, grad_out, needs, shapes, dtypes):
                 _lib.check(lib.mscs_scatter_rows_nhwc_batch(items, len(idx), st), "mscs_scatter_rows_nhwc_batch")
             return [None if not needs[s] else (outs[s] if dtypes[s] == torch.float32 else outs[s].to(dtypes[s]))
                     for s in range(S)]
-    dense = state.gradbufs is None and \
-        all((not needs[s]) or (state.slots[s] is not None) for s in range(S))
-    if dense:
-        with _timed("scatter"):
-            idx = [s for s in range(S) if needs[s]]
-            sizes = [shapes[s][0] * shapes[s][1] * shapes[s][2] * shapes[s][3] for s in idx]
-            mask_words = sum((shapes[s][0] * shapes[s][2] * shapes[s][3] + 31) // 32 for s in idx)
-            slab = torch.empty(sum(sizes) + mask_words, dtype=torch.float32, device=dev)    # gradients | pixel mask
-            items = (_lib.ScatterItem * len(idx))()
-            rows = (C.c_int32 * len(idx))()
-            outs, off = {}, 0
-            for j, s in enumerate(idx):
-                n, Cc, h, w = shapes[s]
-                outs[s] = slab[off:off + sizes[j]].view(shapes[s])
-                it = items[j]
-                it.dF, it.ldF, it.anc_f32, it.inv_norm = ptrs[s], sp.C_pad, fbase + 4 * sp.foff[s][0], fbase + 4 * sp.foff[s][1]
-                it.slot, it.n, it.C, it.plane = state.slots[s].data_ptr(), n, Cc, h * w
-                it.dfeat = slab.data_ptr() + 4 * off
-                rows[j] = state.samples[s].N
-                off += sizes[j]
-            if idx:
-                _lib.check(lib.mscs_scatter_dense_batch(items, rows, len(idx), slab.data_ptr() + 4 * sum(sizes), st),
-                           "mscs_scatter_dense_batch")
-            grads = [None if not needs[s] else (outs[s] if dtypes[s] == torch.float32 else outs[s].to(dtypes[s]))
-                     for s in range(S)]
-        return grads
     with _timed("scatter"):
         gb = state.gradbufs
         if gb is not None:

@@ -300,6 +300,46 @@ int mscs_scatter_dense_batch(const mscs_scatter_item* items, const int32_t* rows
                              void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * One forward / one backward of the single-process path in ONE call each (csrc/step.cu): the same entry points as
+ * above in the device-driven order, so that the host mirror crosses the ABI once per pass.  Replaces the host side
+ * of DenseContrastiveLossV2_ms.forward's scale loop (_ms.py:44-82) and of its autograd backward.
+ *
+ * forward:  on `sample_stream` (ordered after what `main_stream` holds): workspace fills, mscs_sample_plan[_i16],
+ *           mscs_plan_fetch_begin, mscs_sample_select_async;  on `main_stream` (ordered after the selection): the
+ *           batched gather + normalisation, mscs_sim_forward;  then mscs_plan_fetch_end -- the one host wait.
+ *           Returns like the parts (0 = ok; plan_host[s].error holds the reference's error conditions).
+ *           sample_stream == main_stream runs everything on one stream.
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+  const mscs_sample_cfg* cfg;
+  const void* labels;              /* int64 [n][H][W], or the int16 compact labels of mscs_label_pass (labels_i16 = 1) */
+  int32_t labels_i16;
+  int32_t v_cap;                   /* as mscs_sample_select_async */
+  void* workspace;                 /* mscs_sample_workspace_bytes */
+  mscs_scale_plan* plan_dev;       /* device plan records [num_scales] */
+  const uint32_t* draws;           /* MT19937 / Philox stream buffer of this call */
+  void* wait_event;                /* optional cudaEvent_t the sampling stream waits for (stream buffer complete) */
+  int32_t* const* idx_ref; int32_t* const* pair_ref; int32_t* const* pix; int32_t* const* cls; int32_t* const* seg;
+  int32_t* const* slot;            /* per scale, as mscs_sample_select_async */
+  void* const* fill_ptrs; const int32_t* fill_values; const size_t* fill_bytes; int32_t n_fill;   /* mscs_fill_bytes */
+  void* main_zero_ptr; size_t main_zero_bytes;   /* optional: cleared on main_stream while the sampling chain runs (the
+                                      gradient-row accumulators of the backward) */
+  int32_t gather_kind;             /* 0: NCHW (mscs_gather_item[num_scales], lane loads), 1: channels-last rows
+                                      (mscs_rows_item[num_scales]), 2: NCHW through bulk-tensor copies */
+  const void* gather_items;
+  const mscs_sim_job* job;         /* forward job (upper bounds + device-resident row counts) */
+  void* stage_events[5];           /* optional cudaEvent_t, recorded at: sampling start / end (sample stream), gather
+                                      start, gather end = similarity start, similarity end (main stream) */
+} mscs_forward_chain_args;
+int mscs_forward_chain(const mscs_forward_chain_args* args, void* sample_stream, void* main_stream,
+                       mscs_scale_plan* plan_host);
+/* backward: mscs_sim_backward, then mscs_scatter_dense_batch (count may be 0: no dense gradient wanted).
+ * stage_events: NULL or 3 optional cudaEvent_t recorded before / between / after the two. */
+int mscs_backward_chain(const mscs_sim_job* job, const float* grad_out, float* const* dF_sets, const int32_t* dF_ld,
+                        const mscs_scatter_item* items, const int32_t* rows, int count, uint32_t* mask_scratch,
+                        void* const* stage_events, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Co-loss on the same label read.  The reference's LossWrapper evaluates a class-weighted
  * nn.CrossEntropyLoss(ignore_index, weight) on the full-resolution logits next to the contrastive loss
  * (losses/LossWrapper.py:22-31,81-82; TwoScaleLoss.py:62-73 applies it to two logit maps); both start from the int64

@@ -41,7 +41,7 @@ def test_struct_layouts_match_compiler(tmp_path):
         pytest.skip("gcc not available")
     pairs = {"mscs_sample_cfg": _lib.SampleCfg, "mscs_scale_plan": _lib.ScalePlan, "mscs_gather_item": _lib.GatherItem,
              "mscs_scatter_item": _lib.ScatterItem, "mscs_rows_item": _lib.RowsItem, "mscs_term": _lib.Term,
-             "mscs_sim_job": _lib.SimJob}
+             "mscs_sim_job": _lib.SimJob, "mscs_forward_chain_args": _lib.ForwardChainArgs}
     header = open(os.path.join(ROOT, "include", "mscs.h")).read()
     assert set(re.findall(r"^}\s*(mscs_[a-z_]+);", header, re.M)) == set(pairs), "a header struct has no ctypes mirror"
     lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "mscs.h"', "int main(void) {"]
