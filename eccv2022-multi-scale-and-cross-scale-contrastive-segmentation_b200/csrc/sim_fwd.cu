@@ -498,9 +498,17 @@ int make_tensor_map(CUtensorMap* out, const void* base, int rows, int c_pad) {
   cuuint64_t strides[1] = {(cuuint64_t)c_pad * 2};
   cuuint32_t box[2] = {(cuuint32_t)kKBlk, 128};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = CUDA_SUCCESS;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    // A DRIVER-API call needs a context current to the calling thread.  The backward runs on autograd's device thread,
+    // and since the one-call backward (step.cu) nothing in front of it on that thread is a runtime call that would have
+    // bound the primary context: bind it (cudaFree(0)) and encode again.
+    if (r != CUDA_ERROR_INVALID_CONTEXT) break;
+    MSCS_CUDA(cudaFree(nullptr));
+  }
   MSCS_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return 0;
 }
@@ -521,9 +529,14 @@ int make_tensor_map_2d(CUtensorMap* out, int dtype, int elem_bytes, const void* 
   cuuint64_t strides[1] = {(cuuint64_t)row_pitch_bytes};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, (CUtensorMapDataType)dtype, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = CUDA_SUCCESS;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    r = fn(out, (CUtensorMapDataType)dtype, 2, const_cast<void*>(base), dims, strides, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_ERROR_INVALID_CONTEXT) break;      // see make_tensor_map
+    MSCS_CUDA(cudaFree(nullptr));
+  }
   MSCS_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (2d) failed with CUresult %d", (int)r);
   return 0;
 }

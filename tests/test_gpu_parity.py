@@ -819,3 +819,29 @@ def test_feature_plane_larger_than_downsampled_label(layout, dev):
         got = f.grad.cpu().numpy().astype(np.float64)
         assert np.array_equal(np.abs(got).sum(1) != 0, np.abs(want["grads"][s]).sum(1) != 0), "different pixels touched"
         assert cosine(got, want["grads"][s]) >= 0.999
+
+
+def test_first_backward_of_a_fresh_process():
+    """The backward is ONE C call that starts with a driver-API call (tensor-map encode) on autograd's device thread; in
+    a fresh process nothing has bound a CUDA context to that thread yet (found with tools/pooled_check.py, round 2)."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import torch, mscs_b200\n"
+        "from mscs_b200 import synth\n"
+        "dev = torch.device('cuda:0')\n"
+        "cfg = dict(dataset='CITYSCAPES', experiment=1, temperature=0.1, scales=2, weights=[1.0, 0.5],\n"
+        "           cross_scale_contrast=True, w_high_low=0.5, min_views_per_class=5, max_views_per_class=20,\n"
+        "           max_features_total=2000)\n"
+        "labels = synth.synth_labels(2, 64, 128, 19, 5, 8, 0.05, 3).to(dev)\n"
+        "feats = [f.to(dev).requires_grad_(True) for f in synth.synth_features(2, 32, 64, 128, [4, 8], 4)]\n"
+        "torch.manual_seed(0)\n"
+        "loss = mscs_b200.DenseContrastiveLossV2_ms(cfg)(labels, feats)\n"
+        "loss.backward()\n"
+        "torch.cuda.synchronize()\n"
+        "assert all(torch.isfinite(f.grad).all() and f.grad.abs().sum() > 0 for f in feats)\n"
+        "print('fresh-process backward ok', float(loss))\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "fresh-process backward ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
