@@ -43,14 +43,14 @@ def test_reference_arm_line():
 
 
 def test_committed_main_arm_line_has_the_contract_keys():
-    d = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_cfg2.json")))
+    d = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_cfg2.json")))
     assert BASE_KEYS | {"roofline", "clocks", "cpu_baseline"} <= set(d)
     assert d["dtype"] == "bf16" and d["data"] == "synthetic" and d["scaling"] == "weak" and d["n_gpus"] == 1
     rf = d["roofline"]
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(rf)
     assert rf["bound"] == "tensor" and rf["unit"] == "TFLOP/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
     # achieved = algorithmic FLOPs per launch / measured launch time (4*C per anchor pair backward)
-    pairs, C = d["config"]["anchor_pairs_per_step"], 256
+    pairs, C = d["detail"]["anchor_pairs_per_step"], 256       # (config is identical on both arms: run facts live in detail)
     assert rf["algorithmic_flops_per_launch"] == 4 * C * pairs
     assert abs(rf["achieved"] - 4 * C * pairs / (rf["launch_ms"] * 1e-3) / 1e12) < 1e-6 * rf["achieved"]
     assert abs(d["value"] - pairs / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]

@@ -149,7 +149,7 @@ def test_launch_count_claim_matches_committed_launch_list():
     """`gpu_launches` of the bench line is LAUNCHES_PER_STEP x steps: the per-step figure must equal the number of
     libmscs.so kernels between two `k_label_hist` launches of the committed ncu launch list (same command)."""
     import csv
-    for name in ("r01_launches_cfg2.csv",):     # the channels-last list predates the merged work-table launch (16 then)
+    for name in ("r02_launches_cfg2.csv",):
         rows = [r for r in csv.reader(open(os.path.join(ROOT, "profiles", name))) if r and r[0].isdigit()]
         names = [r[4] for r in rows]
         first = [i for i, n in enumerate(names) if "k_label_hist" in n]
