@@ -73,7 +73,6 @@ _SIGNATURES = {
     "mscs_last_error": (C.c_char_p, []),
     "mscs_device_ok": (C.c_int, []),
     "mscs_read_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
-    "mscs_copy_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mscs_fill_bytes": (C.c_int, [_PTRS, C.POINTER(C.c_int32), C.POINTER(C.c_size_t), C.c_int, C.c_void_p]),
     "mscs_debug_trap_info": (C.c_int, [C.c_char_p, C.c_int]),
     "mscs_debug_wait_profile_fwd": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -89,9 +89,3 @@ extern "C" int mscs_fill_bytes(void* const* ptrs, const int32_t* values, const s
   return 0;
 }
 
-// asynchronous device-to-device copy (pooled mode: private copy of the operand matrices of the exchange slab)
-extern "C" int mscs_copy_d2d(void* dst, const void* src, size_t bytes, void* stream_) {
-  MSCS_CHECK_ARG(dst && src, "null pointer argument");
-  if (bytes) MSCS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
-  return 0;
-}

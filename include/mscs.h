@@ -59,8 +59,6 @@ int mscs_device_ok(void);
 /* small device->host read on `stream`, ordered after `wait_event` (cudaEvent_t or NULL), synchronised before return */
 int mscs_read_to_host(void* dst_host, const void* src_dev, size_t bytes, void* wait_event, void* stream);
 int mscs_fill_bytes(void* const* ptrs, const int32_t* values, const size_t* bytes, int count, void* stream);
-/* asynchronous device-to-device copy on `stream` */
-int mscs_copy_d2d(void* dst, const void* src, size_t bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * K1 -- sampling.  Replaces get_dist_and_classes (DenseContrastiveLossV2.py:194-206),
