@@ -238,6 +238,8 @@ class _StreamCache:
         self.last_use = [None, None]   # event: last main-stream reader of each buffer
         self.lock = threading.Lock()
         self.pending = None      # deferred prefetch request (mt, pos, words), see release_and_prefetch
+        self.host = [None, None]       # pinned host mirrors of the raw streams (see state_after)
+        self.host_ready = None         # event: mirror of buffer `cur` complete
         self.copy = torch.cuda.Stream(device=dev)      # read-back of the generator state (see state_after)
 
     def _generate(self, which, mt, pos, words):
@@ -263,7 +265,17 @@ class _StreamCache:
             TIMING.setdefault("mt_stream_side", []).append((t0, t1))
         ev = torch.cuda.Event()
         ev.record(self.side)
-        self.cur, self.key, self.words, self.ready = which, (mt.tobytes(), pos), words, ev
+        # pinned host mirror of the raw stream, copied behind the generator on the side stream (2 MB at cfg-2): the
+        # forward reads the next generator state out of it (state_after) without a device round trip in the window
+        # between the plan fetch and the launch of the backward
+        hb = self.host[which]
+        if hb is None or hb.numel() < words:
+            hb = self.host[which] = torch.empty(words + 1024, dtype=torch.int32, pin_memory=True)
+        with torch.cuda.stream(self.side):
+            hb[:words].copy_(self.bufs[which][:words], non_blocking=True)
+        hev = torch.cuda.Event()
+        hev.record(self.side)
+        self.cur, self.key, self.words, self.ready, self.host_ready = which, (mt.tobytes(), pos), words, ev, hev
 
     def acquire(self, mt, pos, words):
         """Buffer holding >= words outputs from (mt,pos); the current stream is made to wait for it."""
@@ -299,10 +311,14 @@ class _StreamCache:
             buf = self.bufs[self.cur]
             if self.key != (mt.tobytes(), pos) or off + _MT_N > self.words:
                 return None
-            host = np.empty(_MT_N, dtype=np.uint32)
-            _lib.check(_lib.load().mscs_read_to_host(host.ctypes.data, buf.data_ptr() + 4 * off, 4 * _MT_N,
-                                                     C.c_void_p(self.ready.cuda_event), C.c_void_p(self.copy.cuda_stream)),
-                       "mscs_read_to_host")
+            if self.host_ready is not None and self.host[self.cur] is not None:
+                self.host_ready.synchronize()       # complete long ago (the mirror follows the generator kernel)
+                host = self.host[self.cur][off:off + _MT_N].numpy().view(np.uint32).copy()
+            else:
+                host = np.empty(_MT_N, dtype=np.uint32)
+                _lib.check(_lib.load().mscs_read_to_host(host.ctypes.data, buf.data_ptr() + 4 * off, 4 * _MT_N,
+                                                         C.c_void_p(self.ready.cuda_event),
+                                                         C.c_void_p(self.copy.cuda_stream)), "mscs_read_to_host")
         return host, newpos
 
     def release_and_prefetch(self, mt_next, pos_next, words, defer=False):
@@ -1084,6 +1100,19 @@ def _run_forward_fast(sp, labels, feats32, needs, philox=None):
     # no gradient is wanted at all)
     dF_in_ws = any(needs) and gradbufs is None
     ch.main_zero_bytes = 4 * sp.dF_n if dF_in_ws else 0
+    # the dense gradients of the backward (written in one pass, no fill): allocated HERE, before the host waits for the
+    # plan, with the addresses entered into the backward's prebuilt structures -- not in the window after the wait
+    grad_slab = grad_outs = None
+    if dF_in_ws and all(needs) and not sp.nhwc:
+        sizes = [f.numel() for f in feats32]
+        mask_words = sum((f.shape[0] * f.shape[2] * f.shape[3] + 31) // 32 for f in feats32)
+        grad_slab = torch.empty(sum(sizes) + mask_words, dtype=torch.float32, device=dev)    # gradients | pixel mask
+        sbase, off, grad_outs = grad_slab.data_ptr(), 0, []
+        for j in range(S):
+            grad_outs.append(grad_slab[off:off + sizes[j]].view(feats32[j].shape))
+            e.bw_items[j].dfeat = sbase + 4 * off
+            off += sizes[j]
+        grad_mask_ptr = sbase + 4 * off
     evs = None
     if TIMING is not None and TIMING_ALL:      # stage accounting (bench.py): five events recorded INSIDE the chain
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
@@ -1125,6 +1154,8 @@ def _run_forward_fast(sp, labels, feats32, needs, philox=None):
     state.term_loss, state.total, state.scalars = out[:nt], total_t, out
     state.num_ms, state.cs_logged, state.comm = S, sp.cs_logged, None
     state.dF_ws = e.dF_ptr if dF_in_ws else None
+    state.grad_slab, state.grad_outs = grad_slab, grad_outs
+    state.grad_mask_ptr = grad_mask_ptr if grad_slab is not None else None
     for s in range(S):
         e.bw_rows[s] = samples[s].N
     return state
@@ -1457,18 +1488,19 @@ def run_backward(state, grad_out, needs, shapes, dtypes):
     if dense:
         # default path: similarity backward + normalisation backward + one-pass dense writer in ONE C call
         idx = [s for s in range(S) if needs[s]]
-        sizes = [shapes[s][0] * shapes[s][1] * shapes[s][2] * shapes[s][3] for s in idx]
-        mask_words = sum((shapes[s][0] * shapes[s][2] * shapes[s][3] + 31) // 32 for s in idx)
-        slab = torch.empty(sum(sizes) + mask_words, dtype=torch.float32, device=dev)    # gradients | pixel mask
-        sbase = slab.data_ptr()
-        outs, off = {}, 0
-        if in_ws and len(idx) == S:         # the structures built with the workspace: only the addresses change
-            items, rows = e.bw_items, e.bw_rows
-            for j in range(S):
-                outs[j] = slab[off:off + sizes[j]].view(shapes[j])
-                items[j].dfeat = sbase + 4 * off
-                off += sizes[j]
+        pre = getattr(state, "grad_slab", None) if (in_ws and len(idx) == S) else None
+        if pre is not None:                 # allocated and entered into the prebuilt structures by the forward
+            state.grad_slab = None
+            slab, items, rows = pre, e.bw_items, e.bw_rows
+            outs, mask_ptr = dict(enumerate(state.grad_outs)), state.grad_mask_ptr
+            state.grad_outs = None
         else:
+            sizes = [shapes[s][0] * shapes[s][1] * shapes[s][2] * shapes[s][3] for s in idx]
+            mask_words = sum((shapes[s][0] * shapes[s][2] * shapes[s][3] + 31) // 32 for s in idx)
+            slab = torch.empty(sum(sizes) + mask_words, dtype=torch.float32, device=dev)    # gradients | pixel mask
+            sbase = slab.data_ptr()
+            mask_ptr = sbase + 4 * sum(sizes)
+            outs, off = {}, 0
             items = (_lib.ScatterItem * max(1, len(idx)))()
             rows = (C.c_int32 * max(1, len(idx)))()
             for j, s in enumerate(idx):
@@ -1487,7 +1519,7 @@ def run_backward(state, grad_out, needs, shapes, dtypes):
                 ev.record()         # creates the CUDA event; the chain records it again at its stage boundary
             evp = _lib.ptr_array([ev.cuda_event for ev in evs] + [None] * (3 - len(evs)))
         _lib.check(lib.mscs_backward_chain(C.byref(state.job), g.data_ptr(), ptrs_arr, lds, items, rows,
-                                           len(idx), sbase + 4 * sum(sizes), evp, st), "mscs_backward_chain")
+                                           len(idx), mask_ptr, evp, st), "mscs_backward_chain")
         _stream_cache(dev).flush()        # the deferred generator launch of the next call's stream
         if evs is not None:
             TIMING.setdefault("sim_bwd", []).append((evs[0], evs[1]))
