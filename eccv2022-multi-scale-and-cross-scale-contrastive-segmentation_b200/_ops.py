@@ -10,7 +10,7 @@ import os
 import struct
 import threading
 from dataclasses import dataclass, field
-from typing import List, Optional
+from typing import List
 
 import numpy as np
 import torch

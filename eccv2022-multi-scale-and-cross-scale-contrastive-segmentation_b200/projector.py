@@ -21,8 +21,6 @@ Same loss, same gradients w.r.t. z_s, W_s and b_s as the dense evaluation (tests
 ``nn.Conv2d`` + the reference's own loss class).  It is NOT a reference class name: the reference has no such module,
 so it sits next to the drop-in classes with its own, explicit interface.
 """
-import ctypes as C
-
 import torch
 import torch.nn as nn
 
